@@ -1,0 +1,152 @@
+/*
+ * shm3d_grid.h -- C ABI of the B200-native signed-heat grid solver (libshm3d_grid.so).
+ *
+ * This is the drop-in boundary for ONE hot path of nzfeng/signed-heat-3d:
+ * SignedHeatGridSolver::computeDistance (reference: include/signed_heat_grid_solver.h:16-20,
+ * src/signed_heat_grid_solver.cpp:5-222).  Everything behind these entry points runs as
+ * hand-written sm_100a CUDA; there is no CPU fallback -- calls fail with SHM3D_ERR_CUDA when
+ * no device is usable.
+ *
+ * What the reference's FFI for this path would bind (file:line = interface replaced):
+ *   shm3d_ctx_create / destroy      <- SignedHeatGridSolver() ctor + unique_ptr lifetime
+ *                                      (src/signed_heat_grid_solver.cpp:3, src/main.cpp:52,290)
+ *   shm3d_solve                     <- computeDistance(...), Steps 1-3 + shift
+ *                                      (src/signed_heat_grid_solver.cpp:38-113 and :146-221)
+ *   shm3d_step12 / shm3d_rhs        <- the Step 1-2 loop (:48-65, :157-174) and D^T Y (:70-74,:179-180);
+ *                                      exposed so parity tests can check intermediate fields
+ *   shm3d_last_error                <- the C++ exceptions geometry-central raises
+ *                                      (deps/geometry-central/src/numerical/square_solvers.cpp:123-125,164-169)
+ * Host-side work the caller (adapter) keeps: grid setup a4, lambda a5, face areas/normals/
+ * barycentres a6 -- see include/shm3d_host.hpp for the dependency-free
+ * C++ mirror and INTEGRATION.md for the geometry-central adapter.
+ *
+ * Layouts: all host arrays are caller-owned, plain row-major.  pos/nrm are [M][3] doubles,
+ * area is [M].  Source ORDER matters: it defines which source pins each grid cell
+ * (src/signed_heat_grid_solver.cpp:86-98 "first face per cell wins").
+ * phi_out is double[nx*ny*(k1-k0)], node index i + j*nx + (k-k0)*nx*ny  (x fastest,
+ * src/signed_heat_grid_solver.cpp:505-508); k0..k1 is the calling rank's z-slab
+ * (the whole grid when the context is single-GPU).
+ */
+#ifndef SHM3D_GRID_H
+#define SHM3D_GRID_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHM3D_OK 0
+#define SHM3D_ERR_INVALID_ARG 1
+#define SHM3D_ERR_CUDA 2            /* no device / CUDA runtime failure */
+#define SHM3D_ERR_NONFINITE 3       /* non-finite source data or rhs (reference: checkFinite throws) */
+#define SHM3D_ERR_FACTORIZATION 4   /* constraint system A A^T not positive definite */
+#define SHM3D_ERR_NO_CONVERGENCE 5  /* constrained PCG hit cg_max_iters */
+#define SHM3D_ERR_NCCL 6
+
+#define SHM3D_FLAG_FAST 1u             /* SignedHeat3DOptions.fastIntegration (include/signed_heat_3d.h:27) */
+#define SHM3D_FLAG_SCRUB_NONFINITE 2u  /* mesh overload zeroes non-finite rhs entries (:72-74); point overload does not */
+#define SHM3D_FLAG_VERBOSE 4u          /* SignedHeatGridSolver::VERBOSE */
+#define SHM3D_FLAG_NO_MG 8u            /* diagnostics: plain projected CG (no multigrid preconditioner) */
+
+typedef struct shm3d_ctx shm3d_ctx;
+
+typedef struct shm3d_params {
+    int32_t nx, ny, nz;   /* grid nodes per axis (reference: nx=ny=nz=16*2^hCoef, :24) */
+    double bbox_min[3];   /* position of node (0,0,0) (:17-18) */
+    double cell;          /* node spacing 2s/(nx-1) (:26) */
+    double lambda;        /* 1/sqrt(tCoef h^2) (:42-44) */
+    uint32_t flags;
+    double cull_tau;      /* far-field cut: drop sources with lambda*(r - r_min) > tau.  <=0: default 12.
+                             +inf: brute force (every source at every node, like the reference) */
+    double cg_rel_tol;    /* <=0: default 1e-6 (relative preconditioned residual) */
+    int32_t cg_max_iters; /* <=0: default 2000 */
+    int32_t mg_smooth;    /* Jacobi sweeps per multigrid leg; <=0: default 2 */
+} shm3d_params;
+
+typedef struct shm3d_stats {
+    double ms_total;        /* wall time of the call */
+    double ms_h2d;          /* source upload + clustering */
+    double ms_sum;          /* Steps 1-2 kernel(s) (device time) */
+    double ms_rhs;          /* D^T Y */
+    double ms_constraints;  /* constraint rows + A A^T nested-dissection factorisation (host) + upload */
+    double ms_pcg;          /* constrained multigrid-PCG (device time) */
+    double ms_shift;        /* source average + shift */
+    double ms_d2h;          /* phi download */
+    int64_t pairs_evaluated;  /* (node,source) pairs the summation kernel actually evaluated */
+    int64_t pairs_bruteforce; /* N*M */
+    int32_t n_clusters;
+    int32_t m_constraints;
+    int32_t cg_iters;
+    double cg_rel_residual;
+    double shift;
+    int64_t kernel_launches;  /* CUDA kernels launched by this call */
+    double ms_pcg_stencil;    /* device time inside the fused stencil-apply+dot kernel, summed */
+    int64_t pcg_stencil_launches;
+    double ms_pcg_vcycle;     /* device time inside multigrid V-cycles, summed */
+} shm3d_stats;
+
+/* Context: one per GPU.  device = CUDA ordinal.  Returns SHM3D_ERR_CUDA when no usable device. */
+int shm3d_ctx_create(shm3d_ctx** out, int device);
+/* One rank of a z-slab-partitioned solve over `world` GPUs (NCCL over NVLink).  nccl_id is the 128-byte
+ * ncclUniqueId from shm3d_nccl_unique_id() on rank 0, distributed by the caller (e.g. torch.distributed). */
+int shm3d_ctx_create_dist(shm3d_ctx** out, int device, int rank, int world, const void* nccl_id);
+int shm3d_nccl_unique_id(void* out128);
+void shm3d_ctx_destroy(shm3d_ctx* ctx);
+/* Message of the last failing call on this context (or of a failed create when ctx == NULL). */
+const char* shm3d_last_error(const shm3d_ctx* ctx);
+/* z-slab [k0,k1) this context owns for a grid of nz planes. */
+int shm3d_slab(const shm3d_ctx* ctx, int32_t nz, int32_t* k0, int32_t* k1);
+
+/* computeDistance: Steps 1-3 + shift.  phi_out: double[nx*ny*(k1-k0)]. stats may be NULL. */
+int shm3d_solve(shm3d_ctx* ctx, const shm3d_params* p, int64_t n_sources, const double* pos, const double* nrm,
+                const double* area, double* phi_out, shm3d_stats* stats);
+
+/* Same solve with the source arrays already resident on the device (device pointers, same layout) and phi
+ * left on the device as float[local N] (phi_dev).  Used to time the path without host<->device copies. */
+int shm3d_solve_device(shm3d_ctx* ctx, const shm3d_params* p, int64_t n_sources, const double* d_pos,
+                       const double* d_nrm, const double* d_area, float* phi_dev, shm3d_stats* stats);
+
+/* Steps 1-2 only: Y_out float[3][local N] (component-major: Yx, then Yy, then Yz). */
+int shm3d_step12(shm3d_ctx* ctx, const shm3d_params* p, int64_t n_sources, const double* pos, const double* nrm,
+                 const double* area, float* Y_out, shm3d_stats* stats);
+
+/* b = cell^2 * D^T Y for a given Y (component-major float[3][local N]) -> b_out float[local N]. */
+int shm3d_rhs(shm3d_ctx* ctx, const shm3d_params* p, const float* Y, float* b_out);
+
+/* Step 3 only, from a given right-hand side b (= cell^2 D^T Y, float[local N]): constrained solve + shift. */
+int shm3d_step3(shm3d_ctx* ctx, const shm3d_params* p, int64_t n_sources, const double* pos, const double* area,
+                const float* b, double* phi_out, shm3d_stats* stats);
+
+/* Host half of the reference interface (rows a4-a6 of SURVEY.md section 8a), dependency-free:
+ * fills `out` (grid, lambda, flags) and, when the three arrays are non-NULL, the per-face barycentre / unit
+ * normal / area arrays ([nF][3], [nF][3], [nF]) that shm3d_solve consumes.  Faces are polygons:
+ * face f uses vertices face_vertices[face_offsets[f] .. face_offsets[f+1]).
+ * Replaces centroid/radius (src/signed_heat_3d.cpp:3-22), the grid set-up (src/signed_heat_grid_solver.cpp:13-26),
+ * meanEdgeLength (src/signed_heat_3d.cpp:51-60), setFaceVectorAreas (:62-89), barycenter (grid_solver.cpp:498-503). */
+int shm3d_prepare_mesh(const double* V, int64_t nV, const int64_t* face_vertices, const int64_t* face_offsets,
+                       int64_t nF, double tCoef, double hCoef, double scale, shm3d_params* out, double* pos_out,
+                       double* nrm_out, double* area_out, double* h_out);
+/* Point-cloud overload set-up (src/signed_heat_grid_solver.cpp:124-137, :151-153): h is the mean edge length of
+ * the caller's tufted triangulation; the per-point areas are passed to shm3d_solve as `area`. */
+int shm3d_prepare_points(const double* P, int64_t nP, double h, double tCoef, double hCoef, double scale,
+                         shm3d_params* out);
+
+/* Host-logic probes for the CPU test-suite (no device code runs; not part of the product path):
+ * constraint rows (src/signed_heat_grid_solver.cpp:80-100, :433-464) and the nested-dissection factor of
+ * A D^-1 A^T applied on the host with the same block layout the GPU kernels consume. */
+int shm3d_debug_constraints(const shm3d_params* p, int64_t n_sources, const double* pos, int32_t* m_out,
+                            int64_t* node_out /*[m*8]*/, double* w_out /*[m*8]*/, int64_t* src_out /*[m]*/,
+                            int64_t capacity_rows);
+int shm3d_debug_factor_solve(const shm3d_params* p, int64_t n_sources, const double* pos, int32_t uniform,
+                             double* v /*[m] in/out*/, int32_t m_expected, double* factor_megabytes,
+                             int32_t* tree_height);
+
+/* Library / build identification ("shm3d-b200 <version> sm_100a"). */
+const char* shm3d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHM3D_GRID_H */

@@ -1,0 +1,478 @@
+"""
+oracle/shm_oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU fp64 restatement ("port") of the reference's grid-solver hot path
+(SignedHeatGridSolver::computeDistance).  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module.  The product
+path (signed-heat-3d_b200/) never does and fails loudly without its CUDA library.
+
+PARITY STATUS: UNPINNED by the reference's own tests -- the reference has no tests or
+golden vectors for this path and cannot be compiled here (Eigen 3.3.8 is fetched at
+configure time).  The restatement follows the reference source
+line by line (citations below, relative to /root/reference) and Step 3 is solved two
+ways -- a direct sparse LU of the reference's KKT matrix (scipy SuperLU, the lineage of
+Eigen::SparseLU that geometry-central's solveSquare uses) and an fp64 projected CG --
+which must agree (tests/test_oracle.py).
+
+Nothing here reads /root/reference at run time except the helper readers when a test
+explicitly passes such a path (CPU-only fixture generation, tests/golden/make_golden.py).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+# --------------------------------------------------------------------------------------
+# C helper (Steps 1-2 O(N*M) loop) -- built by oracle/Makefile or on first use
+# --------------------------------------------------------------------------------------
+def build_clib(force: bool = False) -> str:
+    out = os.path.join(_HERE, "_build", "libshm_oracle.so")
+    src = os.path.join(_HERE, "csrc", "shm_oracle.c")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        # same optimisation flags as the reference's Release build (CMakeLists.txt:46)
+        cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"]
+        subprocess.check_call(cmd)
+    return out
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build_clib())
+        dp = ctypes.POINTER(ctypes.c_double)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        _LIB.oracle_step12.argtypes = [ctypes.c_int] * 5 + [dp, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                                                            dp, dp, dp, dp, ctypes.c_int]
+        _LIB.oracle_step12_aswritten.argtypes = [ctypes.c_int] * 5 + [dp, ctypes.c_double, ctypes.c_double,
+                                                                      ctypes.c_int64, dp, ip, dp, dp, dp, ctypes.c_int]
+        _LIB.oracle_apply_K.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double, dp, dp, ctypes.c_int]
+        _LIB.oracle_max_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def max_threads() -> int:
+    return int(_lib().oracle_max_threads())
+
+
+# --------------------------------------------------------------------------------------
+# Input readers (restating the reference's loaders)
+# --------------------------------------------------------------------------------------
+def read_obj(path):
+    """OBJ reader following deps/geometry-central/src/surface/simple_polygon_mesh.cpp:167-232
+    (v / f tokens, index before the first '/', 1-based) and meshio.cpp:22-29
+    (stripUnusedVertices; OBJ vertices at identical positions are NOT merged).
+    Returns (V float64[nV,3], faces list[list[int]])."""
+    verts, faces = [], []
+    with open(path, "rb") as fh:
+        for raw in fh:
+            line = raw.decode("ascii", "replace").split()
+            if not line:
+                continue
+            if line[0] == "v":
+                verts.append([float(line[1]), float(line[2]), float(line[3])])
+            elif line[0] == "f":
+                faces.append([int(tok.split("/")[0]) - 1 for tok in line[1:]])
+    V = np.asarray(verts, dtype=np.float64)
+    used = np.zeros(len(V), dtype=bool)
+    for f in faces:
+        used[f] = True
+    remap = np.cumsum(used) - 1
+    V = V[used]
+    faces = [[int(remap[i]) for i in f] for f in faces]
+    return V, faces
+
+
+def read_pc(path):
+    """.pc reader following src/main.cpp:196-225 ('v x y z' / 'vn x y z' lines)."""
+    P, Nn = [], []
+    with open(path, "r") as fh:
+        for line in fh:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "v":
+                P.append([float(t[1]), float(t[2]), float(t[3])])
+            elif t[0] == "vn":
+                Nn.append([float(t[1]), float(t[2]), float(t[3])])
+    return np.asarray(P, dtype=np.float64), np.asarray(Nn, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------
+# Source quantities
+# --------------------------------------------------------------------------------------
+def mesh_sources(V, faces):
+    """Per-face area / unit normal / barycentre and the mesh scalars the grid solver uses.
+
+    setFaceVectorAreas (src/signed_heat_3d.cpp:62-89: shoelace vector area, always taken
+    because the triangular fast path has no return), barycenter
+    (src/signed_heat_grid_solver.cpp:498-503), meanEdgeLength (src/signed_heat_3d.cpp:51-60;
+    edges = unique unordered vertex pairs, surface_mesh.cpp:145,162-166), centroid / radius
+    (src/signed_heat_3d.cpp:3-22)."""
+    V = np.asarray(V, dtype=np.float64)
+    tri = all(len(f) == 3 for f in faces)
+    M = len(faces)
+    if tri:
+        F = np.asarray(faces, dtype=np.int64).reshape(M, 3)
+        p = V[F]  # M,3,3
+        Nvec = 0.5 * (np.cross(p[:, 0], p[:, 1]) + np.cross(p[:, 1], p[:, 2]) + np.cross(p[:, 2], p[:, 0]))
+        bary = (p[:, 0] + p[:, 1] + p[:, 2]) / 3.0
+        e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]])
+    else:
+        Nvec = np.zeros((M, 3))
+        bary = np.zeros((M, 3))
+        es = []
+        for fi, f in enumerate(faces):
+            pf = V[f]
+            n = np.zeros(3)
+            for a in range(len(f)):
+                n += np.cross(pf[a], pf[(a + 1) % len(f)])
+                es.append((f[a], f[(a + 1) % len(f)]))
+            Nvec[fi] = 0.5 * n
+            c = np.zeros(3)
+            for a in range(len(f)):
+                c += pf[a]
+            bary[fi] = c / len(f)
+        e = np.asarray(es, dtype=np.int64)
+    area = np.linalg.norm(Nvec, axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        nrm = Nvec / area[:, None]
+    e = np.sort(e, axis=1)
+    e = np.unique(e, axis=0)
+    h = np.linalg.norm(V[e[:, 0]] - V[e[:, 1]], axis=1).sum() / len(e)
+    c = V.sum(axis=0) / len(V)
+    r = np.sqrt(((V - c) ** 2).sum(axis=1)).max()
+    return dict(pos=np.ascontiguousarray(bary), nrm=np.ascontiguousarray(nrm), area=np.ascontiguousarray(area),
+                h=float(h), centroid=c, radius=float(r))
+
+
+@dataclass
+class Grid:
+    nx: int
+    ny: int
+    nz: int
+    bmin: np.ndarray
+    cell: float
+
+    @property
+    def N(self):
+        return self.nx * self.ny * self.nz
+
+
+def make_grid(centroid, radius, hCoef=0.0, scale=2.0) -> Grid:
+    """src/signed_heat_grid_solver.cpp:13-26: cube c +- scale*r, nx = (size_t)(2*2^(hCoef+3)),
+    cell = 2s/(nx-1)."""
+    s = radius * scale
+    nx = int(2 * 2.0 ** (hCoef + 3))
+    cell = 2.0 * s / (nx - 1)
+    return Grid(nx, nx, nx, np.asarray(centroid, dtype=np.float64) - s, float(cell))
+
+
+def lambda_from_h(h, tCoef=1.0):
+    """src/signed_heat_grid_solver.cpp:42-44: shortTime = tCoef h^2, lambda = sqrt(1/shortTime)."""
+    return float(np.sqrt(1.0 / (tCoef * h * h)))
+
+
+# --------------------------------------------------------------------------------------
+# Steps 1-2
+# --------------------------------------------------------------------------------------
+def step12(g: Grid, lam, pos, nrm, area, threads=None, k0=0, k1=None):
+    """Y[3N] interleaved (src/signed_heat_grid_solver.cpp:48-65).  C loop, fp64."""
+    if k1 is None:
+        k1 = g.nz
+    if threads is None:
+        threads = max_threads()
+    Y = np.zeros(3 * g.N, dtype=np.float64)
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    nrm = np.ascontiguousarray(nrm, dtype=np.float64)
+    area = np.ascontiguousarray(area, dtype=np.float64)
+    bmin = np.ascontiguousarray(g.bmin, dtype=np.float64)
+    _lib().oracle_step12(g.nx, g.ny, g.nz, k0, k1, _dp(bmin), g.cell, lam, len(area), _dp(pos), _dp(nrm), _dp(area),
+                         _dp(Y), int(threads))
+    return Y
+
+
+def step12_aswritten(g: Grid, lam, V, F, nrm, area, threads=1, k0=0, k1=None):
+    if k1 is None:
+        k1 = g.nz
+    Y = np.zeros(3 * g.N, dtype=np.float64)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    F = np.ascontiguousarray(F, dtype=np.int32)
+    nrm = np.ascontiguousarray(nrm, dtype=np.float64)
+    area = np.ascontiguousarray(area, dtype=np.float64)
+    bmin = np.ascontiguousarray(g.bmin, dtype=np.float64)
+    _lib().oracle_step12_aswritten(g.nx, g.ny, g.nz, k0, k1, _dp(bmin), g.cell, lam, len(area), _dp(V),
+                                   F.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _dp(nrm), _dp(area), _dp(Y),
+                                   int(threads))
+    return Y
+
+
+# --------------------------------------------------------------------------------------
+# Step 3 operators
+# --------------------------------------------------------------------------------------
+def gradient_matrix(g: Grid):
+    """D (3N x N), src/signed_heat_grid_solver.cpp:336-402: forward differences, backward at
+    the far face, all / cell.  Built as a scipy CSR exactly like the triplet list."""
+    import scipy.sparse as sp
+    nx, ny, nz = g.nx, g.ny, g.nz
+    N = g.N
+    idx = np.arange(N).reshape(nz, ny, nx)
+    rows, cols, vals = [], [], []
+    strides = (1, nx, nx * ny)
+    dims = (nx, ny, nz)
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cur = (I + J * nx + K * nx * ny).ravel()
+    coords = (I.ravel(), J.ravel(), K.ravel())
+    for a in range(3):
+        far = coords[a] == dims[a] - 1
+        nxt = np.where(far, cur, cur + strides[a])
+        c = np.where(far, cur - strides[a], cur)
+        rows += [3 * cur + a, 3 * cur + a]
+        cols += [nxt, c]
+        vals += [np.ones(N), -np.ones(N)]
+    D = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(3 * N, N)).tocsr()
+    del idx
+    return D / g.cell
+
+
+def laplacian_matrix(g: Grid):
+    """L (N x N), src/signed_heat_grid_solver.cpp:278-334: 7-point, out-of-range neighbours
+    redirected to the node itself (so the diagonal is -(#in-range neighbours)), / cell^2."""
+    import scipy.sparse as sp
+    nx, ny, nz = g.nx, g.ny, g.nz
+    N = g.N
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cur = (I + J * nx + K * nx * ny).ravel()
+    coords = (I.ravel(), J.ravel(), K.ravel())
+    strides = (1, nx, nx * ny)
+    dims = (nx, ny, nz)
+    rows, cols, vals = [cur], [cur], [-6.0 * np.ones(N)]
+    for a in range(3):
+        nxt = np.where(coords[a] == dims[a] - 1, cur, cur + strides[a])
+        prv = np.where(coords[a] == 0, cur, cur - strides[a])
+        rows += [cur, cur]
+        cols += [nxt, prv]
+        vals += [np.ones(N), np.ones(N)]
+    L = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N)).tocsr()
+    return L / (g.cell * g.cell)
+
+
+def div_rhs(g: Grid, Y, scrub_nonfinite=True):
+    """b = D^T Y (src/signed_heat_grid_solver.cpp:70-74) in stencil form:
+    per axis with gl = Y_a/cell along a line of n nodes:
+      b[0] = -gl[0]; b[t] = gl[t-1]-gl[t] (1<=t<=n-3); b[n-2] = gl[n-3]-gl[n-2]-gl[n-1];
+      b[n-1] = gl[n-2]+gl[n-1].
+    Mesh overload zeroes non-finite entries (:72-74); point overload does not (:180)."""
+    nx, ny, nz = g.nx, g.ny, g.nz
+    Y3 = np.asarray(Y, dtype=np.float64).reshape(nz, ny, nx, 3)
+    b = np.zeros((nz, ny, nx))
+    for a, ax in ((0, 2), (1, 1), (2, 0)):
+        gl = np.moveaxis(Y3[..., a], ax, 0) / g.cell
+        n = gl.shape[0]
+        ba = np.zeros_like(gl)
+        ba[0] = -gl[0]
+        ba[1:n - 1] = gl[0:n - 2] - gl[1:n - 1]
+        ba[n - 2] -= gl[n - 1]
+        ba[n - 1] = gl[n - 2] + gl[n - 1]
+        b += np.moveaxis(ba, 0, ax)
+    b = b.ravel()
+    if scrub_nonfinite:
+        b[~np.isfinite(b)] = 0.0
+    return b
+
+
+def apply_K(g: Grid, u, threads=None):
+    """K u = -L u (matrix-free), C loop."""
+    if threads is None:
+        threads = max_threads()
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty_like(u)
+    _lib().oracle_apply_K(g.nx, g.ny, g.nz, g.cell, _dp(u), _dp(out), int(threads))
+    return out
+
+
+def trilinear(g: Grid, q):
+    """Cell indices, the 8 node indices {000,100,010,001,110,101,011,111} and weights for
+    points q[n,3] (src/signed_heat_grid_solver.cpp:433-464)."""
+    q = np.atleast_2d(np.asarray(q, dtype=np.float64))
+    d = q - g.bmin
+    ijk = np.floor(d / g.cell).astype(np.int64)
+    p000 = g.bmin + ijk * g.cell
+    t = (q - p000) / g.cell
+    tx, ty, tz = t[:, 0], t[:, 1], t[:, 2]
+    i, j, k = ijk[:, 0], ijk[:, 1], ijk[:, 2]
+    nx, ny = g.nx, g.ny
+
+    def nid(a, b, c):
+        return (i + a) + (j + b) * nx + (k + c) * nx * ny
+
+    idx = np.stack([nid(0, 0, 0), nid(1, 0, 0), nid(0, 1, 0), nid(0, 0, 1), nid(1, 1, 0), nid(1, 0, 1), nid(0, 1, 1),
+                    nid(1, 1, 1)], axis=1)
+    w = np.stack([(1 - tx) * (1 - ty) * (1 - tz), tx * (1 - ty) * (1 - tz), (1 - tx) * ty * (1 - tz),
+                  (1 - tx) * (1 - ty) * tz, tx * ty * (1 - tz), tx * (1 - ty) * tz, (1 - tx) * ty * tz, tx * ty * tz],
+                 axis=1)
+    cell_id = i + j * nx + k * nx * ny
+    return cell_id, idx, w
+
+
+def constraints(g: Grid, pos):
+    """Constraint rows (src/signed_heat_grid_solver.cpp:80-100): sources in input order, first
+    source per grid cell wins.  Returns (src_index[m], node_idx[m,8], w[m,8])."""
+    cell_id, idx, w = trilinear(g, pos)
+    _, first = np.unique(cell_id, return_index=True)
+    first = np.sort(first)  # row order = order of first occurrence
+    return first, idx[first], w[first]
+
+
+def constraint_matrix(g: Grid, idx, w):
+    import scipy.sparse as sp
+    m = idx.shape[0]
+    rows = np.repeat(np.arange(m), 8)
+    return sp.coo_matrix((w.ravel(), (rows, idx.ravel())), shape=(m, g.N)).tocsr()
+
+
+def evaluate_function(g: Grid, u, q):
+    """Trilinear interpolation (src/signed_heat_grid_solver.cpp:405-431)."""
+    _, idx, w = trilinear(g, q)
+    # the reference evaluates the nested-lerp form; algebraically identical to sum w_i u_i
+    return (w * u[idx]).sum(axis=1)
+
+
+def source_average(g: Grid, u, pos, area):
+    """evaluateAverageAlongSourceGeometry (src/signed_heat_grid_solver.cpp:466-496)."""
+    return float((area * evaluate_function(g, u, pos)).sum() / area.sum())
+
+
+# --------------------------------------------------------------------------------------
+# Step 3 solvers
+# --------------------------------------------------------------------------------------
+def solve_kkt_lu(g: Grid, b, idx, w):
+    """The reference's Step 3 verbatim (src/signed_heat_grid_solver.cpp:101-108):
+    [[L, A^T],[A, 0]] [x; mu] = [b; 0], phi = -x, by direct sparse LU."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    L = laplacian_matrix(g)
+    A = constraint_matrix(g, idx, w)
+    m = A.shape[0]
+    LHS = sp.bmat([[L, A.T], [A, None if m == 0 else sp.csr_matrix((m, m))]], format="csc") if m > 0 else L.tocsc()
+    rhs = np.concatenate([b, np.zeros(m)])
+    sol = spla.splu(LHS).solve(rhs)
+    return -sol[:g.N]
+
+
+class Projector:
+    """P = I - A^T (A A^T)^-1 A with a direct sparse factorisation of A A^T (fp64)."""
+
+    def __init__(self, g: Grid, idx, w):
+        import scipy.sparse.linalg as spla
+        self.A = constraint_matrix(g, idx, w)
+        self.m = self.A.shape[0]
+        if self.m > 0:
+            self.fac = spla.splu((self.A @ self.A.T).tocsc())
+
+    def __call__(self, v):
+        if self.m == 0:
+            return v
+        return v - self.A.T @ self.fac.solve(self.A @ v)
+
+
+def solve_projected_cg(g: Grid, b, idx, w, tol=1e-12, maxit=20000, precond=None, callback=None):
+    """min 1/2 phi^T K phi - b^T phi  s.t.  A phi = 0 -- the same system as solve_kkt_lu
+     -- by CG on the null space of A (projected CG), fp64.
+    precond: optional callable z = M^-1 r (symmetric PSD)."""
+    P = Projector(g, idx, w)
+    x = np.zeros(g.N)
+    r = P(np.asarray(b, dtype=np.float64))
+    z = P(precond(r)) if precond else r
+    p = z.copy()
+    rho = float(r @ z)
+    rho0 = rho
+    its = 0
+    while its < maxit and rho > tol * tol * rho0 and rho > 0:
+        q = apply_K(g, p)
+        alpha = rho / float(p @ q)
+        x += alpha * p
+        r -= alpha * P(q)
+        z = P(precond(r)) if precond else r
+        rho_new = float(r @ z)
+        p = z + (rho_new / rho) * p
+        rho = rho_new
+        its += 1
+        if callback:
+            callback(its, x, rho / rho0)
+    return x, its
+
+
+def integrate_greedily(g: Grid, Y):
+    """--fast path (src/signed_heat_grid_solver.cpp:224-275): FIFO BFS from node (0,0,0),
+    neighbour order -x,+x,-y,+y,-z,+z; phi[q] = phi[p] + normalize(Y_p+Y_q).(q-p)."""
+    from collections import deque
+    nx, ny, nz = g.nx, g.ny, g.nz
+    Y3 = np.asarray(Y).reshape(-1, 3)
+    phi = np.zeros(g.N)
+    visited = np.zeros(g.N, dtype=bool)
+    dq = deque([(0, 0, 0)])
+    visited[0] = True
+    dims = (nx, ny, nz)
+    strides = (1, nx, nx * ny)
+    while dq:
+        cur = dq.popleft()
+        ci = cur[0] + cur[1] * nx + cur[2] * nx * ny
+        Yp = Y3[ci]
+        for a in range(3):
+            for sgn in (-1, 1):
+                if (sgn < 0 and cur[a] > 0) or (sgn > 0 and cur[a] < dims[a] - 1):
+                    ni = ci + sgn * strides[a]
+                    if not visited[ni]:
+                        Ya = Yp + Y3[ni]
+                        Ya = Ya / np.linalg.norm(Ya)
+                        phi[ni] = phi[ci] + Ya[a] * sgn * g.cell
+                        visited[ni] = True
+                        nxt = list(cur)
+                        nxt[a] += sgn
+                        dq.append(tuple(nxt))
+    return phi
+
+
+# --------------------------------------------------------------------------------------
+# End-to-end restatement of computeDistance
+# --------------------------------------------------------------------------------------
+def compute_distance(pos, nrm, area, h, centroid, radius, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False,
+                     scrub_nonfinite=True, step3="lu", tol=1e-12, threads=None, return_all=False):
+    """computeDistance (src/signed_heat_grid_solver.cpp:5-114 mesh / :116-222 points) on flat
+    source arrays.  step3: 'lu' (the reference's KKT sparse LU) or 'pcg' (fp64 projected CG)."""
+    g = make_grid(centroid, radius, hCoef, scale)
+    lam = lambda_from_h(h, tCoef)
+    Y = step12(g, lam, pos, nrm, area, threads=threads)
+    b = div_rhs(g, Y, scrub_nonfinite=scrub_nonfinite)
+    its = 0
+    if fast:
+        phi = integrate_greedily(g, Y)
+        src, idx, w = None, None, None
+    else:
+        src, idx, w = constraints(g, pos)
+        if step3 == "lu":
+            phi = solve_kkt_lu(g, b, idx, w)
+        else:
+            phi, its = solve_projected_cg(g, b, idx, w, tol=tol)
+    phi = phi - source_average(g, phi, pos, area)
+    if return_all:
+        return dict(phi=phi, Y=Y, b=b, grid=g, lam=lam, m=0 if idx is None else len(idx), its=its)
+    return phi
+
+
+def compute_distance_mesh(V, faces, **kw):
+    s = mesh_sources(V, faces)
+    return compute_distance(s["pos"], s["nrm"], s["area"], s["h"], s["centroid"], s["radius"], **kw)

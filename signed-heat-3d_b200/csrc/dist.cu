@@ -1,0 +1,147 @@
+// dist.cu -- NCCL plumbing for the slab-partitioned solve (see dist.cuh).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <mutex>
+
+#include "dist.cuh"
+
+namespace shm3d {
+
+namespace {
+
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+
+NcclApi& api() {
+    static NcclApi a;
+    static std::once_flag once;
+    std::call_once(once, [&] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so",
+                               "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2"};
+        for (const char* n : names) {
+            a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (a.h) break;
+        }
+        if (!a.h) {
+            a.err = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return;
+        }
+#define BIND(field, sym)                                        \
+    a.field = (decltype(a.field))dlsym(a.h, sym);               \
+    if (!a.field) a.err = std::string("missing NCCL symbol ") + sym;
+        BIND(GetUniqueId, "ncclGetUniqueId")
+        BIND(CommInitRank, "ncclCommInitRank")
+        BIND(CommDestroy, "ncclCommDestroy")
+        BIND(AllReduce, "ncclAllReduce")
+        BIND(Send, "ncclSend")
+        BIND(Recv, "ncclRecv")
+        BIND(GroupStart, "ncclGroupStart")
+        BIND(GroupEnd, "ncclGroupEnd")
+        BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+    });
+    return a;
+}
+
+#define NCCL_CHECK(expr)                                                                                  \
+    do {                                                                                                  \
+        ncclResult_t _r = (expr);                                                                         \
+        if (_r != ncclSuccess)                                                                            \
+            throw Error(SHM3D_ERR_NCCL, std::string(#expr) + ": " + api().GetErrorString(_r));            \
+    } while (0)
+
+}  // namespace
+
+int Dist::unique_id(void* out128) {
+    if (!out128) return SHM3D_ERR_INVALID_ARG;
+    NcclApi& a = api();
+    if (!a.err.empty() || !a.h) return SHM3D_ERR_NCCL;
+    ncclUniqueId id;
+    if (a.GetUniqueId(&id) != ncclSuccess) return SHM3D_ERR_NCCL;
+    memcpy(out128, &id, sizeof(id));
+    return SHM3D_OK;
+}
+
+Dist::Dist(int rank, int world, const void* nccl_id, cudaStream_t s) : rank_(rank), world_(world), stream_(s) {
+    NcclApi& a = api();
+    if (!a.h || !a.err.empty()) throw Error(SHM3D_ERR_NCCL, a.err.empty() ? "NCCL unavailable" : a.err);
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof(id));
+    ncclComm_t comm;
+    NCCL_CHECK(a.CommInitRank(&comm, world, id, rank));
+    comm_ = comm;
+    SHM3D_CUDA_CHECK(cudaMalloc((void**)&d_tmp_, sizeof(unsigned int)));
+}
+
+Dist::~Dist() {
+    if (comm_) api().CommDestroy((ncclComm_t)comm_);
+    cudaFree(d_tmp_);
+}
+
+void Dist::exchange_halo(float* v, const LevelDims& L, cudaStream_t s) {
+    NcclApi& a = api();
+    ncclComm_t comm = (ncclComm_t)comm_;
+    const size_t pl = L.plane();
+    const size_t n = L.n();
+    // slab neighbours are rank+-1 whenever that rank owns planes of this level
+    NCCL_CHECK(a.GroupStart());
+    if (L.k0 > 0) {  // lower neighbour exists
+        NCCL_CHECK(a.Send(v, pl, ncclFloat32, rank_ - 1, comm, s));
+        NCCL_CHECK(a.Recv(v - pl, pl, ncclFloat32, rank_ - 1, comm, s));
+    }
+    if (L.k1 < L.nz) {
+        NCCL_CHECK(a.Send(v + n - pl, pl, ncclFloat32, rank_ + 1, comm, s));
+        NCCL_CHECK(a.Recv(v + n, pl, ncclFloat32, rank_ + 1, comm, s));
+    }
+    NCCL_CHECK(a.GroupEnd());
+}
+
+void Dist::exchange_halo3(float* v, size_t cs, const LevelDims& L, cudaStream_t s) {
+    NcclApi& a = api();
+    ncclComm_t comm = (ncclComm_t)comm_;
+    const size_t pl = L.plane();
+    const size_t n = L.n();
+    NCCL_CHECK(a.GroupStart());
+    for (int c = 0; c < 3; c++) {
+        float* p = v + (size_t)c * cs;
+        if (L.k0 > 0) {
+            NCCL_CHECK(a.Send(p, pl, ncclFloat32, rank_ - 1, comm, s));
+            NCCL_CHECK(a.Recv(p - pl, pl, ncclFloat32, rank_ - 1, comm, s));
+        }
+        if (L.k1 < L.nz) {
+            NCCL_CHECK(a.Send(p + n - pl, pl, ncclFloat32, rank_ + 1, comm, s));
+            NCCL_CHECK(a.Recv(p + n, pl, ncclFloat32, rank_ + 1, comm, s));
+        }
+    }
+    NCCL_CHECK(a.GroupEnd());
+}
+
+void Dist::allreduce(double* dev, int n, cudaStream_t s) {
+    NCCL_CHECK(api().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)comm_, s));
+}
+
+unsigned int Dist::allreduce_max_host(unsigned int v) {
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(d_tmp_, &v, sizeof(v), cudaMemcpyHostToDevice, stream_));
+    NCCL_CHECK(api().AllReduce(d_tmp_, d_tmp_, 1, ncclUint32, ncclMax, (ncclComm_t)comm_, stream_));
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(&v, d_tmp_, sizeof(v), cudaMemcpyDeviceToHost, stream_));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return v;
+}
+
+void Dist::attach(Projector& P) {
+    P.reduce_hook_ = [this](double* rhs, int m, cudaStream_t s) { this->allreduce(rhs, m, s); };
+}
+
+}  // namespace shm3d

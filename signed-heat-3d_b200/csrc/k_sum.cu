@@ -1,0 +1,282 @@
+// k_sum.cu -- Steps 1-2 of the signed heat method on the grid: heat-kernel (Yukawa) summation of the source
+// normals at every node, then per-node normalisation.
+//
+// Replaces the O(N*M) double loop of the reference, src/signed_heat_grid_solver.cpp:48-65 (mesh) and
+// :157-174 (points), with yukawaPotential = exp(-lambda r)/r from src/signed_heat_3d.cpp:45-49:
+//     X(x) = sum_s n_s A_s exp(-lambda |x - y_s|) / |x - y_s|,   Y = X / |X|.
+//
+// B200 design (compute/SFU-bound; no tensor cores -- this is not a contraction):
+//  * one CTA per 8x8x8 tile of nodes, one warp per 4x4x4 brick, two nodes per lane (same x,y; z and z+2);
+//  * sources arrive Morton-clustered (<=32 per cluster, sources.cu).  A tile first filters ALL clusters with a
+//    conservative sphere/box test into a shared-memory candidate list (ordered compaction -> deterministic
+//    summation order), then each warp filters the candidates again for its own brick and evaluates the kept
+//    clusters: the cluster's sources are staged into a per-warp shared-memory buffer by one coalesced float4
+//    load per lane and read back as LDS.128 broadcasts in the pair loop;
+//  * far-field culling: a cluster is dropped for a brick when lambda*(r_lo - r_min_hi) > tau, where r_lo is a
+//    lower bound of the distance from any brick node to any source of the cluster and r_min_hi an upper
+//    bound on the distance from any brick node to its nearest source (exact nearest-source distance at the
+//    brick centre + brick half-diagonal).  Dropped terms are < e^-tau relative to the leading term of that
+//    node; the normalisation in Step 2 makes only relative size matter;
+//  * range: exp(-lambda r) underflows fp32 for lambda*r > 87.  Every node keeps a running
+//    reference distance m <= every r it has seen (a lower bound from the cluster spheres) and accumulates
+//    sum w exp(-lambda (r - m)); when m decreases the accumulator is rescaled.  Arguments of ex2 are <= 0
+//    and the nearest source's term is >= e^{-2 lambda rad_cluster} (>= e^-8 by construction);
+//  * per pair: 2 MUFU (rsqrt, ex2) + ~10 FP32 instructions -> MUFU-bound at 16/clk/SM.
+#include "kernels.cuh"
+
+namespace shm3d {
+
+namespace {
+
+constexpr int kTile = 8;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kListCap = 2048;
+
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float dist3(float ax, float ay, float az, const float4& b) {
+    float dx = ax - b.x, dy = ay - b.y, dz = az - b.z;
+    return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// running-reference update for one node when a new cluster (sphere b) is about to be accumulated
+__device__ __forceinline__ void update_ref(float px, float py, float pz, const float4& b, float lam2, float& m,
+                                           float& cm, float& X0, float& X1, float& X2) {
+    float lb = fmaxf(0.f, dist3(px, py, pz, b) - b.w);
+    if (lb < m) {
+        float f = fast_ex2(lam2 * (lb - m));  // m = 3e38 initially -> f = 0, X = 0
+        X0 *= f;
+        X1 *= f;
+        X2 *= f;
+        m = lb;
+        cm = lam2 * lb;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict__ cl_range,
+      const float4* __restrict__ src_pos, const float4* __restrict__ src_wn, float* __restrict__ Y, size_t ystride,
+      unsigned long long* __restrict__ pair_counter) {
+    __shared__ int s_list[kListCap];
+    __shared__ float4 s_src[kWarps][2][32];
+    __shared__ float s_redf[kWarps];
+    __shared__ int s_wcount[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ntx = (P.nx + kTile - 1) / kTile, nty = (P.ny + kTile - 1) / kTile;
+    int t = blockIdx.x;
+    const int tx = t % ntx;
+    t /= ntx;
+    const int ty = t % nty;
+    const int tz = t / nty;
+    const int nzl = P.k1 - P.k0;
+
+    // tile centre / half diagonal (always the full 8^3 box: conservative for partial tiles)
+    const float hdT = P.cell * 3.5f * 1.7320508f * 1.0001f;
+    const float cTx = P.ox + P.cell * (tx * kTile + 3.5f);
+    const float cTy = P.oy + P.cell * (ty * kTile + 3.5f);
+    const float cTz = P.oz + P.cell * (P.k0 + tz * kTile + 3.5f);
+
+    // ---- A1: upper bound of the nearest-source distance over the tile
+    float best = 3e38f;
+    for (int c = tid; c < P.n_clusters; c += kThreads) {
+        float4 b = cl_bounds[c];
+        best = fminf(best, dist3(cTx, cTy, cTz, b) + b.w);
+    }
+    best = warp_min(best);
+    if (lane == 0) s_redf[w] = best;
+    __syncthreads();
+    float UT = s_redf[0];
+#pragma unroll
+    for (int i = 1; i < kWarps; i++) UT = fminf(UT, s_redf[i]);
+    UT += hdT;
+    __syncthreads();
+
+    // ---- brick / node geometry
+    const int bx0 = tx * kTile + 4 * (w & 1), by0 = ty * kTile + 4 * ((w >> 1) & 1), bz0 = tz * kTile + 4 * (w >> 2);
+    const float hdB = P.cell * 1.5f * 1.7320508f * 1.0001f;
+    const float cBx = P.ox + P.cell * (bx0 + 1.5f), cBy = P.oy + P.cell * (by0 + 1.5f),
+                cBz = P.oz + P.cell * (P.k0 + bz0 + 1.5f);
+    const int ix = bx0 + (lane & 3), iy = by0 + ((lane >> 2) & 3), iz0 = bz0 + (lane >> 4), iz1 = iz0 + 2;
+    const float px = P.ox + P.cell * ix, py = P.oy + P.cell * iy;
+    const float pz0 = P.oz + P.cell * (P.k0 + iz0), pz1 = P.oz + P.cell * (P.k0 + iz1);
+
+    float m0 = 3e38f, m1 = 3e38f, cm0 = 0.f, cm1 = 0.f;
+    float X00 = 0.f, X01 = 0.f, X02 = 0.f, X10 = 0.f, X11 = 0.f, X12 = 0.f;
+    float best2 = 3e38f;  // squared distance brick centre -> nearest source seen so far
+    unsigned long long npairs = 0;
+    const float lam2 = P.lam2, nlam2 = -P.lam2, tol = P.tol;
+
+    for (int cbase = 0; cbase < P.n_clusters;) {
+        // ---- A2: ordered compaction of the clusters that can matter anywhere in the tile
+        int nl = 0;
+        while (cbase < P.n_clusters && nl + kThreads <= kListCap) {
+            int c = cbase + tid;
+            bool keep = false;
+            if (c < P.n_clusters) {
+                float4 b = cl_bounds[c];
+                float lb = fmaxf(0.f, dist3(cTx, cTy, cTz, b) - b.w - hdT);
+                keep = (lb - UT) <= tol;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_wcount[w] = __popc(mask);
+            __syncthreads();
+            int off = nl, tot = 0;
+#pragma unroll
+            for (int i = 0; i < kWarps; i++) {
+                int cnt = s_wcount[i];
+                if (i < w) off += cnt;
+                tot += cnt;
+            }
+            if (keep) s_list[off + __popc(mask & ((1u << lane) - 1u))] = c;
+            nl += tot;
+            cbase += kThreads;
+            __syncthreads();
+        }
+        const int nlist = nl;
+
+        // ---- B0: exact nearest-source distance at the brick centre (culling only; never enters the sum)
+        {
+            float ub = 3e38f;
+            for (int i = lane; i < nlist; i += 32) {
+                float4 b = cl_bounds[s_list[i]];
+                ub = fminf(ub, dist3(cBx, cBy, cBz, b) + b.w);
+            }
+            ub = warp_min(ub);
+            best2 = fminf(best2, ub * ub);
+            for (int base = 0; base < nlist; base += 32) {
+                int i = base + lane;
+                bool need = false;
+                if (i < nlist) {
+                    float4 b = cl_bounds[s_list[i]];
+                    float lb = dist3(cBx, cBy, cBz, b) - b.w;
+                    need = lb * fabsf(lb) < best2;
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, need);
+                while (mask) {
+                    int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    int2 rg = cl_range[s_list[base + j]];
+                    float d2 = 3e38f;
+                    if (lane < rg.y) {
+                        float4 p = src_pos[rg.x + lane];
+                        float dx = p.x - cBx, dy = p.y - cBy, dz = p.z - cBz;
+                        d2 = dx * dx + dy * dy + dz * dz;
+                    }
+                    best2 = fminf(best2, warp_min(d2));
+                }
+            }
+        }
+        const float UB = sqrtf(best2) * 1.00001f + hdB;
+
+        // ---- B1: evaluate the clusters kept for this brick
+        for (int base = 0; base < nlist; base += 32) {
+            int i = base + lane;
+            bool keep = false;
+            int c = 0;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nlist) {
+                c = s_list[i];
+                b = cl_bounds[c];
+                float lb = fmaxf(0.f, dist3(cBx, cBy, cBz, b) - b.w - hdB);
+                keep = (lb - UB) <= tol;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                int cj = __shfl_sync(0xffffffffu, c, j);
+                float4 bj;
+                bj.x = __shfl_sync(0xffffffffu, b.x, j);
+                bj.y = __shfl_sync(0xffffffffu, b.y, j);
+                bj.z = __shfl_sync(0xffffffffu, b.z, j);
+                bj.w = __shfl_sync(0xffffffffu, b.w, j);
+                int2 rg = cl_range[cj];
+                __syncwarp();
+                if (lane < rg.y) {
+                    s_src[w][0][lane] = src_pos[rg.x + lane];
+                    s_src[w][1][lane] = src_wn[rg.x + lane];
+                }
+                __syncwarp();
+                update_ref(px, py, pz0, bj, lam2, m0, cm0, X00, X01, X02);
+                update_ref(px, py, pz1, bj, lam2, m1, cm1, X10, X11, X12);
+#pragma unroll 4
+                for (int s = 0; s < rg.y; s++) {
+                    float4 p = s_src[w][0][s];
+                    float4 n = s_src[w][1][s];
+                    float dx = px - p.x, dy = py - p.y;
+                    float dxy2 = fmaf(dy, dy, dx * dx);
+                    float dz0 = pz0 - p.z, dz1 = pz1 - p.z;
+                    float r20 = fmaf(dz0, dz0, dxy2), r21 = fmaf(dz1, dz1, dxy2);
+                    float ri0 = fast_rsqrt(r20), ri1 = fast_rsqrt(r21);
+                    float r0 = r20 * ri0, r1 = r21 * ri1;
+                    float e0 = fast_ex2(fmaf(nlam2, r0, cm0)), e1 = fast_ex2(fmaf(nlam2, r1, cm1));
+                    float w0 = e0 * ri0, w1 = e1 * ri1;
+                    X00 = fmaf(w0, n.x, X00);
+                    X01 = fmaf(w0, n.y, X01);
+                    X02 = fmaf(w0, n.z, X02);
+                    X10 = fmaf(w1, n.x, X10);
+                    X11 = fmaf(w1, n.y, X11);
+                    X12 = fmaf(w1, n.z, X12);
+                }
+                npairs += 2ull * (unsigned)rg.y;
+            }
+        }
+        __syncthreads();  // s_list is rebuilt by the next chunk
+    }
+
+    // ---- Step 2: normalise and store (component-major Y)
+    const size_t nloc = ystride;
+    if (ix < P.nx && iy < P.ny) {
+        if (iz0 < nzl) {
+            float s = fmaxf(fmaxf(fabsf(X00), fabsf(X01)), fabsf(X02));
+            float a = X00 / s, b = X01 / s, c = X02 / s;
+            float nrm = sqrtf(a * a + b * b + c * c);
+            size_t idx = (size_t)ix + (size_t)iy * P.nx + (size_t)iz0 * P.nx * P.ny;
+            Y[idx] = a / nrm;
+            Y[idx + nloc] = b / nrm;
+            Y[idx + 2 * nloc] = c / nrm;
+        }
+        if (iz1 < nzl) {
+            float s = fmaxf(fmaxf(fabsf(X10), fabsf(X11)), fabsf(X12));
+            float a = X10 / s, b = X11 / s, c = X12 / s;
+            float nrm = sqrtf(a * a + b * b + c * c);
+            size_t idx = (size_t)ix + (size_t)iy * P.nx + (size_t)iz1 * P.nx * P.ny;
+            Y[idx] = a / nrm;
+            Y[idx + nloc] = b / nrm;
+            Y[idx + 2 * nloc] = c / nrm;
+        }
+    }
+    if (pair_counter) {
+        // one atomic per warp: every lane evaluated the same number of (node,source) pairs
+        if (lane == 0) atomicAdd(pair_counter, npairs * 32ull);
+    }
+}
+
+}  // namespace
+
+void launch_heat_sum(const SumParams& P, const float4* cl_bounds, const int2* cl_range, const float4* src_pos,
+                     const float4* src_wn, float* Y, size_t ystride, unsigned long long* pair_counter,
+                     cudaStream_t stream) {
+    int ntx = (P.nx + kTile - 1) / kTile, nty = (P.ny + kTile - 1) / kTile, ntz = (P.k1 - P.k0 + kTile - 1) / kTile;
+    size_t nblocks = (size_t)ntx * nty * ntz;
+    k_sum<<<(unsigned)nblocks, kThreads, 0, stream>>>(P, cl_bounds, cl_range, src_pos, src_wn, Y, ystride, pair_counter);
+    SHM3D_LAUNCHED();
+    SHM3D_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace shm3d

@@ -1,0 +1,656 @@
+// projector.cu -- constraint rows, nested-dissection multifrontal Cholesky of A D^-1 A^T (host, fp64) and the
+// device-side projector application.  See projector.cuh for the role of each piece.
+#include <omp.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+#include "projector.cuh"
+
+namespace shm3d {
+
+// ================================================================================================
+// constraint rows (host)
+// ================================================================================================
+void build_constraint_rows(int nx, int ny, int nz, const double bmin[3], double cell, int64_t M, const double* pos,
+                           bool strict, ConstraintRows& out) {
+    out = ConstraintRows();
+    std::unordered_map<int64_t, int> used;
+    used.reserve((size_t)std::min<int64_t>(M, 1 << 22));
+    for (int64_t s = 0; s < M; s++) {
+        // trilinearCoefficients, src/signed_heat_grid_solver.cpp:433-464
+        double d[3] = {pos[3 * s] - bmin[0], pos[3 * s + 1] - bmin[1], pos[3 * s + 2] - bmin[2]};
+        double fi = std::floor(d[0] / cell), fj = std::floor(d[1] / cell), fk = std::floor(d[2] / cell);
+        if (!(fi >= 0 && fj >= 0 && fk >= 0 && fi < nx - 1 && fj < ny - 1 && fk < nz - 1)) {
+            if (strict) throw Error(SHM3D_ERR_INVALID_ARG, "source " + std::to_string(s) + " lies outside the grid");
+            continue;
+        }
+        int i = (int)fi, j = (int)fj, k = (int)fk;
+        int64_t cid = (int64_t)i + (int64_t)j * nx + (int64_t)k * nx * ny;
+        if (!used.emplace(cid, out.m).second) continue;  // hasCellBeenUsed (:93)
+        double tx = (pos[3 * s] - (bmin[0] + i * cell)) / cell;
+        double ty = (pos[3 * s + 1] - (bmin[1] + j * cell)) / cell;
+        double tz = (pos[3 * s + 2] - (bmin[2] + k * cell)) / cell;
+        static const int cx[8] = {0, 1, 0, 0, 1, 1, 0, 1}, cy[8] = {0, 0, 1, 0, 1, 0, 1, 1},
+                         cz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+        for (int c = 0; c < 8; c++) {
+            out.node.push_back(cid + cx[c] + (int64_t)cy[c] * nx + (int64_t)cz[c] * nx * ny);
+            out.w.push_back((cx[c] ? tx : 1. - tx) * (cy[c] ? ty : 1. - ty) * (cz[c] ? tz : 1. - tz));
+        }
+        out.cell.push_back(i);
+        out.cell.push_back(j);
+        out.cell.push_back(k);
+        out.src.push_back(s);
+        out.m++;
+    }
+}
+
+// ================================================================================================
+// nested dissection + multifrontal Cholesky (host)
+// ================================================================================================
+namespace {
+
+struct TreeNode {
+    int s0 = 0, s1 = 0;
+    int left = -1, right = -1;
+    int height = 0;
+    std::vector<int> B;  // sorted permuted indices > s1
+    long long fwd = 0, bwd = 0, bidx = 0;
+};
+
+struct ND {
+    const int* cell;
+    int leaf;
+    std::vector<int> order;  // permuted index -> row
+    std::vector<TreeNode> nodes;
+
+    int build(std::vector<int>& rows) {
+        const int n = (int)rows.size();
+        TreeNode t;
+        if (n <= leaf) {
+            t.s0 = (int)order.size();
+            order.insert(order.end(), rows.begin(), rows.end());
+            t.s1 = (int)order.size();
+            nodes.push_back(std::move(t));
+            return (int)nodes.size() - 1;
+        }
+        int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+        for (int r : rows)
+            for (int a = 0; a < 3; a++) {
+                lo[a] = std::min(lo[a], cell[3 * r + a]);
+                hi[a] = std::max(hi[a], cell[3 * r + a]);
+            }
+        int ax = 0;
+        for (int a = 1; a < 3; a++)
+            if (hi[a] - lo[a] > hi[ax] - lo[ax]) ax = a;
+        std::vector<int> coords(n);
+        for (int i = 0; i < n; i++) coords[i] = cell[3 * rows[i] + ax];
+        std::nth_element(coords.begin(), coords.begin() + n / 2, coords.end());
+        const int c = coords[n / 2];
+        std::vector<int> L, R, S;
+        for (int r : rows) {
+            int v = cell[3 * r + ax];
+            (v < c ? L : (v > c ? R : S)).push_back(r);
+        }
+        std::vector<int>().swap(rows);
+        int li = -1, ri = -1, h = 0;
+        if (!L.empty()) { li = build(L); h = std::max(h, nodes[li].height + 1); }
+        if (!R.empty()) { ri = build(R); h = std::max(h, nodes[ri].height + 1); }
+        t.left = li;
+        t.right = ri;
+        t.height = h;
+        t.s0 = (int)order.size();
+        order.insert(order.end(), S.begin(), S.end());
+        t.s1 = (int)order.size();
+        nodes.push_back(std::move(t));
+        return (int)nodes.size() - 1;
+    }
+};
+
+// blocked partial Cholesky of the leading s columns of the f x f symmetric matrix F (row-major, lower part used)
+bool partial_cholesky(double* F, int f, int s, bool par) {
+    const int NB = 48;
+    for (int k0 = 0; k0 < s; k0 += NB) {
+        const int k1 = std::min(s, k0 + NB), nb = k1 - k0;
+        // diagonal block
+        for (int k = k0; k < k1; k++) {
+            double d = F[(size_t)k * f + k];
+            for (int t = k0; t < k; t++) d -= F[(size_t)k * f + t] * F[(size_t)k * f + t];
+            if (!(d > 0.0)) return false;
+            d = std::sqrt(d);
+            F[(size_t)k * f + k] = d;
+            for (int i = k + 1; i < k1; i++) {
+                double v = F[(size_t)i * f + k];
+                for (int t = k0; t < k; t++) v -= F[(size_t)i * f + t] * F[(size_t)k * f + t];
+                F[(size_t)i * f + k] = v / d;
+            }
+        }
+        // panel rows below: row_i[k0:k1] <- row_i[k0:k1] * Lkk^-T
+#pragma omp parallel for schedule(static) if (par && (f - k1) > 64)
+        for (int i = k1; i < f; i++) {
+            double* ri = F + (size_t)i * f;
+            for (int k = k0; k < k1; k++) {
+                double v = ri[k];
+                const double* rk = F + (size_t)k * f;
+                for (int t = k0; t < k; t++) v -= ri[t] * rk[t];
+                ri[k] = v / rk[k];
+            }
+        }
+        // trailing update (lower triangle): F[i][j] -= <row_i[k0:k1], row_j[k0:k1]>
+#pragma omp parallel for schedule(dynamic, 8) if (par && (f - k1) > 64)
+        for (int i = k1; i < f; i++) {
+            const double* ri = F + (size_t)i * f + k0;
+            double* out = F + (size_t)i * f;
+            for (int j = k1; j <= i; j++) {
+                const double* rj = F + (size_t)j * f + k0;
+                double acc = 0;
+                for (int t = 0; t < nb; t++) acc += ri[t] * rj[t];
+                out[j] -= acc;
+            }
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+// ================================================================================================
+// device kernels
+// ================================================================================================
+namespace {
+
+__global__ void k_proj_gather(int m, const int64_t* __restrict__ rnode, const double* __restrict__ rw,
+                              const int* __restrict__ rperm, const float* __restrict__ v, const float* __restrict__ w,
+                              const double* shift_num, double shift_den, double* __restrict__ rhs) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const double shift = shift_num ? *shift_num / shift_den : 0.0;
+    double acc = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int64_t n = rnode[(size_t)r * 8 + c];
+        if (n >= 0) {
+            double val = (double)v[n] - shift;
+            if (w) val -= (double)w[n];
+            acc += rw[(size_t)r * 8 + c] * val;
+        }
+    }
+    rhs[rperm[r]] = acc;
+}
+
+using NodeDescD = ProjNodeDesc;
+
+// forward: for every row R of every supernode at this height:  val = <FWD[R, 0:s], v[s0:s0+s]>;
+// R < s -> y[s0+R] = val ; else v[B[R-s]] -= val
+__global__ void k_proj_fwd(int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local,
+                           const NodeDescD* __restrict__ nodes, const double* __restrict__ mat,
+                           const int* __restrict__ bidx, double* v, double* __restrict__ y) {
+    int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (R >= n_rows) return;
+    const NodeDescD nd = nodes[row_node[R]];
+    const int rl = row_local[R];
+    const double* row = mat + nd.fwd + (long long)rl * nd.s;
+    const double* x = v + nd.s0;
+    double acc = 0;
+    const int cend = rl < nd.s ? rl + 1 : nd.s;  // W is lower triangular
+    for (int c = lane; c < cend; c += 32) acc += row[c] * x[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        if (rl < nd.s)
+            y[nd.s0 + rl] = acc;
+        else
+            atomicAdd(&v[bidx[nd.bidx + rl - nd.s]], -acc);
+    }
+}
+
+// backward: x[s0+R] = <BWD[R, 0:s], y[s0:]> + <BWD[R, s:s+b], x[B]>
+__global__ void k_proj_bwd(int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local,
+                           const NodeDescD* __restrict__ nodes, const double* __restrict__ mat,
+                           const int* __restrict__ bidx, const double* __restrict__ y, double* x) {
+    int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (R >= n_rows) return;
+    const NodeDescD nd = nodes[row_node[R]];
+    const int rl = row_local[R];
+    const int f = nd.s + nd.b;
+    const double* row = mat + nd.bwd + (long long)rl * f;
+    double acc = 0;
+    for (int c = rl + lane; c < nd.s; c += 32) acc += row[c] * y[nd.s0 + c];  // W^T is upper triangular
+    const int* bi = bidx + nd.bidx;
+    for (int c = lane; c < nd.b; c += 32) acc += row[nd.s + c] * x[bi[c]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) x[nd.s0 + rl] = acc;
+}
+
+__global__ void k_proj_scatter(int n_touched, const int64_t* __restrict__ tnode, const int* __restrict__ tptr,
+                               const int* __restrict__ trow, const double* __restrict__ tw,
+                               const double* __restrict__ sol, float* __restrict__ v) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_touched) return;
+    double acc = 0;
+    for (int e = tptr[t]; e < tptr[t + 1]; e++) acc += tw[e] * sol[trow[e]];
+    int64_t n = tnode[t];
+    v[n] = (float)((double)v[n] - acc);
+}
+
+}  // namespace
+
+// ================================================================================================
+// Projector
+// ================================================================================================
+Projector::~Projector() {
+    cudaFree(d_rnode_);
+    cudaFree(d_rw_);
+    cudaFree(d_tnode_);
+    cudaFree(d_tptr_);
+    cudaFree(d_trow_);
+    cudaFree(d_tw_);
+    cudaFree(d_nodes_);
+    cudaFree(d_mat_);
+    cudaFree(d_bidx_);
+    cudaFree(d_rowmaps_);
+    cudaFree(d_rhs_);
+    cudaFree(d_y_);
+    cudaFree(d_sol_);
+}
+
+template <typename T>
+static T* to_device(const std::vector<T>& h, cudaStream_t s) {
+    T* d = nullptr;
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    SHM3D_CUDA_CHECK(cudaMalloc((void**)&d, bytes));
+    if (!h.empty()) SHM3D_CUDA_CHECK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return d;
+}
+
+void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, bool uniform, HostFactor& out) {
+    out = HostFactor();
+    out.m = rows.m;
+    if (rows.m == 0) return;
+    const int m = rows.m;
+    const int64_t nx = nx_, ny = ny_, nz = nz_;
+    const int64_t pl = nx * ny;
+
+    // ---- node diagonal (number of in-range neighbours) and the "all interior" property
+    auto node_d = [&](int64_t n) -> double {
+        int64_t k = n / pl, rem = n - k * pl, j = rem / nx, i = rem - j * nx;
+        return (double)((i > 0) + (i < nx - 1) + (j > 0) + (j < ny - 1) + (k > 0) + (k < nz - 1));
+    };
+    std::vector<double>& dinv = out.dinv;
+    dinv.resize((size_t)m * 8);
+    for (size_t e = 0; e < (size_t)m * 8; e++) {
+        double d = node_d(rows.node[e]);
+        if (d != 6.0) out.all_interior = false;
+        dinv[e] = uniform ? 1.0 : 1.0 / d;
+    }
+
+    // ---- adjacency through the cell lattice
+    std::unordered_map<int64_t, int> cellrow;
+    cellrow.reserve((size_t)m * 2);
+    for (int r = 0; r < m; r++)
+        cellrow[(int64_t)rows.cell[3 * r] + (int64_t)rows.cell[3 * r + 1] * nx + (int64_t)rows.cell[3 * r + 2] * pl] = r;
+    std::vector<int> nb_ptr(m + 1, 0), nb;
+    nb.reserve((size_t)m * 12);
+    for (int r = 0; r < m; r++) {
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    int ci = rows.cell[3 * r] + dx, cj = rows.cell[3 * r + 1] + dy, ck = rows.cell[3 * r + 2] + dz;
+                    if (ci < 0 || cj < 0 || ck < 0 || ci >= nx || cj >= ny || ck >= nz) continue;
+                    auto it = cellrow.find((int64_t)ci + (int64_t)cj * nx + (int64_t)ck * pl);
+                    if (it != cellrow.end()) nb.push_back(it->second);
+                }
+        nb_ptr[r + 1] = (int)nb.size();
+    }
+    auto entry = [&](int r, int q) -> double {  // (A D^-1 A^T)_{rq}
+        double a = 0;
+        for (int c = 0; c < 8; c++)
+            for (int e = 0; e < 8; e++)
+                if (rows.node[(size_t)r * 8 + c] == rows.node[(size_t)q * 8 + e])
+                    a += rows.w[(size_t)r * 8 + c] * rows.w[(size_t)q * 8 + e] * dinv[(size_t)r * 8 + c];
+        return a;
+    };
+
+    // ---- nested dissection ordering
+    ND nd;
+    nd.cell = rows.cell.data();
+    nd.leaf = 40;
+    nd.order.reserve(m);
+    {
+        std::vector<int> all(m);
+        for (int r = 0; r < m; r++) all[r] = r;
+        nd.build(all);
+    }
+    std::vector<TreeNode>& T = nd.nodes;
+    const int nT = (int)T.size();
+    std::vector<int>& perm_ = out.perm;
+    perm_.assign(m, 0);
+    for (int p = 0; p < m; p++) perm_[nd.order[p]] = p;
+
+    // ---- symbolic: boundary sets (children precede parents in T)
+    for (int t = 0; t < nT; t++) {
+        TreeNode& n = T[t];
+        std::vector<int>& B = n.B;
+        for (int p = n.s0; p < n.s1; p++) {
+            int r = nd.order[p];
+            for (int e = nb_ptr[r]; e < nb_ptr[r + 1]; e++) {
+                int q = perm_[nb[e]];
+                if (q >= n.s1) B.push_back(q);
+            }
+        }
+        for (int ch : {n.left, n.right})
+            if (ch >= 0)
+                for (int q : T[ch].B)
+                    if (q >= n.s1) B.push_back(q);
+        std::sort(B.begin(), B.end());
+        B.erase(std::unique(B.begin(), B.end()), B.end());
+    }
+
+    // ---- storage layout
+    long long mat_total = 0, bidx_total = 0;
+    int max_h = 0;
+    for (int t = 0; t < nT; t++) {
+        TreeNode& n = T[t];
+        long long s = n.s1 - n.s0, b = (long long)n.B.size(), f = s + b;
+        n.fwd = mat_total;
+        mat_total += f * s;
+        n.bwd = mat_total;
+        mat_total += s * f;
+        n.bidx = bidx_total;
+        bidx_total += b;
+        max_h = std::max(max_h, n.height);
+    }
+    std::vector<double>& mat = out.mat;
+    mat.assign((size_t)mat_total, 0.0);
+    std::vector<int>& bidx = out.bidx;
+    bidx.resize((size_t)bidx_total);
+    for (int t = 0; t < nT; t++) std::copy(T[t].B.begin(), T[t].B.end(), bidx.begin() + T[t].bidx);
+
+    // ---- numeric multifrontal factorisation, level by level (nodes of equal height are independent)
+    std::vector<std::vector<int>>& by_h = out.by_height;
+    by_h.assign(max_h + 1, {});
+    for (int t = 0; t < nT; t++) by_h[T[t].height].push_back(t);
+    std::vector<std::vector<double>> U(nT);  // update matrices (b x b, lower used)
+    const int nthreads = std::max(1, omp_get_max_threads());
+    bool ok = true;
+    for (int h = 0; h <= max_h && ok; h++) {
+        const std::vector<int>& lv = by_h[h];
+        const bool outer = (int)lv.size() >= 2 * nthreads;
+#pragma omp parallel for schedule(dynamic, 1) if (outer)
+        for (int li = 0; li < (int)lv.size(); li++) {
+            if (!ok) continue;
+            const int t = lv[li];
+            TreeNode& n = T[t];
+            const int s = n.s1 - n.s0, b = (int)n.B.size(), f = s + b;
+            std::vector<double> F((size_t)f * f, 0.0);
+            auto loc = [&](int q) -> int {
+                if (q < n.s1) return q - n.s0;
+                return s + (int)(std::lower_bound(n.B.begin(), n.B.end(), q) - n.B.begin());
+            };
+            // original entries of the separator rows
+            for (int p = n.s0; p < n.s1; p++) {
+                int r = nd.order[p];
+                for (int e = nb_ptr[r]; e < nb_ptr[r + 1]; e++) {
+                    int q = perm_[nb[e]];
+                    if (q < p) continue;
+                    F[(size_t)loc(q) * f + (p - n.s0)] += entry(r, nb[e]);
+                }
+            }
+            // extend-add the children's update matrices
+            for (int ch : {n.left, n.right}) {
+                if (ch < 0) continue;
+                const std::vector<int>& CB = T[ch].B;
+                const int cb = (int)CB.size();
+                std::vector<int> map(cb);
+                for (int i = 0; i < cb; i++) map[i] = loc(CB[i]);
+                const std::vector<double>& Uc = U[ch];
+                for (int i = 0; i < cb; i++)
+                    for (int j = 0; j <= i; j++) F[(size_t)map[i] * f + map[j]] += Uc[(size_t)i * cb + j];
+                std::vector<double>().swap(U[ch]);
+            }
+            if (!partial_cholesky(F.data(), f, s, !outer)) {
+                ok = false;
+                continue;
+            }
+            // update matrix for the parent
+            if (b > 0) {
+                U[t].resize((size_t)b * b);
+                for (int i = 0; i < b; i++)
+                    for (int j = 0; j <= i; j++) U[t][(size_t)i * b + j] = F[(size_t)(s + i) * f + (s + j)];
+            }
+            // W = L11^-1 (lower), G = L21 W ; FWD = [W; G] (f x s), BWD = [W^T | -G^T] (s x f)
+            double* FW = mat.data() + n.fwd;
+            double* BW = mat.data() + n.bwd;
+#pragma omp parallel for schedule(dynamic, 4) if (!outer && s > 64)
+            for (int c = 0; c < s; c++) {  // column c of W: solve L11 w = e_c
+                for (int i = c; i < s; i++) {
+                    double v = (i == c) ? 1.0 : 0.0;
+                    const double* Li = F.data() + (size_t)i * f;
+                    for (int k = c; k < i; k++) v -= Li[k] * FW[(size_t)k * s + c];
+                    FW[(size_t)i * s + c] = v / Li[i];
+                }
+            }
+#pragma omp parallel for schedule(dynamic, 4) if (!outer && b > 64)
+            for (int i = 0; i < b; i++) {  // G[i, c] = sum_{k>=c} L21[i,k] W[k,c]
+                const double* Li = F.data() + (size_t)(s + i) * f;
+                double* Gi = FW + (size_t)(s + i) * s;
+                for (int k = 0; k < s; k++) {
+                    const double l = Li[k];
+                    const double* Wk = FW + (size_t)k * s;
+                    for (int c = 0; c <= k; c++) Gi[c] += l * Wk[c];
+                }
+            }
+            for (int r = 0; r < s; r++) {
+                for (int c = 0; c < s; c++) BW[(size_t)r * f + c] = FW[(size_t)c * s + r];
+                for (int c = 0; c < b; c++) BW[(size_t)r * f + s + c] = -FW[(size_t)(s + c) * s + r];
+            }
+        }
+    }
+    if (!ok)
+        throw Error(SHM3D_ERR_FACTORIZATION,
+                    "constraint system A A^T is not positive definite (coincident / dependent source constraints)");
+    out.nodes.resize(nT);
+    for (int t = 0; t < nT; t++) {
+        out.nodes[t].s0 = T[t].s0;
+        out.nodes[t].s = T[t].s1 - T[t].s0;
+        out.nodes[t].b = (int)T[t].B.size();
+        out.nodes[t].fwd = T[t].fwd;
+        out.nodes[t].bwd = T[t].bwd;
+        out.nodes[t].bidx = T[t].bidx;
+    }
+}
+
+// Host mirror of k_proj_fwd / k_proj_bwd (tests only).
+void HostFactor::solve_host(std::vector<double>& v) const {
+    if (!m) return;
+    std::vector<double> y(m, 0.0), x(m, 0.0);
+    for (size_t h = 0; h < by_height.size(); h++)
+        for (int t : by_height[h]) {
+            const ProjNodeDesc& nd = nodes[t];
+            const int f = nd.s + nd.b;
+            std::vector<double> val(f, 0.0);
+            for (int r = 0; r < f; r++) {
+                const double* row = mat.data() + nd.fwd + (long long)r * nd.s;
+                double acc = 0;
+                for (int c = 0; c < nd.s; c++) acc += row[c] * v[nd.s0 + c];
+                val[r] = acc;
+            }
+            for (int r = 0; r < nd.s; r++) y[nd.s0 + r] = val[r];
+            for (int r = 0; r < nd.b; r++) v[bidx[nd.bidx + r]] -= val[nd.s + r];
+        }
+    for (int h = (int)by_height.size() - 1; h >= 0; h--)
+        for (int t : by_height[h]) {
+            const ProjNodeDesc& nd = nodes[t];
+            const int f = nd.s + nd.b;
+            for (int r = 0; r < nd.s; r++) {
+                const double* row = mat.data() + nd.bwd + (long long)r * f;
+                double acc = 0;
+                for (int c = 0; c < nd.s; c++) acc += row[c] * y[nd.s0 + c];
+                for (int c = 0; c < nd.b; c++) acc += row[nd.s + c] * x[bidx[nd.bidx + c]];
+                x[nd.s0 + r] = acc;
+            }
+        }
+    v = x;
+}
+
+void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool uniform, cudaStream_t stream) {
+    m_ = rows.m;
+    L_ = L;
+    if (m_ == 0) return;
+    const int m = m_;
+    HostFactor hf;
+    factor_constraints(rows, L.nx, L.ny, L.nz, uniform, hf);
+    all_interior_ = hf.all_interior;
+    perm_ = hf.perm;
+    factor_bytes_ = hf.mat.size() * sizeof(double);
+    const std::vector<ProjNodeDesc>& descs = hf.nodes;
+    const std::vector<std::vector<int>>& by_h = hf.by_height;
+    const int max_h = (int)by_h.size() - 1;
+    const std::vector<double>& dinv = hf.dinv;
+    const int64_t pl = (int64_t)L.nx * L.ny;
+
+    // ---- launch batches per height: forward rows = f per node, backward rows = s per node
+    std::vector<int> rowmaps;
+    fwd_levels_.clear();
+    std::vector<size_t> offs;  // (fwd node, fwd local, bwd node, bwd local) offsets per height
+    for (int h = 0; h <= max_h; h++) {
+        LevelBatch lb;
+        size_t o_fn = rowmaps.size();
+        for (int t : by_h[h])
+            for (int r = 0; r < descs[t].s + descs[t].b; r++) rowmaps.push_back(t);
+        size_t o_fl = rowmaps.size();
+        for (int t : by_h[h])
+            for (int r = 0; r < descs[t].s + descs[t].b; r++) rowmaps.push_back(r);
+        lb.n_rows = (int)(o_fl - o_fn);
+        size_t o_bn = rowmaps.size();
+        for (int t : by_h[h])
+            for (int r = 0; r < descs[t].s; r++) rowmaps.push_back(t);
+        size_t o_bl = rowmaps.size();
+        for (int t : by_h[h])
+            for (int r = 0; r < descs[t].s; r++) rowmaps.push_back(r);
+        lb.n_nodes = (int)(o_bl - o_bn);  // = backward rows at this height
+        offs.push_back(o_fn);
+        offs.push_back(o_fl);
+        offs.push_back(o_bn);
+        offs.push_back(o_bl);
+        fwd_levels_.push_back(lb);
+    }
+    d_rowmaps_ = to_device(rowmaps, stream);
+    for (int h = 0; h <= max_h; h++) {
+        fwd_levels_[h].row_node = d_rowmaps_ + offs[4 * h];
+        fwd_levels_[h].row_local = d_rowmaps_ + offs[4 * h + 1];
+    }
+    bwd_off_.assign(offs.begin(), offs.end());
+
+    // ---- upload rows (local node indices), transpose, factor
+    const int64_t lo = (int64_t)L.k0 * pl, hi = (int64_t)L.k1 * pl;
+    std::vector<int64_t> rnode((size_t)m * 8);
+    for (size_t e = 0; e < rnode.size(); e++) {
+        int64_t n = rows.node[e];
+        rnode[e] = (n >= lo && n < hi) ? n - lo : -1;
+    }
+    // node-centric transpose over the nodes this rank owns
+    std::vector<std::pair<int64_t, int>> ent;  // (local node, e)
+    ent.reserve((size_t)m * 8);
+    for (size_t e = 0; e < rnode.size(); e++)
+        if (rnode[e] >= 0) ent.emplace_back(rnode[e], (int)e);
+    std::sort(ent.begin(), ent.end());
+    std::vector<int64_t> tnode;
+    std::vector<int> tptr, trow;
+    std::vector<double> tw;
+    for (size_t a = 0; a < ent.size(); a++) {
+        if (a == 0 || ent[a].first != ent[a - 1].first) {
+            tnode.push_back(ent[a].first);
+            tptr.push_back((int)a);
+        }
+        int e = ent[a].second;
+        trow.push_back(perm_[e / 8]);
+        tw.push_back(rows.w[e] * dinv[e]);
+    }
+    tptr.push_back((int)ent.size());
+    n_touched_ = (int)tnode.size();
+
+    d_rnode_ = to_device(rnode, stream);
+    d_rw_ = to_device(rows.w, stream);
+    d_rperm_ = to_device(perm_, stream);
+    d_tnode_ = to_device(tnode, stream);
+    d_tptr_ = to_device(tptr, stream);
+    d_trow_ = to_device(trow, stream);
+    d_tw_ = to_device(tw, stream);
+    d_nodes_ = to_device(descs, stream);
+    d_mat_ = to_device(hf.mat, stream);
+    d_bidx_ = to_device(hf.bidx, stream);
+    SHM3D_CUDA_CHECK(cudaMalloc((void**)&d_rhs_, (size_t)m * sizeof(double)));
+    SHM3D_CUDA_CHECK(cudaMalloc((void**)&d_y_, (size_t)m * sizeof(double)));
+    SHM3D_CUDA_CHECK(cudaMalloc((void**)&d_sol_, (size_t)m * sizeof(double)));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
+}
+
+void Projector::gather(const float* v, const float* w, const double* shift_num, double shift_den,
+                       cudaStream_t s) const {
+    if (!m_) return;
+    k_proj_gather<<<(m_ + 127) / 128, 128, 0, s>>>(m_, d_rnode_, d_rw_, d_rperm_, v, w, shift_num, shift_den, d_rhs_);
+    SHM3D_LAUNCHED();
+    if (reduce_hook_) reduce_hook_(d_rhs_, m_, s);
+}
+
+void Projector::solve(cudaStream_t s) const {
+    if (!m_) return;
+    const NodeDescD* nodes = (const NodeDescD*)d_nodes_;
+    const int H = (int)fwd_levels_.size();
+    for (int h = 0; h < H; h++) {
+        const LevelBatch& lb = fwd_levels_[h];
+        if (!lb.n_rows) continue;
+        k_proj_fwd<<<(lb.n_rows * 32 + 255) / 256, 256, 0, s>>>(lb.n_rows, lb.row_node, lb.row_local, nodes, d_mat_,
+                                                                 d_bidx_, d_rhs_, d_y_);
+        SHM3D_LAUNCHED();
+    }
+    for (int h = H - 1; h >= 0; h--) {
+        const LevelBatch& lb = fwd_levels_[h];
+        const int nr = lb.n_nodes;
+        if (!nr) continue;
+        k_proj_bwd<<<(nr * 32 + 255) / 256, 256, 0, s>>>(nr, d_rowmaps_ + bwd_off_[4 * h + 2],
+                                                          d_rowmaps_ + bwd_off_[4 * h + 3], nodes, d_mat_, d_bidx_, d_y_,
+                                                          d_sol_);
+        SHM3D_LAUNCHED();
+    }
+    SHM3D_CUDA_CHECK(cudaGetLastError());
+}
+
+void Projector::scatter_sub(float* v, cudaStream_t s) const {
+    if (!m_ || !n_touched_) return;
+    k_proj_scatter<<<(n_touched_ + 127) / 128, 128, 0, s>>>(n_touched_, d_tnode_, d_tptr_, d_trow_, d_tw_, d_sol_, v);
+    SHM3D_LAUNCHED();
+}
+
+void Projector::apply(float* v, cudaStream_t s) const {
+    if (!m_) return;
+    gather(v, nullptr, nullptr, 1.0, s);
+    solve(s);
+    scatter_sub(v, s);
+}
+
+void Projector::apply_update(float* v, const float* w, cudaStream_t s) const {
+    if (!m_) return;
+    gather(v, w, nullptr, 1.0, s);
+    solve(s);
+    scatter_sub(v, s);
+}
+
+void Projector::multipliers(const float* v, std::vector<double>& lam_host, cudaStream_t s) const {
+    lam_host.assign(m_, 0.0);
+    if (!m_) return;
+    gather(v, nullptr, nullptr, 1.0, s);
+    solve(s);
+    std::vector<double> tmp(m_);
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), d_sol_, m_ * sizeof(double), cudaMemcpyDeviceToHost, s));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int r = 0; r < m_; r++) lam_host[r] = tmp[perm_[r]];
+}
+
+}  // namespace shm3d

@@ -1,0 +1,857 @@
+// solver.cu -- orchestration of the grid-solver hot path and the C ABI (include/shm3d_grid.h).
+//
+// Mirrors SignedHeatGridSolver::computeDistance (reference src/signed_heat_grid_solver.cpp:5-114 / :116-222):
+//   Steps 1-2  k_sum (k_sum.cu)            <- :48-65
+//   rhs        k_div_rhs (grid_ops.cu)      <- :70-74
+//   Step 3     constrained multigrid-PCG    <- :80-108 (same KKT system, solved in the null space of A)
+//   shift      k_source_average             <- :110-111, :466-496
+// No CPU fallback exists: every entry point needs a CUDA device.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "dist.cuh"
+#include "projector.cuh"
+
+using namespace shm3d;
+
+namespace shm3d {
+
+static std::string g_create_error;
+
+struct PVec {  // float vector with one ghost plane on each side of the slab
+    DevBuf<float> buf;
+    size_t plane = 0, n = 0;
+    void alloc(const LevelDims& L, cudaStream_t s) {
+        plane = L.plane();
+        n = L.n();
+        size_t tot = n + 2 * plane;
+        if (buf.n < tot) {
+            buf.alloc(tot);
+        }
+        SHM3D_CUDA_CHECK(cudaMemsetAsync(buf.p, 0, tot * sizeof(float), s));
+    }
+    float* ip() const { return buf.p + plane; }
+};
+
+struct MGLevel {
+    LevelDims L;
+    double bmin[3];
+    double cell;
+    PVec x, tmp, r;  // iterate, second iterate buffer, residual scratch
+    PVec b;          // right-hand side (level >= 1)
+    std::unique_ptr<Projector> proj;
+    ConstraintRows rows;
+};
+
+}  // namespace shm3d
+
+struct shm3d_ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::unique_ptr<Dist> dist;
+    // device scalars
+    DevBuf<double> sc;  // see enum Sc
+    DevBuf<unsigned long long> counters;
+    DevBuf<unsigned int> nonfinite;
+    // cached across calls (sizes only grow)
+    DevBuf<float4> d_spos, d_swn, d_cbounds;
+    DevBuf<int2> d_crange;
+    DevBuf<double> d_pos, d_area, d_nrm;
+    PVec Y[1];  // component-major: 3 padded components stored back to back
+    DevBuf<float> Ybuf;
+    PVec vx, vr, vp, vq;
+    DevBuf<float> d_pinv;
+    DevBuf<double> d_phi64;
+    std::vector<MGLevel> levels;
+};
+
+namespace shm3d {
+
+enum Sc { kRho = 0, kPQ, kSumR, kRZ, kSumZ, kRhoNew, kRho0, kShiftNum, kShiftDen, kTmp, kNumSc = 16 };
+
+// ------------------------------------------------------------------------------------------------
+// small device kernels that belong to the orchestration
+// ------------------------------------------------------------------------------------------------
+__global__ void k_scalars_after_dot(double* sc, double n_global) {
+    // rho_new = r.g = r.z - mean(z) * sum(r)   (r is in range(P), so r.(A^T lam) = 0)
+    double mean_z = sc[kSumZ] / n_global;
+    sc[kRhoNew] = sc[kRZ] - mean_z * sc[kSumR];
+}
+__global__ void k_scalars_commit(double* sc, int first) {
+    if (first) sc[kRho0] = sc[kRhoNew];
+    sc[kTmp] = sc[kRho];  // previous rho (beta denominator)
+    sc[kRho] = sc[kRhoNew];
+}
+
+// weighted source average of the trilinear interpolant (src/signed_heat_grid_solver.cpp:405-431, :466-496)
+__global__ void k_source_average(LevelDims L, double bx, double by, double bz, double cell, int64_t M,
+                                 const double* __restrict__ pos, const double* __restrict__ area,
+                                 const float* __restrict__ phi, double* out /* [2]: sum A*phi, sum A */) {
+    double a0 = 0, a1 = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < M; s += (int64_t)gridDim.x * blockDim.x) {
+        double qx = pos[3 * s], qy = pos[3 * s + 1], qz = pos[3 * s + 2];
+        int i = (int)floor((qx - bx) / cell), j = (int)floor((qy - by) / cell), k = (int)floor((qz - bz) / cell);
+        double tx = (qx - (bx + i * cell)) / cell, ty = (qy - (by + j * cell)) / cell, tz = (qz - (bz + k * cell)) / cell;
+        double A = area[s];
+        double v = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            int di = c & 1, dj = (c >> 1) & 1, dk = c >> 2;
+            int kk = k + dk;
+            if (kk < L.k0 || kk >= L.k1) continue;  // owned by another rank
+            double w = (di ? tx : 1. - tx) * (dj ? ty : 1. - ty) * (dk ? tz : 1. - tz);
+            v += w * (double)phi[(size_t)(i + di) + (size_t)(j + dj) * L.nx + (size_t)(kk - L.k0) * L.nx * L.ny];
+        }
+        a0 += A * v;
+        a1 += A;
+    }
+    __shared__ double s0[256], s1[256];
+    s0[threadIdx.x] = a0;
+    s1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s0[threadIdx.x] += s0[threadIdx.x + o];
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[2 * blockIdx.x] = s0[0];
+        out[2 * blockIdx.x + 1] = s1[0];
+    }
+}
+__global__ void k_fold_pairs(const double* part, int nb, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int i = 0; i < nb; i++) {
+            a += part[2 * i];
+            b += part[2 * i + 1];
+        }
+        out[0] = a;
+        out[1] = b;
+    }
+}
+__global__ void k_finish_phi(size_t n, const float* __restrict__ x, const double* sc, double* __restrict__ out64,
+                             float* __restrict__ out32) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double shift = sc[kShiftNum] / sc[kShiftDen];
+    double v = (double)x[e] - shift;
+    if (out64) out64[e] = v;
+    if (out32) out32[e] = (float)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side dense helpers for the coarsest multigrid level
+// ------------------------------------------------------------------------------------------------
+static void jacobi_eig(std::vector<double>& A, int n, std::vector<double>& V) {  // A symmetric -> diag; V columns
+    V.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < i; j++) off += A[(size_t)i * n + j] * A[(size_t)i * n + j];
+        if (off < 1e-26) break;
+        for (int p = 0; p < n; p++)
+            for (int q = p + 1; q < n; q++) {
+                double apq = A[(size_t)p * n + q];
+                if (std::fabs(apq) < 1e-300) continue;
+                double th = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2 * apq);
+                double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1));
+                double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < n; k++) {
+                    double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
+                    A[(size_t)k * n + p] = c * akp - s * akq;
+                    A[(size_t)k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; k++) {
+                    double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
+                    A[(size_t)p * n + k] = c * apk - s * aqk;
+                    A[(size_t)q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+                    V[(size_t)k * n + p] = c * vkp - s * vkq;
+                    V[(size_t)k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+// dense operator of the coarsest level: e = B b solves min 1/2 e^T K' e - b^T e s.t. A e = 0 (pseudo-inverse of P K' P)
+static void coarse_operator(const LevelDims& L, const ConstraintRows& rows, std::vector<float>& B) {
+    const int nx = L.nx, ny = L.ny, nz = L.nz, n = nx * ny * nz;
+    std::vector<double> K((size_t)n * n, 0.0);
+    auto id = [&](int i, int j, int k) { return i + j * nx + k * nx * ny; };
+    for (int k = 0; k < nz; k++)
+        for (int j = 0; j < ny; j++)
+            for (int i = 0; i < nx; i++) {
+                int c = id(i, j, k);
+                const int nb[6][3] = {{i - 1, j, k}, {i + 1, j, k}, {i, j - 1, k}, {i, j + 1, k}, {i, j, k - 1}, {i, j, k + 1}};
+                for (auto& q : nb) {
+                    if (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[0] >= nx || q[1] >= ny || q[2] >= nz) continue;
+                    K[(size_t)c * n + c] += 1;
+                    K[(size_t)c * n + id(q[0], q[1], q[2])] -= 1;
+                }
+            }
+    // orthonormal basis Q of the constraint rows (modified Gram-Schmidt, dependent rows dropped)
+    std::vector<std::vector<double>> Q;
+    for (int r = 0; r < rows.m; r++) {
+        std::vector<double> v(n, 0.0);
+        for (int c = 0; c < 8; c++) v[rows.node[(size_t)r * 8 + c]] += rows.w[(size_t)r * 8 + c];
+        for (int pass = 0; pass < 2; pass++)
+            for (auto& q : Q) {
+                double d = 0;
+                for (int i = 0; i < n; i++) d += q[i] * v[i];
+                for (int i = 0; i < n; i++) v[i] -= d * q[i];
+            }
+        double nn = 0;
+        for (int i = 0; i < n; i++) nn += v[i] * v[i];
+        if (nn < 1e-16) continue;
+        nn = 1 / std::sqrt(nn);
+        for (int i = 0; i < n; i++) v[i] *= nn;
+        Q.push_back(std::move(v));
+    }
+    // M = P K P with P = I - Q^T Q
+    auto applyP_cols = [&](std::vector<double>& X) {  // X <- P X (columns)
+        for (auto& q : Q) {
+            std::vector<double> d(n, 0.0);
+            for (int i = 0; i < n; i++)
+                for (int c = 0; c < n; c++) d[c] += q[i] * X[(size_t)i * n + c];
+            for (int i = 0; i < n; i++)
+                for (int c = 0; c < n; c++) X[(size_t)i * n + c] -= q[i] * d[c];
+        }
+    };
+    applyP_cols(K);  // P K
+    // (P K) P = (P (P K)^T)^T, K symmetric
+    std::vector<double> Kt((size_t)n * n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) Kt[(size_t)i * n + j] = K[(size_t)j * n + i];
+    applyP_cols(Kt);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            double v = 0.5 * (Kt[(size_t)i * n + j] + Kt[(size_t)j * n + i]);
+            Kt[(size_t)i * n + j] = Kt[(size_t)j * n + i] = v;
+        }
+    std::vector<double> V;
+    jacobi_eig(Kt, n, V);
+    double lmax = 0;
+    for (int i = 0; i < n; i++) lmax = std::max(lmax, std::fabs(Kt[(size_t)i * n + i]));
+    B.assign((size_t)n * n, 0.f);
+    std::vector<double> Bd((size_t)n * n, 0.0);
+    for (int e = 0; e < n; e++) {
+        double lam = Kt[(size_t)e * n + e];
+        if (lam < 1e-9 * lmax) continue;
+        for (int i = 0; i < n; i++) {
+            double vi = V[(size_t)i * n + e] / lam;
+            for (int j = 0; j < n; j++) Bd[(size_t)i * n + j] += vi * V[(size_t)j * n + e];
+        }
+    }
+    for (size_t i = 0; i < Bd.size(); i++) B[i] = (float)Bd[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// the solver
+// ------------------------------------------------------------------------------------------------
+struct Timer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit Timer(cudaStream_t st) : s(st) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+    }
+    ~Timer() {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+    void start() { cudaEventRecord(a, s); }
+    void stop() { cudaEventRecord(b, s); }
+    double ms() {
+        cudaEventSynchronize(b);
+        float t = 0;
+        cudaEventElapsedTime(&t, a, b);
+        return t;
+    }
+};
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Solver {
+    shm3d_ctx* c;
+    const shm3d_params* p;
+    GridDesc G;
+    LevelDims L0;
+    cudaStream_t s;
+    shm3d_stats st;
+    float omega = 0.8f;
+    int nu = 2;
+    bool use_mg = true;
+
+    Solver(shm3d_ctx* ctx, const shm3d_params* prm) : c(ctx), p(prm), s(ctx->stream) {
+        memset(&st, 0, sizeof(st));
+        if (!prm) throw Error(SHM3D_ERR_INVALID_ARG, "params is NULL");
+        if (prm->nx < 4 || prm->ny < 4 || prm->nz < 4) throw Error(SHM3D_ERR_INVALID_ARG, "grid must be at least 4^3");
+        if (!(prm->cell > 0) || !(prm->lambda > 0) || !std::isfinite(prm->cell) || !std::isfinite(prm->lambda))
+            throw Error(SHM3D_ERR_INVALID_ARG, "cell and lambda must be positive and finite");
+        G.nx = prm->nx;
+        G.ny = prm->ny;
+        G.nz = prm->nz;
+        int k0, k1;
+        slab_range(c->rank, c->world, prm->nz, k0, k1);
+        G.k0 = k0;
+        G.k1 = k1;
+        for (int a = 0; a < 3; a++) G.bmin[a] = prm->bbox_min[a];
+        G.cell = prm->cell;
+        L0 = LevelDims{G.nx, G.ny, G.nz, G.k0, G.k1};
+        if (L0.nzl() < 1) throw Error(SHM3D_ERR_INVALID_ARG, "more ranks than grid planes");
+        nu = prm->mg_smooth > 0 ? prm->mg_smooth : 2;
+        use_mg = !(prm->flags & SHM3D_FLAG_NO_MG);
+        if (c->sc.n < kNumSc) c->sc.alloc(kNumSc);
+        if (c->counters.n < 4) c->counters.alloc(4);
+        if (c->nonfinite.n < 1) c->nonfinite.alloc(1);
+    }
+
+    // ---------------------------------------------------------------- sources
+    ClusteredSources cs;
+    int64_t M = 0;
+    std::vector<double> h_pos, h_nrm, h_area;  // host copies when inputs are device-resident
+    const double *pos = nullptr, *nrm = nullptr, *area = nullptr;
+
+    void prepare_sources(int64_t M_, const double* pos_, const double* nrm_, const double* area_, bool on_device) {
+        M = M_;
+        if (M <= 0 || !pos_ || !area_) throw Error(SHM3D_ERR_INVALID_ARG, "no sources");
+        double t0 = now_ms();
+        if (on_device) {
+            h_pos.resize(3 * M);
+            h_area.resize(M);
+            SHM3D_CUDA_CHECK(cudaMemcpyAsync(h_pos.data(), pos_, 3 * M * sizeof(double), cudaMemcpyDeviceToHost, s));
+            SHM3D_CUDA_CHECK(cudaMemcpyAsync(h_area.data(), area_, M * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (nrm_) {
+                h_nrm.resize(3 * M);
+                SHM3D_CUDA_CHECK(cudaMemcpyAsync(h_nrm.data(), nrm_, 3 * M * sizeof(double), cudaMemcpyDeviceToHost, s));
+            }
+            SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+            pos = h_pos.data();
+            area = h_area.data();
+            nrm = nrm_ ? h_nrm.data() : nullptr;
+            c->d_pos.alloc(3 * M);
+            c->d_area.alloc(M);
+            SHM3D_CUDA_CHECK(cudaMemcpyAsync(c->d_pos.p, pos_, 3 * M * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            SHM3D_CUDA_CHECK(cudaMemcpyAsync(c->d_area.p, area_, M * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        } else {
+            pos = pos_;
+            nrm = nrm_;
+            area = area_;
+            c->d_pos.upload(pos, 3 * M, s);
+            c->d_area.upload(area, M, s);
+        }
+        st.ms_h2d += now_ms() - t0;
+    }
+
+    void cluster_and_upload() {
+        double t0 = now_ms();
+        if (!nrm) throw Error(SHM3D_ERR_INVALID_ARG, "normals are required for Steps 1-2");
+        double origin[3];
+        origin[0] = G.bmin[0] + 0.5 * G.cell * (G.nx - 1);
+        origin[1] = G.bmin[1] + 0.5 * G.cell * (G.ny - 1);
+        origin[2] = G.bmin[2] + 0.5 * G.cell * (G.nz - 1);
+        build_clusters(M, pos, nrm, area, origin, p->lambda, 4.0, cs);
+        c->d_spos.upload(cs.pos, s);
+        c->d_swn.upload(cs.wn, s);
+        c->d_cbounds.upload(cs.bounds, s);
+        c->d_crange.upload(cs.range, s);
+        st.n_clusters = (int)cs.bounds.size();
+        st.ms_h2d += now_ms() - t0;
+    }
+
+    // ---------------------------------------------------------------- Steps 1-2
+    size_t ycomp() const { return L0.n() + 2 * L0.plane(); }  // stride between padded components
+    float* Ycomp(int a) const { return c->Ybuf.p + (size_t)a * ycomp() + L0.plane(); }
+
+    void run_step12() {
+        c->Ybuf.alloc(3 * ycomp());
+        SumParams P;
+        P.nx = G.nx;
+        P.ny = G.ny;
+        P.nz = G.nz;
+        P.k0 = G.k0;
+        P.k1 = G.k1;
+        P.ox = (float)(G.bmin[0] - cs.origin[0]);
+        P.oy = (float)(G.bmin[1] - cs.origin[1]);
+        P.oz = (float)(G.bmin[2] - cs.origin[2]);
+        P.cell = (float)G.cell;
+        P.lam2 = (float)(p->lambda * 1.4426950408889634);
+        double tau = p->cull_tau > 0 ? p->cull_tau : 12.0;
+        P.tol = std::isinf(tau) ? INFINITY : (float)(tau / p->lambda);
+        P.n_clusters = (int)cs.bounds.size();
+        SHM3D_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), s));
+        SHM3D_CUDA_CHECK(cudaMemsetAsync(c->Ybuf.p, 0, 3 * ycomp() * sizeof(float), s));
+        pending_sum_timer.reset(new Timer(s));
+        pending_sum_timer->start();
+        // Y is written component-major with the padded component stride
+        launch_heat_sum(P, c->d_cbounds.p, c->d_crange.p, c->d_spos.p, c->d_swn.p, Ycomp(0), ycomp(), c->counters.p, s);
+        pending_sum_timer->stop();
+        st.pairs_bruteforce = (int64_t)L0.n() * M;
+    }
+    std::unique_ptr<Timer> pending_sum_timer;
+
+    void finish_step12_stats() {
+        if (pending_sum_timer) {
+            st.ms_sum = pending_sum_timer->ms();
+            pending_sum_timer.reset();
+            unsigned long long np = 0;
+            SHM3D_CUDA_CHECK(cudaMemcpy(&np, c->counters.p, sizeof(np), cudaMemcpyDeviceToHost));
+            st.pairs_evaluated = (int64_t)np;
+        }
+    }
+
+    // ---------------------------------------------------------------- rhs
+    void run_rhs(float* b) {
+        Timer t(s);
+        t.start();
+        if (c->dist) c->dist->exchange_halo3(Ycomp(0), ycomp(), L0, s);
+        SHM3D_CUDA_CHECK(cudaMemsetAsync(c->nonfinite.p, 0, sizeof(unsigned int), s));
+        launch_div_rhs(L0, (float)G.cell, Ycomp(0), ycomp(), b, (p->flags & SHM3D_FLAG_SCRUB_NONFINITE) ? 1 : 0,
+                       c->nonfinite.p, s);
+        t.stop();
+        st.ms_rhs = t.ms();
+        unsigned int nf = 0;
+        SHM3D_CUDA_CHECK(cudaMemcpy(&nf, c->nonfinite.p, sizeof(nf), cudaMemcpyDeviceToHost));
+        if (c->dist) nf = c->dist->allreduce_max_host(nf);
+        if (nf && !(p->flags & SHM3D_FLAG_SCRUB_NONFINITE))
+            // the point-cloud overload does not scrub (reference :180) and solveSquare's checkFinite throws
+            throw Error(SHM3D_ERR_NONFINITE, "right-hand side has " + std::to_string(nf) + " non-finite entries");
+    }
+
+    // ---------------------------------------------------------------- multigrid hierarchy + constraints
+    void build_levels() {
+        double t0 = now_ms();
+        std::vector<MGLevel>& lv = c->levels;
+        lv.clear();
+        lv.emplace_back();
+        lv[0].L = L0;
+        for (int a = 0; a < 3; a++) lv[0].bmin[a] = G.bmin[a];
+        lv[0].cell = G.cell;
+        if (use_mg) {
+            while (true) {
+                const LevelDims Lf = lv.back().L;
+                if ((size_t)Lf.nx * Lf.ny * Lf.nz <= 64) break;  // small enough for the dense coarse solve
+                if ((Lf.nx | Lf.ny | Lf.nz) & 1) break;
+                if (Lf.nx / 2 < 4 || Lf.ny / 2 < 4 || Lf.nz / 2 < 4) break;
+                if ((Lf.k0 & 1) || (Lf.k1 & 1)) break;  // slab boundaries must coarsen cleanly
+                MGLevel cl;
+                cl.L = LevelDims{Lf.nx / 2, Lf.ny / 2, Lf.nz / 2, Lf.k0 / 2, Lf.k1 / 2};
+                for (int a = 0; a < 3; a++) cl.bmin[a] = lv.back().bmin[a] + 0.5 * lv.back().cell;
+                cl.cell = 2 * lv.back().cell;
+                lv.push_back(std::move(cl));
+            }
+            const LevelDims Lc = lv.back().L;
+            if (lv.size() == 1 || (size_t)Lc.nx * Lc.ny * Lc.nz > 512 || c->world > 1) {
+                // no usable hierarchy (odd sizes); distributed multigrid is not wired up yet -> plain projected CG
+                lv.resize(1);
+                use_mg = false;
+            }
+        }
+        // constraints per level
+        for (size_t l = 0; l < lv.size(); l++) {
+            MGLevel& Lv = lv[l];
+            build_constraint_rows(Lv.L.nx, Lv.L.ny, Lv.L.nz, Lv.bmin, Lv.cell, M, pos, l == 0, Lv.rows);
+            bool last = use_mg && (l + 1 == lv.size());
+            if (!last || lv.size() == 1) {
+                Lv.proj.reset(new Projector());
+                Lv.proj->build(Lv.rows, Lv.L, /*uniform=*/l == 0, s);
+                if (c->dist) c->dist->attach(*Lv.proj);
+            }
+            Lv.x.alloc(Lv.L, s);
+            Lv.tmp.alloc(Lv.L, s);
+            Lv.r.alloc(Lv.L, s);
+            if (l > 0) Lv.b.alloc(Lv.L, s);
+        }
+        st.m_constraints = lv[0].rows.m;
+        if (use_mg) {
+            std::vector<float> B;
+            coarse_operator(lv.back().L, lv.back().rows, B);
+            c->d_pinv.upload(B, s);
+        }
+        st.ms_constraints = now_ms() - t0;
+    }
+
+    // one projected-Jacobi sweep: xo = x + Pi w D^-1 (b - K x)
+    void smooth_sweep(MGLevel& Lv, const float* b, const double* sum_b, double n_global) {
+        launch_mg_smooth(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, s);
+        if (Lv.proj) Lv.proj->apply_update(Lv.tmp.ip(), Lv.x.ip(), s);
+        std::swap(Lv.x, Lv.tmp);
+        if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
+    }
+
+    // V-cycle: levels[l].x = V(b - mean)   (mean only at level 0, passed as device scalar)
+    void vcycle(int l, const float* b, const double* sum_b, double n_global) {
+        std::vector<MGLevel>& lv = c->levels;
+        MGLevel& Lv = lv[l];
+        if (l + 1 == (int)lv.size()) {
+            launch_mg_coarse_solve((int)Lv.L.n(), c->d_pinv.p, b, Lv.x.ip(), s);
+            return;
+        }
+        launch_mg_smooth0(Lv.L, Lv.x.ip(), b, sum_b, n_global, omega, s);
+        if (Lv.proj) Lv.proj->apply(Lv.x.ip(), s);
+        if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
+        for (int k = 1; k < nu; k++) smooth_sweep(Lv, b, sum_b, n_global);
+        MGLevel& Lc = lv[l + 1];
+        launch_mg_residual(Lv.L, Lv.x.ip(), b, sum_b, n_global, Lv.r.ip(), s);
+        if (c->dist) c->dist->exchange_halo(Lv.r.ip(), Lv.L, s);
+        launch_mg_restrict(Lv.L, Lc.L, Lv.r.ip(), Lc.b.ip(), s);
+        vcycle(l + 1, Lc.b.ip(), nullptr, 1.0);
+        if (c->dist) c->dist->exchange_halo(Lc.x.ip(), Lc.L, s);
+        launch_mg_prolong_add(Lv.L, Lc.L, Lv.x.ip(), Lc.x.ip(), s);
+        if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
+        for (int k = 0; k < nu; k++) smooth_sweep(Lv, b, sum_b, n_global);
+    }
+
+    // ---------------------------------------------------------------- constrained PCG
+    // On entry c->vr holds b' = cell^2 D^T Y.  On exit c->vx holds phi (unshifted).
+    void run_pcg() {
+        std::vector<MGLevel>& lv = c->levels;
+        Projector& P = *lv[0].proj;
+        double* sc = c->sc.p;
+        const double Ng = (double)G.nglobal();
+        const size_t n = L0.n();
+        float *x = c->vx.ip(), *r = c->vr.ip(), *pv = c->vp.ip(), *q = c->vq.ip();
+        const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : 3e-6;
+        const int maxit = p->cg_max_iters > 0 ? p->cg_max_iters : 2000;
+        Timer t(s);
+        t.start();
+        SHM3D_CUDA_CHECK(cudaMemsetAsync(sc, 0, kNumSc * sizeof(double), s));
+        SHM3D_CUDA_CHECK(cudaMemsetAsync(x, 0, n * sizeof(float), s));
+        P.apply(r, s);  // r~ = P b
+        launch_vec_sum(r, n, sc + kSumR, s);
+        if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
+        double rho0 = 0, rho = 0;
+        int it = 0, bad = 0;
+        double rel = 1.0;
+        for (;; it++) {
+            // z = V(r - mean r)
+            const float* z;
+            if (use_mg) {
+                vcycle(0, r, sc + kSumR, Ng);
+                z = lv[0].x.ip();
+            } else {
+                z = r;
+            }
+            launch_dot_rz(L0, r, z, sc + kRZ, s);  // writes kRZ, kSumZ
+            if (c->dist) c->dist->allreduce(sc + kRZ, 2, s);
+            // g = P (z - mean z): multipliers first, the scatter is applied to p after the axpy
+            P.gather(z, nullptr, sc + kSumZ, Ng, s);
+            P.solve(s);
+            k_scalars_after_dot<<<1, 1, 0, s>>>(sc, Ng);
+            SHM3D_LAUNCHED();
+            k_scalars_commit<<<1, 1, 0, s>>>(sc, it == 0);
+            SHM3D_LAUNCHED();
+            double h[2];
+            SHM3D_CUDA_CHECK(cudaMemcpyAsync(h, sc + kRho, sizeof(double), cudaMemcpyDeviceToHost, s));
+            SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+            rho = h[0];
+            if (it == 0) rho0 = rho;
+            if (!(rho0 > 0) || !std::isfinite(rho)) {
+                if (rho0 == 0) { rel = 0; break; }  // zero right-hand side: phi = 0
+                throw Error(SHM3D_ERR_NONFINITE, "constrained PCG broke down (non-finite or non-positive r.z)");
+            }
+            rel = std::sqrt(std::fabs(rho) / rho0);
+            if (p->flags & SHM3D_FLAG_VERBOSE) fprintf(stderr, "[shm3d] pcg it %d rel %.3e\n", it, rel);
+            if (rel < tol || it >= maxit) break;
+            if (rho <= 0) {
+                if (++bad > 2) break;
+            }
+            launch_update_p(L0, pv, z, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
+            P.scatter_sub(pv, s);
+            if (c->dist) c->dist->exchange_halo(pv, L0, s);
+            // q = K p ; alpha = rho / p.q ; x += alpha p ; r -= alpha P q
+            launch_stencil_dot(L0, pv, q, sc + kPQ, s);
+            if (c->dist) c->dist->allreduce(sc + kPQ, 1, s);
+            P.apply(q, s);
+            launch_update_xr(L0, x, r, pv, q, sc + kRho, sc + kPQ, sc + kSumR, s);
+            if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
+        }
+        t.stop();
+        st.ms_pcg = t.ms();
+        st.cg_iters = it;
+        st.cg_rel_residual = rel;
+        if (it >= maxit && rel >= tol)
+            throw Error(SHM3D_ERR_NO_CONVERGENCE, "constrained PCG did not converge in " + std::to_string(maxit) +
+                                                      " iterations (rel " + std::to_string(rel) + ")");
+    }
+
+    // ---------------------------------------------------------------- shift + output
+    void run_shift_and_output(double* phi_host, float* phi_dev) {
+        double* sc = c->sc.p;
+        Timer t(s);
+        t.start();
+        const int nb = 128;
+        DevBuf<double> part(2 * nb);
+        k_source_average<<<nb, 256, 0, s>>>(L0, G.bmin[0], G.bmin[1], G.bmin[2], G.cell, M, c->d_pos.p, c->d_area.p,
+                                            c->vx.ip(), part.p);
+        SHM3D_LAUNCHED();
+        k_fold_pairs<<<1, 32, 0, s>>>(part.p, nb, sc + kShiftNum);
+        SHM3D_LAUNCHED();
+        if (c->dist) c->dist->allreduce(sc + kShiftNum, 1, s);  // numerator only: every rank sums all areas
+        const size_t n = L0.n();
+        if (phi_host) c->d_phi64.alloc(n);
+        k_finish_phi<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, c->vx.ip(), sc, phi_host ? c->d_phi64.p : nullptr,
+                                                                 phi_dev);
+        SHM3D_LAUNCHED();
+        t.stop();
+        st.ms_shift = t.ms();
+        double h[2];
+        SHM3D_CUDA_CHECK(cudaMemcpy(h, sc + kShiftNum, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+        st.shift = h[0] / h[1];
+        if (phi_host) {
+            double t0 = now_ms();
+            SHM3D_CUDA_CHECK(cudaMemcpy(phi_host, c->d_phi64.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+            st.ms_d2h = now_ms() - t0;
+        }
+    }
+
+    void alloc_pcg_vectors() {
+        c->vx.alloc(L0, s);
+        c->vr.alloc(L0, s);
+        c->vp.alloc(L0, s);
+        c->vq.alloc(L0, s);
+    }
+};
+
+}  // namespace shm3d
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+#define SHM3D_API_BEGIN(ctx)                                   \
+    if (!(ctx)) return SHM3D_ERR_INVALID_ARG;                  \
+    try {                                                      \
+        SHM3D_CUDA_CHECK(cudaSetDevice((ctx)->device));
+#define SHM3D_API_END(ctx)                                     \
+    }                                                          \
+    catch (const shm3d::Error& e) {                            \
+        (ctx)->err = e.what();                                 \
+        cudaGetLastError();                                    \
+        return e.code;                                         \
+    }                                                          \
+    catch (const std::exception& e) {                          \
+        (ctx)->err = e.what();                                 \
+        return SHM3D_ERR_INVALID_ARG;                          \
+    }                                                          \
+    return SHM3D_OK;
+
+extern "C" {
+
+const char* shm3d_version(void) { return "shm3d-b200 0.1 sm_100a"; }
+
+static int create_common(shm3d_ctx** out, int device, int rank, int world, const void* nccl_id) {
+    if (!out) return SHM3D_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                         "); this library has no CPU fallback";
+        cudaGetLastError();
+        return SHM3D_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device ordinal out of range";
+        return SHM3D_ERR_INVALID_ARG;
+    }
+    std::unique_ptr<shm3d_ctx> c(new shm3d_ctx());
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    try {
+        SHM3D_CUDA_CHECK(cudaSetDevice(device));
+        SHM3D_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        if (world > 1) c->dist.reset(new Dist(rank, world, nccl_id, c->stream));
+    } catch (const shm3d::Error& ex) {
+        g_create_error = ex.what();
+        return ex.code;
+    }
+    *out = c.release();
+    return SHM3D_OK;
+}
+
+int shm3d_ctx_create(shm3d_ctx** out, int device) { return create_common(out, device, 0, 1, nullptr); }
+
+int shm3d_ctx_create_dist(shm3d_ctx** out, int device, int rank, int world, const void* nccl_id) {
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !nccl_id)) {
+        g_create_error = "bad rank/world/nccl_id";
+        return SHM3D_ERR_INVALID_ARG;
+    }
+    return create_common(out, device, rank, world, nccl_id);
+}
+
+int shm3d_nccl_unique_id(void* out128) { return Dist::unique_id(out128); }
+
+void shm3d_ctx_destroy(shm3d_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->levels.clear();
+    ctx->dist.reset();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* shm3d_last_error(const shm3d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int shm3d_slab(const shm3d_ctx* ctx, int32_t nz, int32_t* k0, int32_t* k1) {
+    if (!ctx || !k0 || !k1 || nz < 1) return SHM3D_ERR_INVALID_ARG;
+    int a, b;
+    slab_range(ctx->rank, ctx->world, nz, a, b);
+    *k0 = a;
+    *k1 = b;
+    return SHM3D_OK;
+}
+
+static int solve_impl(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double* pos, const double* nrm,
+                      const double* area, double* phi_host, float* phi_dev, shm3d_stats* stats, bool on_device) {
+    SHM3D_API_BEGIN(ctx)
+    if (!phi_host && !phi_dev) throw Error(SHM3D_ERR_INVALID_ARG, "no output buffer");
+    double t0 = now_ms();
+    int64_t l0 = g_kernel_launches;
+    Solver S(ctx, p);
+    if (p->flags & SHM3D_FLAG_FAST)
+        throw Error(SHM3D_ERR_INVALID_ARG, "fastIntegration (greedy BFS) is not implemented in this build");
+    S.prepare_sources(M, pos, nrm, area, on_device);
+    S.cluster_and_upload();
+    S.alloc_pcg_vectors();
+    S.run_step12();       // asynchronous on the GPU ...
+    S.build_levels();     // ... while the host builds and factorises the constraint systems
+    S.finish_step12_stats();
+    S.run_rhs(ctx->vr.ip());
+    S.run_pcg();
+    S.run_shift_and_output(phi_host, phi_dev);
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    S.st.kernel_launches = g_kernel_launches - l0;
+    S.st.ms_total = now_ms() - t0;
+    if (stats) *stats = S.st;
+    SHM3D_API_END(ctx)
+}
+
+int shm3d_solve(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double* pos, const double* nrm,
+                const double* area, double* phi_out, shm3d_stats* stats) {
+    return solve_impl(ctx, p, M, pos, nrm, area, phi_out, nullptr, stats, false);
+}
+
+int shm3d_solve_device(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double* d_pos, const double* d_nrm,
+                       const double* d_area, float* phi_dev, shm3d_stats* stats) {
+    return solve_impl(ctx, p, M, d_pos, d_nrm, d_area, nullptr, phi_dev, stats, true);
+}
+
+int shm3d_step12(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double* pos, const double* nrm,
+                 const double* area, float* Y_out, shm3d_stats* stats) {
+    SHM3D_API_BEGIN(ctx)
+    if (!Y_out) throw Error(SHM3D_ERR_INVALID_ARG, "Y_out is NULL");
+    double t0 = now_ms();
+    int64_t l0 = g_kernel_launches;
+    Solver S(ctx, p);
+    S.prepare_sources(M, pos, nrm, area, false);
+    S.cluster_and_upload();
+    S.run_step12();
+    S.finish_step12_stats();
+    const size_t n = S.L0.n();
+    for (int a = 0; a < 3; a++)
+        SHM3D_CUDA_CHECK(cudaMemcpyAsync(Y_out + (size_t)a * n, S.Ycomp(a), n * sizeof(float), cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    S.st.kernel_launches = g_kernel_launches - l0;
+    S.st.ms_total = now_ms() - t0;
+    if (stats) *stats = S.st;
+    SHM3D_API_END(ctx)
+}
+
+int shm3d_rhs(shm3d_ctx* ctx, const shm3d_params* p, const float* Y, float* b_out) {
+    SHM3D_API_BEGIN(ctx)
+    if (!Y || !b_out) throw Error(SHM3D_ERR_INVALID_ARG, "NULL buffer");
+    Solver S(ctx, p);
+    const size_t n = S.L0.n();
+    ctx->Ybuf.alloc(3 * S.ycomp());
+    SHM3D_CUDA_CHECK(cudaMemsetAsync(ctx->Ybuf.p, 0, 3 * S.ycomp() * sizeof(float), ctx->stream));
+    for (int a = 0; a < 3; a++)
+        SHM3D_CUDA_CHECK(cudaMemcpyAsync(S.Ycomp(a), Y + (size_t)a * n, n * sizeof(float), cudaMemcpyHostToDevice,
+                                         ctx->stream));
+    ctx->vr.alloc(S.L0, ctx->stream);
+    S.run_rhs(ctx->vr.ip());
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(b_out, ctx->vr.ip(), n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    SHM3D_API_END(ctx)
+}
+
+int shm3d_step3(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double* pos, const double* area,
+                const float* b, double* phi_out, shm3d_stats* stats) {
+    SHM3D_API_BEGIN(ctx)
+    if (!b || !phi_out) throw Error(SHM3D_ERR_INVALID_ARG, "NULL buffer");
+    double t0 = now_ms();
+    int64_t l0 = g_kernel_launches;
+    Solver S(ctx, p);
+    S.prepare_sources(M, pos, nullptr, area, false);
+    S.alloc_pcg_vectors();
+    S.build_levels();
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(ctx->vr.ip(), b, S.L0.n() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    S.run_pcg();
+    S.run_shift_and_output(phi_out, nullptr);
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    S.st.kernel_launches = g_kernel_launches - l0;
+    S.st.ms_total = now_ms() - t0;
+    if (stats) *stats = S.st;
+    SHM3D_API_END(ctx)
+}
+
+// ---- host-logic probes (no GPU needed): used by the CPU test-suite to check the constraint assembly and the
+// nested-dissection factorisation against scipy.  They run no device code and are not part of the product path.
+int shm3d_debug_constraints(const shm3d_params* p, int64_t M, const double* pos, int32_t* m_out, int64_t* node_out,
+                            double* w_out, int64_t* src_out, int64_t capacity_rows) {
+    if (!p || !pos || !m_out) return SHM3D_ERR_INVALID_ARG;
+    try {
+        ConstraintRows rows;
+        build_constraint_rows(p->nx, p->ny, p->nz, p->bbox_min, p->cell, M, pos, true, rows);
+        *m_out = rows.m;
+        if (node_out && w_out && src_out) {
+            if (capacity_rows < rows.m) return SHM3D_ERR_INVALID_ARG;
+            memcpy(node_out, rows.node.data(), rows.node.size() * sizeof(int64_t));
+            memcpy(w_out, rows.w.data(), rows.w.size() * sizeof(double));
+            memcpy(src_out, rows.src.data(), rows.src.size() * sizeof(int64_t));
+        }
+    } catch (const shm3d::Error& e) {
+        g_create_error = e.what();
+        return e.code;
+    }
+    return SHM3D_OK;
+}
+
+// v (m doubles, constraint-row order) <- (A D^-1 A^T)^-1 v using the host image of the GPU factor
+int shm3d_debug_factor_solve(const shm3d_params* p, int64_t M, const double* pos, int32_t uniform, double* v,
+                             int32_t m_expected, double* factor_megabytes, int32_t* tree_height) {
+    if (!p || !pos || !v) return SHM3D_ERR_INVALID_ARG;
+    try {
+        ConstraintRows rows;
+        build_constraint_rows(p->nx, p->ny, p->nz, p->bbox_min, p->cell, M, pos, true, rows);
+        if (rows.m != m_expected) return SHM3D_ERR_INVALID_ARG;
+        HostFactor hf;
+        factor_constraints(rows, p->nx, p->ny, p->nz, uniform != 0, hf);
+        std::vector<double> pv(rows.m);
+        for (int r = 0; r < rows.m; r++) pv[hf.perm[r]] = v[r];
+        hf.solve_host(pv);
+        for (int r = 0; r < rows.m; r++) v[r] = pv[hf.perm[r]];
+        if (factor_megabytes) *factor_megabytes = hf.mat.size() * sizeof(double) / 1048576.0;
+        if (tree_height) *tree_height = (int)hf.by_height.size();
+    } catch (const shm3d::Error& e) {
+        g_create_error = e.what();
+        return e.code;
+    }
+    return SHM3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// sources.cu -- host-side preparation of the heat sources for the summation kernel.
+//
+// The reference visits sources in mesh order for every node (src/signed_heat_grid_solver.cpp:53-59).
+// The sum is order-independent up to rounding, so for the GPU the sources are Morton-sorted and cut into
+// spatially compact clusters (<= 32 sources, lambda*radius <= rho_max) that the kernel can accept or
+// reject as a unit (far-field culling) and whose bounding sphere drives the per-node range shift.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace shm3d {
+
+static inline uint32_t spread10(uint32_t v) {
+    v &= 0x3ff;
+    v = (v | (v << 16)) & 0x030000FF;
+    v = (v | (v << 8)) & 0x0300F00F;
+    v = (v | (v << 4)) & 0x030C30C3;
+    v = (v | (v << 2)) & 0x09249249;
+    return v;
+}
+
+void build_clusters(int64_t M, const double* pos, const double* nrm, const double* area, const double origin[3],
+                    double lambda, double rho_max, ClusteredSources& out) {
+    out.pos.clear();
+    out.wn.clear();
+    out.bounds.clear();
+    out.range.clear();
+    for (int a = 0; a < 3; a++) out.origin[a] = origin[a];
+    if (M <= 0) throw Error(SHM3D_ERR_INVALID_ARG, "no sources");
+
+    // weights n*A, scaled so the mean |weight| is O(1) (any positive scale cancels in Step 2's normalisation)
+    double asum = 0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t s = 0; s < M; s++) {
+        for (int a = 0; a < 3; a++) {
+            double v = pos[3 * s + a];
+            if (!std::isfinite(v)) throw Error(SHM3D_ERR_NONFINITE, "non-finite source position");
+            lo[a] = std::min(lo[a], v);
+            hi[a] = std::max(hi[a], v);
+            if (!std::isfinite(nrm[3 * s + a] * area[s]))
+                throw Error(SHM3D_ERR_NONFINITE, "non-finite source normal/area (degenerate face?)");
+        }
+        asum += std::fabs(area[s]);
+    }
+    out.wscale = asum > 0 ? (double)M / asum : 1.0;
+
+    // Morton order over the source bounding box
+    double ext = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-300});
+    std::vector<uint64_t> key(M);
+    for (int64_t s = 0; s < M; s++) {
+        uint32_t q[3];
+        for (int a = 0; a < 3; a++) {
+            double t = (pos[3 * s + a] - lo[a]) / ext;
+            q[a] = (uint32_t)std::min(1023.0, std::max(0.0, t * 1024.0));
+        }
+        uint32_t code = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+        key[s] = ((uint64_t)code << 32) | (uint64_t)s;  // ties broken by input order: deterministic
+    }
+    std::sort(key.begin(), key.end());
+
+    const double rmax = rho_max / lambda;  // cluster radius cap (distance units)
+    out.pos.reserve(M);
+    out.wn.reserve(M);
+    int64_t i = 0;
+    while (i < M) {
+        // grow a cluster greedily along the Morton curve
+        double clo[3], chi[3];
+        int cnt = 0;
+        int64_t j = i;
+        for (; j < M && cnt < 32; j++, cnt++) {
+            int64_t s = (int64_t)(key[j] & 0xffffffffu);
+            double nlo[3], nhi[3];
+            for (int a = 0; a < 3; a++) {
+                double v = pos[3 * s + a];
+                nlo[a] = cnt ? std::min(clo[a], v) : v;
+                nhi[a] = cnt ? std::max(chi[a], v) : v;
+            }
+            double hd = 0.5 * std::sqrt((nhi[0] - nlo[0]) * (nhi[0] - nlo[0]) + (nhi[1] - nlo[1]) * (nhi[1] - nlo[1]) +
+                                        (nhi[2] - nlo[2]) * (nhi[2] - nlo[2]));
+            if (cnt > 0 && hd > rmax) break;
+            for (int a = 0; a < 3; a++) { clo[a] = nlo[a]; chi[a] = nhi[a]; }
+        }
+        double c[3] = {0.5 * (clo[0] + chi[0]), 0.5 * (clo[1] + chi[1]), 0.5 * (clo[2] + chi[2])};
+        double rad = 0;
+        int first = (int)out.pos.size();
+        for (int64_t t = i; t < j; t++) {
+            int64_t s = (int64_t)(key[t] & 0xffffffffu);
+            double d[3] = {pos[3 * s] - c[0], pos[3 * s + 1] - c[1], pos[3 * s + 2] - c[2]};
+            rad = std::max(rad, std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]));
+            float4 p, w;
+            p.x = (float)(pos[3 * s] - origin[0]);
+            p.y = (float)(pos[3 * s + 1] - origin[1]);
+            p.z = (float)(pos[3 * s + 2] - origin[2]);
+            p.w = 0.f;
+            double wa = area[s] * out.wscale;
+            w.x = (float)(nrm[3 * s] * wa);
+            w.y = (float)(nrm[3 * s + 1] * wa);
+            w.z = (float)(nrm[3 * s + 2] * wa);
+            w.w = 0.f;
+            out.pos.push_back(p);
+            out.wn.push_back(w);
+        }
+        float4 b;
+        b.x = (float)(c[0] - origin[0]);
+        b.y = (float)(c[1] - origin[1]);
+        b.z = (float)(c[2] - origin[2]);
+        // pad the radius for the fp32 rounding of centre and members so the bound stays conservative
+        b.w = (float)(rad * (1.0 + 1e-5) + 1e-6 * (std::fabs(b.x) + std::fabs(b.y) + std::fabs(b.z)));
+        out.bounds.push_back(b);
+        out.range.push_back(make_int2(first, (int)(j - i)));
+        i = j;
+    }
+}
+
+}  // namespace shm3d

@@ -1,0 +1,303 @@
+"""
+shm3d -- thin ctypes binding of libshm3d_grid.so (include/shm3d_grid.h) plus a Python mirror of the reference's
+operator interface for the grid path (SignedHeat3DOptions / SignedHeatGridSolver.computeDistance,
+reference include/signed_heat_3d.h:20-28 and include/signed_heat_grid_solver.h:11-22).
+
+Plumbing only: every number is produced by the CUDA library.  There is NO CPU fallback -- creating a solver
+without a usable GPU raises Shm3dError(SHM3D_ERR_CUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libshm3d_grid.so")
+
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_FACTORIZATION, ERR_NO_CONVERGENCE, ERR_NCCL = range(7)
+FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG = 1, 2, 4, 8
+
+
+class Params(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("bbox_min", C.c_double * 3),
+                ("cell", C.c_double), ("lambda_", C.c_double), ("flags", C.c_uint32), ("cull_tau", C.c_double),
+                ("cg_rel_tol", C.c_double), ("cg_max_iters", C.c_int32), ("mg_smooth", C.c_int32)]
+
+    @property
+    def N(self):
+        return self.nx * self.ny * self.nz
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_h2d", C.c_double), ("ms_sum", C.c_double), ("ms_rhs", C.c_double),
+                ("ms_constraints", C.c_double), ("ms_pcg", C.c_double), ("ms_shift", C.c_double),
+                ("ms_d2h", C.c_double), ("pairs_evaluated", C.c_int64), ("pairs_bruteforce", C.c_int64),
+                ("n_clusters", C.c_int32), ("m_constraints", C.c_int32), ("cg_iters", C.c_int32),
+                ("cg_rel_residual", C.c_double), ("shift", C.c_double), ("kernel_launches", C.c_int64),
+                ("ms_pcg_stencil", C.c_double), ("pcg_stencil_launches", C.c_int64), ("ms_pcg_vcycle", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Shm3dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"shm3d error {code}: {msg}")
+        self.code = code
+
+
+EXPORTS = ["shm3d_ctx_create", "shm3d_ctx_create_dist", "shm3d_nccl_unique_id", "shm3d_ctx_destroy",
+           "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
+           "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
+           "shm3d_debug_factor_solve", "shm3d_version"]
+
+_lib = None
+
+
+def lib():
+    """Load libshm3d_grid.so (fails loudly if it has not been built: run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Shm3dError(ERR_CUDA, f"{LIB_PATH} is missing -- build it with signed-heat-3d_b200/csrc/build.sh")
+        L = C.CDLL(LIB_PATH)
+        dp, fp, vp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p
+        i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+        PP, SP = C.POINTER(Params), C.POINTER(Stats)
+        L.shm3d_ctx_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.shm3d_ctx_create_dist.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]
+        L.shm3d_nccl_unique_id.argtypes = [vp]
+        L.shm3d_ctx_destroy.argtypes = [vp]
+        L.shm3d_ctx_destroy.restype = None
+        L.shm3d_last_error.argtypes = [vp]
+        L.shm3d_last_error.restype = C.c_char_p
+        L.shm3d_slab.argtypes = [vp, C.c_int32, i32p, i32p]
+        L.shm3d_solve.argtypes = [vp, PP, C.c_int64, dp, dp, dp, dp, SP]
+        L.shm3d_solve_device.argtypes = [vp, PP, C.c_int64, vp, vp, vp, vp, SP]
+        L.shm3d_step12.argtypes = [vp, PP, C.c_int64, dp, dp, dp, fp, SP]
+        L.shm3d_rhs.argtypes = [vp, PP, fp, fp]
+        L.shm3d_step3.argtypes = [vp, PP, C.c_int64, dp, dp, fp, dp, SP]
+        L.shm3d_prepare_mesh.argtypes = [dp, C.c_int64, i64p, i64p, C.c_int64, C.c_double, C.c_double, C.c_double, PP,
+                                         dp, dp, dp, dp]
+        L.shm3d_prepare_points.argtypes = [dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, PP]
+        L.shm3d_debug_constraints.argtypes = [PP, C.c_int64, dp, i32p, i64p, dp, i64p, C.c_int64]
+        L.shm3d_debug_factor_solve.argtypes = [PP, C.c_int64, dp, C.c_int32, dp, C.c_int32, dp, i32p]
+        L.shm3d_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def flatten_faces(faces):
+    """list-of-lists (or [nF,3] array) -> (face_vertices int64[], face_offsets int64[nF+1])"""
+    if isinstance(faces, np.ndarray) and faces.ndim == 2:
+        nF, d = faces.shape
+        return np.ascontiguousarray(faces, dtype=np.int64).ravel(), np.arange(0, (nF + 1) * d, d, dtype=np.int64)
+    off = np.zeros(len(faces) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(f) for f in faces])
+    return np.asarray([v for f in faces for v in f], dtype=np.int64), off
+
+
+def prepare_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0):
+    """Host half of computeDistance(VertexPositionGeometry&) -- rows a4-a6.  Returns (Params, pos, nrm, area, h)."""
+    V = _c64(V)
+    fv, fo = flatten_faces(faces)
+    nF = len(fo) - 1
+    p = Params()
+    pos = np.empty((nF, 3))
+    nrm = np.empty((nF, 3))
+    area = np.empty(nF)
+    h = C.c_double()
+    rc = lib().shm3d_prepare_mesh(_dp(V), len(V), fv.ctypes.data_as(C.POINTER(C.c_int64)),
+                                  fo.ctypes.data_as(C.POINTER(C.c_int64)), nF, tCoef, hCoef, scale, C.byref(p),
+                                  _dp(pos), _dp(nrm), _dp(area), C.byref(h))
+    if rc != OK:
+        raise Shm3dError(rc, "shm3d_prepare_mesh: invalid mesh")
+    return p, pos, nrm, area, h.value
+
+
+def prepare_points(P, h, tCoef=1.0, hCoef=0.0, scale=2.0):
+    P = _c64(P)
+    p = Params()
+    rc = lib().shm3d_prepare_points(_dp(P), len(P), h, tCoef, hCoef, scale, C.byref(p))
+    if rc != OK:
+        raise Shm3dError(rc, "shm3d_prepare_points: invalid input")
+    return p
+
+
+def debug_constraints(p: Params, pos):
+    pos = _c64(pos)
+    m = C.c_int32()
+    rc = lib().shm3d_debug_constraints(C.byref(p), len(pos), _dp(pos), C.byref(m), None, None, None, 0)
+    if rc != OK:
+        raise Shm3dError(rc, lib().shm3d_last_error(None).decode())
+    node = np.empty((m.value, 8), dtype=np.int64)
+    w = np.empty((m.value, 8))
+    src = np.empty(m.value, dtype=np.int64)
+    rc = lib().shm3d_debug_constraints(C.byref(p), len(pos), _dp(pos), C.byref(m),
+                                       node.ctypes.data_as(C.POINTER(C.c_int64)), _dp(w),
+                                       src.ctypes.data_as(C.POINTER(C.c_int64)), m.value)
+    if rc != OK:
+        raise Shm3dError(rc, lib().shm3d_last_error(None).decode())
+    return src, node, w
+
+
+def debug_factor_solve(p: Params, pos, v, uniform=True):
+    pos = _c64(pos)
+    v = np.array(v, dtype=np.float64)
+    mb = C.c_double()
+    th = C.c_int32()
+    rc = lib().shm3d_debug_factor_solve(C.byref(p), len(pos), _dp(pos), 1 if uniform else 0, _dp(v), len(v),
+                                        C.byref(mb), C.byref(th))
+    if rc != OK:
+        raise Shm3dError(rc, lib().shm3d_last_error(None).decode())
+    return v, mb.value, th.value
+
+
+class Context:
+    """One GPU context (shm3d_ctx).  rank/world/nccl_id select the slab-partitioned multi-GPU mode."""
+
+    def __init__(self, device=0, rank=0, world=1, nccl_id: bytes | None = None):
+        self._h = C.c_void_p()
+        L = lib()
+        if world > 1:
+            buf = C.create_string_buffer(nccl_id, 128)
+            rc = L.shm3d_ctx_create_dist(C.byref(self._h), device, rank, world, C.cast(buf, C.c_void_p))
+        else:
+            rc = L.shm3d_ctx_create(C.byref(self._h), device)
+        if rc != OK:
+            raise Shm3dError(rc, L.shm3d_last_error(None).decode())
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self._h:
+            lib().shm3d_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise Shm3dError(rc, lib().shm3d_last_error(self._h).decode())
+
+    def slab(self, nz):
+        k0, k1 = C.c_int32(), C.c_int32()
+        self._check(lib().shm3d_slab(self._h, nz, C.byref(k0), C.byref(k1)))
+        return k0.value, k1.value
+
+    def local_n(self, p: Params):
+        k0, k1 = self.slab(p.nz)
+        return p.nx * p.ny * (k1 - k0)
+
+    def solve(self, p: Params, pos, nrm, area, out=None):
+        pos, nrm, area = _c64(pos), _c64(nrm), _c64(area)
+        phi = out if out is not None else np.empty(self.local_n(p))
+        st = Stats()
+        self._check(lib().shm3d_solve(self._h, C.byref(p), len(area), _dp(pos), _dp(nrm), _dp(area), _dp(phi),
+                                      C.byref(st)))
+        return phi, st
+
+    def solve_device(self, p: Params, d_pos, d_nrm, d_area, d_phi, n_sources):
+        """device pointers (ints) -- inputs double, output float32[local N]"""
+        st = Stats()
+        self._check(lib().shm3d_solve_device(self._h, C.byref(p), n_sources, C.c_void_p(d_pos), C.c_void_p(d_nrm),
+                                             C.c_void_p(d_area), C.c_void_p(d_phi), C.byref(st)))
+        return st
+
+    def step12(self, p: Params, pos, nrm, area):
+        pos, nrm, area = _c64(pos), _c64(nrm), _c64(area)
+        Y = np.empty((3, self.local_n(p)), dtype=np.float32)
+        st = Stats()
+        self._check(lib().shm3d_step12(self._h, C.byref(p), len(area), _dp(pos), _dp(nrm), _dp(area), _fp(Y),
+                                       C.byref(st)))
+        return Y, st
+
+    def rhs(self, p: Params, Y):
+        Y = np.ascontiguousarray(Y, dtype=np.float32)
+        b = np.empty(self.local_n(p), dtype=np.float32)
+        self._check(lib().shm3d_rhs(self._h, C.byref(p), _fp(Y), _fp(b)))
+        return b
+
+    def step3(self, p: Params, pos, area, b):
+        pos, area = _c64(pos), _c64(area)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        phi = np.empty(self.local_n(p))
+        st = Stats()
+        self._check(lib().shm3d_step3(self._h, C.byref(p), len(area), _dp(pos), _dp(area), _fp(b), _dp(phi),
+                                      C.byref(st)))
+        return phi, st
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().shm3d_nccl_unique_id(C.cast(buf, C.c_void_p))
+    if rc != OK:
+        raise Shm3dError(rc, "ncclGetUniqueId failed (NCCL not loadable?)")
+    return buf.raw
+
+
+# ----------------------------------------------------------------------------------------------------
+# Mirror of the reference's operator interface
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class SignedHeat3DOptions:
+    """include/signed_heat_3d.h:20-28 (levelSetConstraint / useCrouzeixRaviart are tet-solver options and are
+    ignored by the grid solver, src/signed_heat_grid_solver.cpp:75)."""
+    tCoef: float = 1.0
+    hCoef: float = 0.0
+    rebuild: bool = True
+    scale: float = 2.0
+    fastIntegration: bool = False
+
+
+class SignedHeatGridSolver:
+    """include/signed_heat_grid_solver.h:11-22.  computeDistance(V, faces) is the mesh overload,
+    computeDistancePoints(P, N, areas, h) the point-cloud overload (the tufted-triangulation areas and mean edge
+    length are the caller's: SURVEY.md section 8f row N1)."""
+
+    def __init__(self, device=0, context: Context | None = None):
+        self.VERBOSE = False
+        self.ctx = context if context is not None else Context(device)
+        self.params = None   # grid of the last solve (the reference caches nx, bbox, cellSize)
+        self.stats = None
+
+    def _finish(self, p, pos, nrm, area, options):
+        if self.VERBOSE:
+            p.flags |= FLAG_VERBOSE
+        if options.fastIntegration:
+            p.flags |= FLAG_FAST
+        phi, st = self.ctx.solve(p, pos, nrm, area)
+        self.params, self.stats = p, st
+        return phi
+
+    def computeDistance(self, V, faces, options: SignedHeat3DOptions = SignedHeat3DOptions()):
+        if self.params is not None and not options.rebuild:
+            # grid cached from the previous call (src/signed_heat_grid_solver.cpp:8): only lambda / sources change
+            p_new, pos, nrm, area, _ = prepare_mesh(V, faces, options.tCoef, 0.0, options.scale)
+            p = Params.from_buffer_copy(self.params)
+            p.lambda_ = p_new.lambda_
+        else:
+            p, pos, nrm, area, _ = prepare_mesh(V, faces, options.tCoef, options.hCoef, options.scale)
+        return self._finish(p, pos, nrm, area, options)
+
+    def computeDistancePoints(self, P, normals, areas, h, options: SignedHeat3DOptions = SignedHeat3DOptions()):
+        p = prepare_points(P, h, options.tCoef, options.hCoef, options.scale)
+        return self._finish(p, _c64(P), _c64(normals), _c64(areas), options)
