@@ -96,6 +96,8 @@ int shm3d_nccl_unique_id(void* out128);
 void shm3d_ctx_destroy(shm3d_ctx* ctx);
 /* Message of the last failing call on this context (or of a failed create when ctx == NULL). */
 const char* shm3d_last_error(const shm3d_ctx* ctx);
+/* z-slab [k0,k1) of rank `rank` of `world` for a grid of nz planes (pure function; no context needed). */
+int shm3d_slab_range(int32_t rank, int32_t world, int32_t nz, int32_t* k0, int32_t* k1);
 /* z-slab [k0,k1) this context owns for a grid of nz planes. */
 int shm3d_slab(const shm3d_ctx* ctx, int32_t nz, int32_t* k0, int32_t* k1);
 

@@ -38,8 +38,9 @@ def build_clib(force: bool = False) -> str:
     src = os.path.join(_HERE, "csrc", "shm_oracle.c")
     if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        # same optimisation flags as the reference's Release build (CMakeLists.txt:46)
-        cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"]
+        # -O3 like the reference's Release build (CMakeLists.txt:46); x86-64-v3 instead of -march=native because
+        # the built .so travels to the GPU box, whose host CPU differs from this container's
+        cmd = ["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"]
         subprocess.check_call(cmd)
     return out
 

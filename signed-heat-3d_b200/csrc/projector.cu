@@ -1,10 +1,13 @@
 // projector.cu -- constraint rows, nested-dissection multifrontal Cholesky of A D^-1 A^T (host, fp64) and the
 // device-side projector application.  See projector.cuh for the role of each piece.
-#include <omp.h>
-
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
+#include <thread>
 #include <unordered_map>
 
 #include "projector.cuh"
@@ -51,6 +54,93 @@ void build_constraint_rows(int nx, int ny, int nz, const double bmin[3], double 
 // nested dissection + multifrontal Cholesky (host)
 // ================================================================================================
 namespace {
+
+// Small blocking thread pool for the host factorisation.  (OpenMP's spin-waiting workers made the many short
+// parallel regions of the multifrontal sweep several times SLOWER on cgroup-limited and 128-thread hosts.)
+class Pool {
+  public:
+    static Pool& get() {
+        static Pool p;
+        return p;
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    // run fn(i) for i in [0,n), dynamically scheduled over the pool + the calling thread
+    template <typename F>
+    void parallel_for(int n, const F& fn) {
+        if (n <= 0) return;
+        if (n == 1 || workers_.empty() || busy_) {
+            for (int i = 0; i < n; i++) fn(i);
+            return;
+        }
+        busy_ = true;
+        std::function<void(int)> f = fn;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &f;
+            n_ = n;
+            next_.store(0);
+            active_ = (int)workers_.size();
+            gen_++;
+        }
+        cv_.notify_all();
+        for (int i; (i = next_.fetch_add(1)) < n;) fn(i);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return active_ == 0; });
+        job_ = nullptr;
+        busy_ = false;
+    }
+
+  private:
+    Pool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int nt = (int)std::max(1u, std::min(16u, hw / 2));
+        if (const char* e = getenv("SHM3D_HOST_THREADS")) nt = std::max(1, atoi(e));
+        for (int i = 1; i < nt; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void loop() {
+        unsigned long seen = 0;
+        for (;;) {
+            std::function<void(int)>* job;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                job = job_;
+                n = n_;
+            }
+            if (job)
+                for (int i; (i = next_.fetch_add(1)) < n;) (*job)(i);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--active_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::function<void(int)>* job_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, active_ = 0;
+    unsigned long gen_ = 0;
+    bool stop_ = false;
+    bool busy_ = false;  // nested use runs serially
+};
+
+double wall() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct TreeNode {
     int s0 = 0, s1 = 0;
@@ -128,27 +218,38 @@ bool partial_cholesky(double* F, int f, int s, bool par) {
             }
         }
         // panel rows below: row_i[k0:k1] <- row_i[k0:k1] * Lkk^-T
-#pragma omp parallel for schedule(static) if (par && (f - k1) > 64)
-        for (int i = k1; i < f; i++) {
-            double* ri = F + (size_t)i * f;
-            for (int k = k0; k < k1; k++) {
-                double v = ri[k];
-                const double* rk = F + (size_t)k * f;
-                for (int t = k0; t < k; t++) v -= ri[t] * rk[t];
-                ri[k] = v / rk[k];
+        auto panel_rows = [&](int i0, int i1) {
+            for (int i = i0; i < i1; i++) {
+                double* ri = F + (size_t)i * f;
+                for (int k = k0; k < k1; k++) {
+                    double v = ri[k];
+                    const double* rk = F + (size_t)k * f;
+                    for (int t = k0; t < k; t++) v -= ri[t] * rk[t];
+                    ri[k] = v / rk[k];
+                }
             }
-        }
+        };
         // trailing update (lower triangle): F[i][j] -= <row_i[k0:k1], row_j[k0:k1]>
-#pragma omp parallel for schedule(dynamic, 8) if (par && (f - k1) > 64)
-        for (int i = k1; i < f; i++) {
-            const double* ri = F + (size_t)i * f + k0;
-            double* out = F + (size_t)i * f;
-            for (int j = k1; j <= i; j++) {
-                const double* rj = F + (size_t)j * f + k0;
-                double acc = 0;
-                for (int t = 0; t < nb; t++) acc += ri[t] * rj[t];
-                out[j] -= acc;
+        auto trailing = [&](int i0, int i1) {
+            for (int i = i0; i < i1; i++) {
+                const double* ri = F + (size_t)i * f + k0;
+                double* out = F + (size_t)i * f;
+                for (int j = k1; j <= i; j++) {
+                    const double* rj = F + (size_t)j * f + k0;
+                    double acc = 0;
+                    for (int t = 0; t < nb; t++) acc += ri[t] * rj[t];
+                    out[j] -= acc;
+                }
             }
+        };
+        const int rows = f - k1;
+        if (par && rows > 256) {
+            const int chunk = 16, nch = (rows + chunk - 1) / chunk;
+            Pool::get().parallel_for(nch, [&](int c) { panel_rows(k1 + c * chunk, std::min(f, k1 + (c + 1) * chunk)); });
+            Pool::get().parallel_for(nch, [&](int c) { trailing(k1 + c * chunk, std::min(f, k1 + (c + 1) * chunk)); });
+        } else {
+            panel_rows(k1, f);
+            trailing(k1, f);
         }
     }
     return true;
@@ -316,6 +417,8 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
         return a;
     };
 
+    const bool dbg = getenv("SHM3D_DEBUG") != nullptr;
+    double tdbg = wall();
     // ---- nested dissection ordering
     ND nd;
     nd.cell = rows.cell.data();
@@ -351,6 +454,17 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
         B.erase(std::unique(B.begin(), B.end()), B.end());
     }
 
+    if (dbg) {
+        fprintf(stderr, "[shm3d] ND: m=%d nodes=%d adjacency+order+symbolic %.3fs\n", m, nT, wall() - tdbg);
+        tdbg = wall();
+        std::vector<std::pair<long long, int>> big;
+        for (int t = 0; t < nT; t++) big.emplace_back((long long)(T[t].s1 - T[t].s0 + (int)T[t].B.size()), t);
+        std::sort(big.rbegin(), big.rend());
+        for (int i = 0; i < std::min(8, nT); i++) {
+            const TreeNode& n = T[big[i].second];
+            fprintf(stderr, "[shm3d]   front %d: s=%d b=%d height=%d\n", big[i].second, n.s1 - n.s0, (int)n.B.size(), n.height);
+        }
+    }
     // ---- storage layout
     long long mat_total = 0, bidx_total = 0;
     int max_h = 0;
@@ -376,14 +490,14 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
     by_h.assign(max_h + 1, {});
     for (int t = 0; t < nT; t++) by_h[T[t].height].push_back(t);
     std::vector<std::vector<double>> U(nT);  // update matrices (b x b, lower used)
-    const int nthreads = std::max(1, omp_get_max_threads());
+    const int nthreads = Pool::get().size();
     bool ok = true;
     for (int h = 0; h <= max_h && ok; h++) {
         const std::vector<int>& lv = by_h[h];
         const bool outer = (int)lv.size() >= 2 * nthreads;
-#pragma omp parallel for schedule(dynamic, 1) if (outer)
-        for (int li = 0; li < (int)lv.size(); li++) {
-            if (!ok) continue;
+        double tl = wall();
+        auto do_node = [&](int li) {
+            if (!ok) return;
             const int t = lv[li];
             TreeNode& n = T[t];
             const int s = n.s1 - n.s0, b = (int)n.B.size(), f = s + b;
@@ -415,7 +529,7 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
             }
             if (!partial_cholesky(F.data(), f, s, !outer)) {
                 ok = false;
-                continue;
+                return;
             }
             // update matrix for the parent
             if (b > 0) {
@@ -426,17 +540,15 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
             // W = L11^-1 (lower), G = L21 W ; FWD = [W; G] (f x s), BWD = [W^T | -G^T] (s x f)
             double* FW = mat.data() + n.fwd;
             double* BW = mat.data() + n.bwd;
-#pragma omp parallel for schedule(dynamic, 4) if (!outer && s > 64)
-            for (int c = 0; c < s; c++) {  // column c of W: solve L11 w = e_c
+            auto w_col = [&](int c) {  // column c of W: solve L11 w = e_c
                 for (int i = c; i < s; i++) {
                     double v = (i == c) ? 1.0 : 0.0;
                     const double* Li = F.data() + (size_t)i * f;
                     for (int k = c; k < i; k++) v -= Li[k] * FW[(size_t)k * s + c];
                     FW[(size_t)i * s + c] = v / Li[i];
                 }
-            }
-#pragma omp parallel for schedule(dynamic, 4) if (!outer && b > 64)
-            for (int i = 0; i < b; i++) {  // G[i, c] = sum_{k>=c} L21[i,k] W[k,c]
+            };
+            auto g_row = [&](int i) {  // G[i, c] = sum_{k>=c} L21[i,k] W[k,c]
                 const double* Li = F.data() + (size_t)(s + i) * f;
                 double* Gi = FW + (size_t)(s + i) * s;
                 for (int k = 0; k < s; k++) {
@@ -444,13 +556,22 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
                     const double* Wk = FW + (size_t)k * s;
                     for (int c = 0; c <= k; c++) Gi[c] += l * Wk[c];
                 }
-            }
+            };
+            if (!outer && s > 256) Pool::get().parallel_for(s, w_col);
+            else for (int c = 0; c < s; c++) w_col(c);
+            if (!outer && b > 256) Pool::get().parallel_for(b, g_row);
+            else for (int i = 0; i < b; i++) g_row(i);
             for (int r = 0; r < s; r++) {
                 for (int c = 0; c < s; c++) BW[(size_t)r * f + c] = FW[(size_t)c * s + r];
                 for (int c = 0; c < b; c++) BW[(size_t)r * f + s + c] = -FW[(size_t)(s + c) * s + r];
             }
-        }
+        };
+        if (outer) Pool::get().parallel_for((int)lv.size(), do_node);
+        else for (int li = 0; li < (int)lv.size(); li++) do_node(li);
+        if (dbg) fprintf(stderr, "[shm3d]   height %d: %d nodes outer=%d %.4fs\n", h, (int)lv.size(), (int)outer, wall() - tl);
     }
+    (void)0;
+    if (dbg) fprintf(stderr, "[shm3d] numeric factorisation %.3fs, %.1f MB\n", wall() - tdbg, mat.size() * 8e-6);
     if (!ok)
         throw Error(SHM3D_ERR_FACTORIZATION,
                     "constraint system A A^T is not positive definite (coincident / dependent source constraints)");

@@ -706,6 +706,15 @@ void shm3d_ctx_destroy(shm3d_ctx* ctx) {
 
 const char* shm3d_last_error(const shm3d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int shm3d_slab_range(int32_t rank, int32_t world, int32_t nz, int32_t* k0, int32_t* k1) {
+    if (!k0 || !k1 || world < 1 || rank < 0 || rank >= world || nz < 1) return SHM3D_ERR_INVALID_ARG;
+    int a, b;
+    slab_range(rank, world, nz, a, b);
+    *k0 = a;
+    *k1 = b;
+    return SHM3D_OK;
+}
+
 int shm3d_slab(const shm3d_ctx* ctx, int32_t nz, int32_t* k0, int32_t* k1) {
     if (!ctx || !k0 || !k1 || nz < 1) return SHM3D_ERR_INVALID_ARG;
     int a, b;

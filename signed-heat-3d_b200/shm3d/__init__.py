@@ -49,7 +49,7 @@ class Shm3dError(RuntimeError):
         self.code = code
 
 
-EXPORTS = ["shm3d_ctx_create", "shm3d_ctx_create_dist", "shm3d_nccl_unique_id", "shm3d_ctx_destroy",
+EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm3d_nccl_unique_id", "shm3d_ctx_destroy",
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
            "shm3d_debug_factor_solve", "shm3d_version"]
@@ -75,6 +75,7 @@ def lib():
         L.shm3d_last_error.argtypes = [vp]
         L.shm3d_last_error.restype = C.c_char_p
         L.shm3d_slab.argtypes = [vp, C.c_int32, i32p, i32p]
+        L.shm3d_slab_range.argtypes = [C.c_int32, C.c_int32, C.c_int32, i32p, i32p]
         L.shm3d_solve.argtypes = [vp, PP, C.c_int64, dp, dp, dp, dp, SP]
         L.shm3d_solve_device.argtypes = [vp, PP, C.c_int64, vp, vp, vp, vp, SP]
         L.shm3d_step12.argtypes = [vp, PP, C.c_int64, dp, dp, dp, fp, SP]
@@ -244,6 +245,14 @@ class Context:
         self._check(lib().shm3d_step3(self._h, C.byref(p), len(area), _dp(pos), _dp(area), _fp(b), _dp(phi),
                                       C.byref(st)))
         return phi, st
+
+
+def slab_range(rank, world, nz):
+    k0, k1 = C.c_int32(), C.c_int32()
+    rc = lib().shm3d_slab_range(rank, world, nz, C.byref(k0), C.byref(k1))
+    if rc != OK:
+        raise Shm3dError(rc, "bad rank/world/nz")
+    return k0.value, k1.value
 
 
 def nccl_unique_id() -> bytes:

@@ -1,0 +1,59 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "signed-heat-3d_b200"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fo, fv = z["face_offsets"], z["face_vertices"]
+    faces = [fv[fo[i]:fo[i + 1]].tolist() for i in range(len(fo) - 1)]
+    return z, faces
+
+
+def icosphere(subdiv=2, radius=1.0, center=(0.0, 0.0, 0.0)):
+    """Deterministic outward-oriented icosphere (20 * 4^subdiv triangles)."""
+    t = (1.0 + 5 ** 0.5) / 2.0
+    V = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    F = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11],
+                  [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    V /= np.linalg.norm(V[0])
+    for _ in range(subdiv):
+        cache = {}
+        verts = V.tolist()
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = (np.asarray(verts[a]) + np.asarray(verts[b])) / 2
+                verts.append((m / np.linalg.norm(m)).tolist())
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        newF = []
+        for a, b, c in F:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            newF += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        V = np.asarray(verts)
+        F = np.asarray(newF, dtype=np.int64)
+    return V * radius + np.asarray(center), F
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    import shm3d
+    ctx = shm3d.Context(0)
+    yield ctx
+    ctx.close()

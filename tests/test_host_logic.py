@@ -1,0 +1,130 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol, the host half
+of the reference interface (rows a4-a6) matches the oracle, constraint assembly and the nested-dissection
+factor match scipy, and the library fails loudly without a GPU.  No compute kernels run here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import shm3d
+from conftest import ROOT, icosphere, load_golden
+from oracle import shm_oracle as o
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "shm3d_grid.h")).read()
+    declared = set(re.findall(r"\b(shm3d_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"shm3d_ctx"}
+    L = ctypes.CDLL(shm3d.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/shm3d_grid.h but not exported"
+    assert set(shm3d.EXPORTS) <= declared
+    assert b"sm_100a" in shm3d.lib().shm3d_version()
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler produces for the two ABI structs (natural alignment)
+    assert ctypes.sizeof(shm3d.Params) == 88
+    assert ctypes.sizeof(shm3d.Stats) == 144
+
+
+@pytest.mark.parametrize("name,hc", [("bunny_small", 1), ("polygon-bear", 0), ("knot", 2)])
+def test_prepare_mesh_matches_oracle(name, hc):
+    z, F = load_golden(name)
+    s = o.mesh_sources(z["V"], F)
+    g = o.make_grid(s["centroid"], s["radius"], hc)
+    p, pos, nrm, area, h = shm3d.prepare_mesh(z["V"], F, hCoef=hc)
+    assert (p.nx, p.ny, p.nz) == (g.nx, g.ny, g.nz)
+    assert abs(p.cell - g.cell) < 1e-13 * g.cell and np.abs(np.array(p.bbox_min) - g.bmin).max() < 1e-12
+    assert abs(h - s["h"]) < 1e-12 and abs(p.lambda_ - o.lambda_from_h(s["h"])) < 1e-9
+    assert np.abs(pos - s["pos"]).max() < 1e-12 and np.abs(area - s["area"]).max() < 1e-12
+    assert np.abs(nrm - s["nrm"]).max() < 1e-9
+    assert p.flags & shm3d.FLAG_SCRUB_NONFINITE
+
+
+def test_fractional_hcoef_truncates_like_reference():
+    V, F = icosphere(1)
+    p, *_ = shm3d.prepare_mesh(V, F, hCoef=0.5)
+    assert p.nx == int(2 * 2 ** 3.5)  # (size_t)(2*2^(hCoef+3)), src/signed_heat_grid_solver.cpp:24
+
+
+@pytest.mark.parametrize("name,hc", [("bunny_small", 0), ("bunny_small", 1), ("knot", 2)])
+def test_constraint_rows_match_oracle(name, hc):
+    z, F = load_golden(name)
+    p, pos, *_ = shm3d.prepare_mesh(z["V"], F, hCoef=hc)
+    g = o.Grid(p.nx, p.ny, p.nz, np.array(p.bbox_min), p.cell)
+    src, node, w = shm3d.debug_constraints(p, pos)
+    src2, idx2, w2 = o.constraints(g, pos)
+    assert np.array_equal(src, src2) and np.array_equal(node, idx2)
+    assert np.abs(w - w2).max() < 1e-12
+    if f"h{hc}_m" in z:
+        assert len(src) == int(z[f"h{hc}_m"])
+
+
+def test_first_source_per_cell_wins_depends_on_order():
+    V, F = icosphere(2)
+    p, pos, *_ = shm3d.prepare_mesh(V, F, hCoef=0)
+    src, _, _ = shm3d.debug_constraints(p, pos)
+    src_r, _, _ = shm3d.debug_constraints(p, pos[::-1].copy())
+    assert len(src) == len(src_r) < len(pos)           # several barycentres share a cell at 16^3
+    assert not np.array_equal(np.sort(src), np.sort(len(pos) - 1 - src_r))
+
+
+def test_source_outside_grid_is_an_error():
+    V, F = icosphere(1)
+    p, pos, *_ = shm3d.prepare_mesh(V, F, hCoef=0)
+    bad = pos.copy()
+    bad[3] += 100.0
+    with pytest.raises(shm3d.Shm3dError) as e:
+        shm3d.debug_constraints(p, bad)
+    assert e.value.code == shm3d.ERR_INVALID_ARG
+
+
+@pytest.mark.parametrize("name,hc,uniform", [("bunny_small", 1, True), ("bunny_small", 1, False), ("knot", 3, True),
+                                             ("polygon-bear", 2, False)])
+def test_nested_dissection_factor_matches_scipy(name, hc, uniform):
+    z, F = load_golden(name)
+    p, pos, *_ = shm3d.prepare_mesh(z["V"], F, hCoef=hc)
+    g = o.Grid(p.nx, p.ny, p.nz, np.array(p.bbox_min), p.cell)
+    _, idx, w = o.constraints(g, pos)
+    A = o.constraint_matrix(g, idx, w)
+    if uniform:
+        S = (A @ A.T).tocsc()
+    else:
+        d = np.full(g.N, 6.0)  # constraints never touch the domain boundary here
+        S = (A @ sp.diags(1 / d) @ A.T).tocsc()
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(A.shape[0])
+    x, mb, height = shm3d.debug_factor_solve(p, pos, v, uniform)
+    xr = spla.splu(S).solve(v)
+    assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-9
+    assert height >= 1 and mb > 0
+
+
+def test_slab_ranges_tile_the_grid():
+    for nz in (16, 32, 100, 1024):
+        for world in (1, 2, 3, 4, 8):
+            edges = [shm3d.slab_range(r, world, nz) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == nz
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly (this box has none; on the GPU box the test is skipped)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(shm3d.Shm3dError) as e:
+        shm3d.Context(0)
+    assert e.value.code == shm3d.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
