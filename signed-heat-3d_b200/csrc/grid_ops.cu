@@ -7,8 +7,14 @@
 //
 // Layout: x-fastest float arrays; every vector that is read through a stencil is allocated with one ghost
 // plane below and above the local z-slab, and kernels receive the pointer to the first interior plane.
-// Reductions are fp64, deterministic: per-block partials, the last block to finish folds them in fixed order.
-#include <cooperative_groups.h>
+//
+// Kernel shape (B200): persistent grid (<= 8 CTAs of 256 threads per SM), grid-stride over "quads" of four
+// x-consecutive nodes moved as float4 (16 B per lane, coalesced 512 B per warp); y/z neighbours are float4 loads
+// of the adjacent rows/planes (L1/L2 hits: a 512^2 plane is 1 MB, the 126 MB L2 holds the working planes), the two
+// x-end neighbours are scalar loads of the adjacent quads.  Reductions are fp64 and deterministic: one partial
+// per CTA, the last CTA to finish (ticket) folds them in a fixed order -- with <= 1184 CTAs the single-address
+// ticket atomic is no longer the bottleneck it was with one CTA per 256 nodes.
+#include <algorithm>
 
 #include "kernels.cuh"
 
@@ -19,9 +25,9 @@ int64_t g_kernel_launches = 0;
 namespace {
 
 constexpr int kT = 256;
+constexpr int kMaxBlocks = 148 * 8;
 
 // ---------------------------------------------------------------- deterministic reduction helper
-// scratch layout per reduction site: partials[blocks*K], counter.
 struct RedScratch {
     double* partials;
     unsigned int* counter;
@@ -29,16 +35,10 @@ struct RedScratch {
 
 static double* g_partials = nullptr;
 static unsigned int* g_counter = nullptr;
-static size_t g_partials_cap = 0;
 
-RedScratch red_scratch(size_t blocks, int K) {
-    size_t need = blocks * (size_t)K;
-    if (need > g_partials_cap) {
-        if (g_partials) cudaFree(g_partials);
-        g_partials_cap = need * 2 + 1024;
-        SHM3D_CUDA_CHECK(cudaMalloc((void**)&g_partials, g_partials_cap * sizeof(double)));
-    }
-    if (!g_counter) {
+RedScratch red_scratch() {
+    if (!g_partials) {
+        SHM3D_CUDA_CHECK(cudaMalloc((void**)&g_partials, (size_t)kMaxBlocks * 4 * sizeof(double)));
         SHM3D_CUDA_CHECK(cudaMalloc((void**)&g_counter, sizeof(unsigned int)));
         SHM3D_CUDA_CHECK(cudaMemset(g_counter, 0, sizeof(unsigned int)));
     }
@@ -46,7 +46,7 @@ RedScratch red_scratch(size_t blocks, int K) {
 }
 
 template <int K>
-__device__ __forceinline__ void block_reduce_commit(double (&v)[K], RedScratch rs, double* out, bool accumulate) {
+__device__ __forceinline__ void block_reduce_commit(double (&v)[K], RedScratch rs, double* out) {
     __shared__ double s_w[K][kT / 32];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -86,194 +86,271 @@ __device__ __forceinline__ void block_reduce_commit(double (&v)[K], RedScratch r
                 double t = 0;
 #pragma unroll
                 for (int i = 0; i < kT / 32; i++) t += s_w[k][i];
-                out[k] = accumulate ? out[k] + t : t;
+                out[k] = t;
             }
         }
         if (threadIdx.x == 0) *rs.counter = 0;
     }
 }
 
-__device__ __forceinline__ void decode(size_t e, int nx, int ny, int& i, int& j, int& kl) {
-    size_t row = e / (size_t)nx;
-    i = (int)(e - row * (size_t)nx);
-    kl = (int)(row / (size_t)ny);
-    j = (int)(row - (size_t)kl * ny);
+// ---------------------------------------------------------------- vector access helpers (V = 4 or 1)
+template <int V>
+struct Vec;
+template <>
+struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ static Vec ld(const float* p) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        Vec r;
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+        return r;
+    }
+    __device__ __forceinline__ void st(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <>
+struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ static Vec ld(const float* p) { Vec r; r.v[0] = *p; return r; }
+    __device__ __forceinline__ void st(float* p) const { *p = v[0]; }
+};
+template <int V>
+__device__ __forceinline__ Vec<V> vzero() {
+    Vec<V> r;
+#pragma unroll
+    for (int t = 0; t < V; t++) r.v[t] = 0.f;
+    return r;
 }
 
-// K'u at one node, given the centre value.  u is an interior pointer (ghost planes addressable).
-__device__ __forceinline__ float stencil_at(const float* __restrict__ u, size_t idx, float c, int i, int j, int k,
-                                            const LevelDims& L) {
-    const size_t pl = (size_t)L.nx * L.ny;
-    float s = 0.f;
-    int cnt = 0;
-    if (i > 0) { s += u[idx - 1]; cnt++; }
-    if (i < L.nx - 1) { s += u[idx + 1]; cnt++; }
-    if (j > 0) { s += u[idx - L.nx]; cnt++; }
-    if (j < L.ny - 1) { s += u[idx + L.nx]; cnt++; }
-    if (k > 0) { s += u[idx - pl]; cnt++; }
-    if (k < L.nz - 1) { s += u[idx + pl]; cnt++; }
-    return (float)cnt * c - s;
+// element index -> (i0, j, kl) for the group starting at element e (e % V == 0, nx % V == 0)
+__device__ __forceinline__ void decode(unsigned int e, int nx, int ny, int& i, int& j, int& kl) {
+    unsigned int row = e / (unsigned int)nx;
+    i = (int)(e - row * (unsigned int)nx);
+    kl = (int)(row / (unsigned int)ny);
+    j = (int)(row - (unsigned int)kl * (unsigned int)ny);
 }
-__device__ __forceinline__ int diag_at(int i, int j, int k, const LevelDims& L) {
-    return (i > 0) + (i < L.nx - 1) + (j > 0) + (j < L.ny - 1) + (k > 0) + (k < L.nz - 1);
+
+// K'u for the V nodes starting at e, and the per-node diagonal (number of in-range neighbours)
+template <int V>
+__device__ __forceinline__ void stencil(const float* __restrict__ u, unsigned int e, const Vec<V>& c, int i0, int j, int k,
+                                        const LevelDims& L, Vec<V>& Ku, Vec<V>& dg) {
+    const unsigned int pl = (unsigned int)L.nx * (unsigned int)L.ny;
+    const bool ym = j > 0, yp = j < L.ny - 1, zm = k > 0, zp = k < L.nz - 1;
+    Vec<V> a = ym ? Vec<V>::ld(u + e - L.nx) : vzero<V>();
+    Vec<V> b = yp ? Vec<V>::ld(u + e + L.nx) : vzero<V>();
+    Vec<V> d = zm ? Vec<V>::ld(u + (ptrdiff_t)e - (ptrdiff_t)pl) : vzero<V>();
+    Vec<V> f = zp ? Vec<V>::ld(u + e + pl) : vzero<V>();
+    const float left = (i0 > 0) ? u[e - 1] : 0.f;
+    const float right = (i0 + V < L.nx) ? u[e + V] : 0.f;
+    const int cyz = (int)ym + (int)yp + (int)zm + (int)zp;
+#pragma unroll
+    for (int t = 0; t < V; t++) {
+        const int i = i0 + t;
+        const float xl = (t > 0) ? c.v[t - 1] : left;
+        const float xr = (t < V - 1) ? c.v[t + 1] : right;
+        const float cnt = (float)(cyz + (i > 0) + (i < L.nx - 1));
+        dg.v[t] = cnt;
+        Ku.v[t] = cnt * c.v[t] - (xl + xr + a.v[t] + b.v[t] + d.v[t] + f.v[t]);
+    }
 }
+
+#define GRID_STRIDE_GROUPS(L_, V_)                                                                   \
+    const unsigned int _ng = (unsigned int)((L_).n() / (V_));                                          \
+    for (unsigned int _g = blockIdx.x * kT + threadIdx.x; _g < _ng; _g += gridDim.x * kT)
 
 // ---------------------------------------------------------------- b = cell * D'^T Y
 __global__ void __launch_bounds__(kT) k_div_rhs(LevelDims L, float cell, const float* __restrict__ Y, size_t cs,
                                                 float* __restrict__ b, int scrub, unsigned int* nonfinite) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e >= L.n()) return;
-    int i, j, kl;
-    decode(e, L.nx, L.ny, i, j, kl);
-    const int k = L.k0 + kl;
-    const size_t pl = L.plane();
-    const float* Yx = Y;
-    const float* Yy = Y + cs;
-    const float* Yz = Y + 2 * cs;
-    // per axis, line index t of n nodes, g = Y_a:
-    //   b_t = [t>=1] g[t-1] - [t<=n-2] g[t] - [t==n-2] g[t+1] + [t==n-1] g[t]
-    float acc = 0.f;
-    {
-        float g = Yx[e];
-        if (i >= 1) acc += Yx[e - 1];
-        if (i <= L.nx - 2) acc -= g;
-        if (i == L.nx - 2) acc -= Yx[e + 1];
-        if (i == L.nx - 1) acc += g;
+    const size_t n = L.n();
+    for (size_t e = (size_t)blockIdx.x * kT + threadIdx.x; e < n; e += (size_t)gridDim.x * kT) {
+        size_t row = e / (size_t)L.nx;
+        const int i = (int)(e - row * (size_t)L.nx);
+        const int kl = (int)(row / (size_t)L.ny);
+        const int j = (int)(row - (size_t)kl * L.ny);
+        const int k = L.k0 + kl;
+        const size_t pl = L.plane();
+        const float* Yx = Y;
+        const float* Yy = Y + cs;
+        const float* Yz = Y + 2 * cs;
+        // per axis, line index t of n nodes, g = Y_a:
+        //   b_t = [t>=1] g[t-1] - [t<=n-2] g[t] - [t==n-2] g[t+1] + [t==n-1] g[t]
+        float acc = 0.f;
+        {
+            float g = Yx[e];
+            if (i >= 1) acc += Yx[e - 1];
+            if (i <= L.nx - 2) acc -= g;
+            if (i == L.nx - 2) acc -= Yx[e + 1];
+            if (i == L.nx - 1) acc += g;
+        }
+        {
+            float g = Yy[e];
+            if (j >= 1) acc += Yy[e - L.nx];
+            if (j <= L.ny - 2) acc -= g;
+            if (j == L.ny - 2) acc -= Yy[e + L.nx];
+            if (j == L.ny - 1) acc += g;
+        }
+        {
+            float g = Yz[e];
+            if (k >= 1) acc += Yz[e - pl];
+            if (k <= L.nz - 2) acc -= g;
+            if (k == L.nz - 2) acc -= Yz[e + pl];
+            if (k == L.nz - 1) acc += g;
+        }
+        float v = cell * acc;
+        if (!isfinite(v)) {
+            atomicAdd(nonfinite, 1u);
+            if (scrub) v = 0.f;
+        }
+        b[e] = v;
     }
-    {
-        float g = Yy[e];
-        if (j >= 1) acc += Yy[e - L.nx];
-        if (j <= L.ny - 2) acc -= g;
-        if (j == L.ny - 2) acc -= Yy[e + L.nx];
-        if (j == L.ny - 1) acc += g;
-    }
-    {
-        float g = Yz[e];
-        if (k >= 1) acc += Yz[e - pl];
-        if (k <= L.nz - 2) acc -= g;
-        if (k == L.nz - 2) acc -= Yz[e + pl];
-        if (k == L.nz - 1) acc += g;
-    }
-    float v = cell * acc;
-    if (!isfinite(v)) {
-        atomicAdd(nonfinite, 1u);
-        if (scrub) v = 0.f;
-    }
-    b[e] = v;
 }
 
-// ---------------------------------------------------------------- q = K'p, acc = sum p q
+// ---------------------------------------------------------------- q = K'p, out = sum p q
+template <int V>
 __global__ void __launch_bounds__(kT) k_stencil_dot(LevelDims L, const float* __restrict__ p, float* __restrict__ q,
                                                     RedScratch rs, double* out) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    double v[1] = {0.0};
-    if (e < L.n()) {
-        int i, j, kl;
-        decode(e, L.nx, L.ny, i, j, kl);
-        float c = p[e];
-        float r = stencil_at(p, e, c, i, j, L.k0 + kl, L);
-        q[e] = r;
-        v[0] = (double)c * (double)r;
+    double acc[1] = {0.0};
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        int i0, j, kl;
+        decode(e, L.nx, L.ny, i0, j, kl);
+        Vec<V> c = Vec<V>::ld(p + e), Ku, dg;
+        stencil<V>(p, e, c, i0, j, L.k0 + kl, L, Ku, dg);
+        Ku.st(q + e);
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < V; t++) s = fmaf(c.v[t], Ku.v[t], s);
+        acc[0] += (double)s;
     }
-    block_reduce_commit<1>(v, rs, out, false);
+    block_reduce_commit<1>(acc, rs, out);
 }
 
-// ---------------------------------------------------------------- x += a p, r -= a q, acc = sum r
-__global__ void __launch_bounds__(kT) k_update_xr(size_t n, float* __restrict__ x, float* __restrict__ r,
+// ---------------------------------------------------------------- x += a p, r -= a q, out = sum r
+template <int V>
+__global__ void __launch_bounds__(kT) k_update_xr(LevelDims L, float* __restrict__ x, float* __restrict__ r,
                                                   const float* __restrict__ p, const float* __restrict__ q,
                                                   const double* rho, const double* pq, RedScratch rs, double* out) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
     const float a = (float)(*rho / *pq);
-    double v[1] = {0.0};
-    if (e < n) {
-        x[e] = fmaf(a, p[e], x[e]);
-        float rr = fmaf(-a, q[e], r[e]);
-        r[e] = rr;
-        v[0] = rr;
+    double acc[1] = {0.0};
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        Vec<V> xv = Vec<V>::ld(x + e), rv = Vec<V>::ld(r + e), pv = Vec<V>::ld(p + e), qv = Vec<V>::ld(q + e);
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            xv.v[t] = fmaf(a, pv.v[t], xv.v[t]);
+            rv.v[t] = fmaf(-a, qv.v[t], rv.v[t]);
+            s += rv.v[t];
+        }
+        xv.st(x + e);
+        rv.st(r + e);
+        acc[0] += (double)s;
     }
-    block_reduce_commit<1>(v, rs, out, false);
+    block_reduce_commit<1>(acc, rs, out);
 }
 
-__global__ void __launch_bounds__(kT) k_dot_rz(size_t n, const float* __restrict__ r, const float* __restrict__ z,
+template <int V>
+__global__ void __launch_bounds__(kT) k_dot_rz(LevelDims L, const float* __restrict__ r, const float* __restrict__ z,
                                                RedScratch rs, double* out) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    double v[2] = {0.0, 0.0};
-    if (e < n) {
-        float zz = z[e];
-        v[0] = (double)r[e] * (double)zz;
-        v[1] = zz;
+    double acc[2] = {0.0, 0.0};
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        Vec<V> rv = Vec<V>::ld(r + e), zv = Vec<V>::ld(z + e);
+        float s = 0.f, sz = 0.f;
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            s = fmaf(rv.v[t], zv.v[t], s);
+            sz += zv.v[t];
+        }
+        acc[0] += (double)s;
+        acc[1] += (double)sz;
     }
-    block_reduce_commit<2>(v, rs, out, false);
+    block_reduce_commit<2>(acc, rs, out);
 }
 
-__global__ void __launch_bounds__(kT) k_update_p(size_t n, float* __restrict__ p, const float* __restrict__ z,
+template <int V>
+__global__ void __launch_bounds__(kT) k_update_p(LevelDims L, float* __restrict__ p, const float* __restrict__ z,
                                                  const double* sum_z, double n_global, const double* rho_new,
                                                  const double* rho_old, int first) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e >= n) return;
     const float mean = (float)(*sum_z / n_global);
-    float g = z[e] - mean;
-    if (first) {
-        p[e] = g;
-    } else {
-        const float beta = (float)(*rho_new / *rho_old);
-        p[e] = fmaf(beta, p[e], g);
+    const float beta = first ? 0.f : (float)(*rho_new / *rho_old);
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        Vec<V> zv = Vec<V>::ld(z + e), pv = first ? vzero<V>() : Vec<V>::ld(p + e);
+#pragma unroll
+        for (int t = 0; t < V; t++) pv.v[t] = fmaf(beta, pv.v[t], zv.v[t] - mean);
+        pv.st(p + e);
     }
 }
 
 __global__ void __launch_bounds__(kT) k_fill(float* p, size_t n, float v) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e < n) p[e] = v;
+    for (size_t e = (size_t)blockIdx.x * kT + threadIdx.x; e < n; e += (size_t)gridDim.x * kT) p[e] = v;
 }
 __global__ void __launch_bounds__(kT) k_copy(float* d, const float* s, size_t n) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e < n) d[e] = s[e];
+    for (size_t e = (size_t)blockIdx.x * kT + threadIdx.x; e < n; e += (size_t)gridDim.x * kT) d[e] = s[e];
 }
 __global__ void __launch_bounds__(kT) k_vec_sum(const float* v, size_t n, RedScratch rs, double* out) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    double a[1] = {e < n ? (double)v[e] : 0.0};
-    block_reduce_commit<1>(a, rs, out, false);
+    double a[1] = {0.0};
+    for (size_t e = (size_t)blockIdx.x * kT + threadIdx.x; e < n; e += (size_t)gridDim.x * kT) a[0] += (double)v[e];
+    block_reduce_commit<1>(a, rs, out);
 }
 __global__ void __launch_bounds__(kT) k_axpy_const(float* v, size_t n, const double* num, double den, float sign) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e < n) v[e] += sign * (float)(*num / den);
+    const float a = sign * (float)(*num / den);
+    for (size_t e = (size_t)blockIdx.x * kT + threadIdx.x; e < n; e += (size_t)gridDim.x * kT) v[e] += a;
 }
 
 // ---------------------------------------------------------------- multigrid
+template <int V>
 __global__ void __launch_bounds__(kT) k_mg_smooth0(LevelDims L, float* __restrict__ x, const float* __restrict__ b,
                                                    const double* sum_b, double n_global, float omega) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e >= L.n()) return;
-    int i, j, kl;
-    decode(e, L.nx, L.ny, i, j, kl);
     const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
-    x[e] = omega * (b[e] - shift) / (float)diag_at(i, j, L.k0 + kl, L);
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        int i0, j, kl;
+        decode(e, L.nx, L.ny, i0, j, kl);
+        const int k = L.k0 + kl;
+        const int cyz = (j > 0) + (j < L.ny - 1) + (k > 0) + (k < L.nz - 1);
+        Vec<V> bv = Vec<V>::ld(b + e), xv;
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            const int i = i0 + t;
+            xv.v[t] = omega * (bv.v[t] - shift) / (float)(cyz + (i > 0) + (i < L.nx - 1));
+        }
+        xv.st(x + e);
+    }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kT) k_mg_smooth(LevelDims L, float* __restrict__ xo, const float* __restrict__ x,
                                                   const float* __restrict__ b, const double* sum_b, double n_global,
                                                   float omega) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e >= L.n()) return;
-    int i, j, kl;
-    decode(e, L.nx, L.ny, i, j, kl);
     const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
-    const int k = L.k0 + kl;
-    float c = x[e];
-    float Kx = stencil_at(x, e, c, i, j, k, L);
-    xo[e] = c + omega * ((b[e] - shift) - Kx) / (float)diag_at(i, j, k, L);
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        int i0, j, kl;
+        decode(e, L.nx, L.ny, i0, j, kl);
+        Vec<V> c = Vec<V>::ld(x + e), bv = Vec<V>::ld(b + e), Ku, dg, o;
+        stencil<V>(x, e, c, i0, j, L.k0 + kl, L, Ku, dg);
+#pragma unroll
+        for (int t = 0; t < V; t++) o.v[t] = c.v[t] + omega * ((bv.v[t] - shift) - Ku.v[t]) / dg.v[t];
+        o.st(xo + e);
+    }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kT) k_mg_residual(LevelDims L, const float* __restrict__ x,
                                                     const float* __restrict__ b, const double* sum_b, double n_global,
                                                     float* __restrict__ r) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e >= L.n()) return;
-    int i, j, kl;
-    decode(e, L.nx, L.ny, i, j, kl);
     const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
-    float c = x[e];
-    r[e] = (b[e] - shift) - stencil_at(x, e, c, i, j, L.k0 + kl, L);
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        int i0, j, kl;
+        decode(e, L.nx, L.ny, i0, j, kl);
+        Vec<V> c = Vec<V>::ld(x + e), bv = Vec<V>::ld(b + e), Ku, dg, o;
+        stencil<V>(x, e, c, i0, j, L.k0 + kl, L, Ku, dg);
+#pragma unroll
+        for (int t = 0; t < V; t++) o.v[t] = (bv.v[t] - shift) - Ku.v[t];
+        o.st(r + e);
+    }
 }
 
 // 1D restriction weights of the transposed clamped trilinear prolongation: coarse I gathers fine 2I-1..2I+2
@@ -286,58 +363,68 @@ __device__ __forceinline__ void rweights(int I, int nc, float (&wt)[4]) {
 
 __global__ void __launch_bounds__(kT) k_mg_restrict(LevelDims Lf, LevelDims Lc, const float* __restrict__ r,
                                                     float* __restrict__ bc) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e >= Lc.n()) return;
-    int I, J, Kl;
-    decode(e, Lc.nx, Lc.ny, I, J, Kl);
-    const int K = Lc.k0 + Kl;
-    float wx[4], wy[4], wz[4];
-    rweights(I, Lc.nx, wx);
-    rweights(J, Lc.ny, wy);
-    rweights(K, Lc.nz, wz);
-    const size_t plf = Lf.plane();
-    float acc = 0.f;
+    const unsigned int nc = (unsigned int)Lc.n();
+    for (unsigned int e = blockIdx.x * kT + threadIdx.x; e < nc; e += gridDim.x * kT) {
+        int I, J, Kl;
+        decode(e, Lc.nx, Lc.ny, I, J, Kl);
+        const int K = Lc.k0 + Kl;
+        float wx[4], wy[4], wz[4];
+        rweights(I, Lc.nx, wx);
+        rweights(J, Lc.ny, wy);
+        rweights(K, Lc.nz, wz);
+        const ptrdiff_t plf = (ptrdiff_t)Lf.plane();
+        float acc = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        if (wz[c] == 0.f) continue;
-        const int kf = 2 * K - 1 + c - Lf.k0;  // local fine plane (may be a ghost plane: -1 or nzl)
+        for (int c = 0; c < 4; c++) {
+            if (wz[c] == 0.f) continue;
+            const int kf = 2 * K - 1 + c - Lf.k0;  // local fine plane (may be a ghost plane: -1 or nzl)
 #pragma unroll
-        for (int bq = 0; bq < 4; bq++) {
-            if (wy[bq] == 0.f) continue;
-            const int jf = 2 * J - 1 + bq;
-            const float* row = r + (ptrdiff_t)kf * (ptrdiff_t)plf + (size_t)jf * Lf.nx;
-            float s = 0.f;
+            for (int bq = 0; bq < 4; bq++) {
+                if (wy[bq] == 0.f) continue;
+                const int jf = 2 * J - 1 + bq;
+                const float* row = r + (ptrdiff_t)kf * plf + (ptrdiff_t)jf * Lf.nx;
+                float s = 0.f;
 #pragma unroll
-            for (int a = 0; a < 4; a++) {
-                if (wx[a] == 0.f) continue;
-                s = fmaf(wx[a], row[2 * I - 1 + a], s);
+                for (int a = 0; a < 4; a++) {
+                    if (wx[a] == 0.f) continue;
+                    s = fmaf(wx[a], row[2 * I - 1 + a], s);
+                }
+                acc = fmaf(wy[bq] * wz[c], s, acc);
             }
-            acc = fmaf(wy[bq] * wz[c], s, acc);
         }
+        bc[e] = 0.5f * acc;
     }
-    bc[e] = 0.5f * acc;
 }
 
+template <int V>
 __global__ void __launch_bounds__(kT) k_mg_prolong_add(LevelDims Lf, LevelDims Lc, float* __restrict__ x,
                                                        const float* __restrict__ ec) {
-    size_t e = (size_t)blockIdx.x * kT + threadIdx.x;
-    if (e >= Lf.n()) return;
-    int i, j, kl;
-    decode(e, Lf.nx, Lf.ny, i, j, kl);
-    const int k = Lf.k0 + kl;
-    const int I0 = i >> 1, J0 = j >> 1, K0 = k >> 1;
-    const int I1 = min(max((i & 1) ? I0 + 1 : I0 - 1, 0), Lc.nx - 1);
-    const int J1 = min(max((j & 1) ? J0 + 1 : J0 - 1, 0), Lc.ny - 1);
-    const int K1 = min(max((k & 1) ? K0 + 1 : K0 - 1, 0), Lc.nz - 1);
-    const ptrdiff_t plc = (ptrdiff_t)Lc.plane();
-    const float* a0 = ec + (ptrdiff_t)(K0 - Lc.k0) * plc;
-    const float* a1 = ec + (ptrdiff_t)(K1 - Lc.k0) * plc;  // may be a ghost plane
-    auto at = [&](const float* pl, int J, int I) { return pl[(size_t)J * Lc.nx + I]; };
-    float v0 = 0.75f * (0.75f * at(a0, J0, I0) + 0.25f * at(a0, J0, I1)) +
-               0.25f * (0.75f * at(a0, J1, I0) + 0.25f * at(a0, J1, I1));
-    float v1 = 0.75f * (0.75f * at(a1, J0, I0) + 0.25f * at(a1, J0, I1)) +
-               0.25f * (0.75f * at(a1, J1, I0) + 0.25f * at(a1, J1, I1));
-    x[e] += 0.75f * v0 + 0.25f * v1;
+    GRID_STRIDE_GROUPS(Lf, V) {
+        const unsigned int e = _g * V;
+        int i0, j, kl;
+        decode(e, Lf.nx, Lf.ny, i0, j, kl);
+        const int k = Lf.k0 + kl;
+        const int J0 = j >> 1, K0 = k >> 1;
+        const int J1 = min(max((j & 1) ? J0 + 1 : J0 - 1, 0), Lc.ny - 1);
+        const int K1 = min(max((k & 1) ? K0 + 1 : K0 - 1, 0), Lc.nz - 1);
+        const ptrdiff_t plc = (ptrdiff_t)Lc.plane();
+        const float* r00 = ec + (ptrdiff_t)(K0 - Lc.k0) * plc + (ptrdiff_t)J0 * Lc.nx;
+        const float* r01 = ec + (ptrdiff_t)(K0 - Lc.k0) * plc + (ptrdiff_t)J1 * Lc.nx;
+        const float* r10 = ec + (ptrdiff_t)(K1 - Lc.k0) * plc + (ptrdiff_t)J0 * Lc.nx;  // may be a ghost plane
+        const float* r11 = ec + (ptrdiff_t)(K1 - Lc.k0) * plc + (ptrdiff_t)J1 * Lc.nx;
+        Vec<V> xv = Vec<V>::ld(x + e);
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            const int i = i0 + t;
+            const int I0 = i >> 1;
+            const int I1 = min(max((i & 1) ? I0 + 1 : I0 - 1, 0), Lc.nx - 1);
+            // y/z-interpolated coarse values at columns I0 and I1
+            const float c0 = 0.75f * (0.75f * r00[I0] + 0.25f * r01[I0]) + 0.25f * (0.75f * r10[I0] + 0.25f * r11[I0]);
+            const float c1 = 0.75f * (0.75f * r00[I1] + 0.25f * r01[I1]) + 0.25f * (0.75f * r10[I1] + 0.25f * r11[I1]);
+            xv.v[t] += 0.75f * c0 + 0.25f * c1;
+        }
+        xv.st(x + e);
+    }
 }
 
 // coarsest level: dense pseudo-inverse matvec, one CTA (n3 <= 512)
@@ -354,7 +441,11 @@ __global__ void __launch_bounds__(512) k_mg_coarse(int n3, const float* __restri
     }
 }
 
-inline unsigned int nblk(size_t n) { return (unsigned int)((n + kT - 1) / kT); }
+inline unsigned int nblk(size_t groups) {
+    size_t b = (groups + kT - 1) / kT;
+    return (unsigned int)std::max<size_t>(1, std::min<size_t>(b, kMaxBlocks));
+}
+inline bool vec4(const LevelDims& L) { return (L.nx % 4) == 0; }
 
 }  // namespace
 
@@ -362,30 +453,34 @@ inline unsigned int nblk(size_t n) { return (unsigned int)((n + kT - 1) / kT); }
     SHM3D_LAUNCHED(); \
     SHM3D_CUDA_CHECK(cudaGetLastError())
 
+// dispatch on the vector width
+#define VDISPATCH(L_, kern, ...)                                                    \
+    do {                                                                            \
+        if (vec4(L_)) kern<4><<<nblk((L_).n() / 4), kT, 0, s>>>(__VA_ARGS__);       \
+        else kern<1><<<nblk((L_).n()), kT, 0, s>>>(__VA_ARGS__);                    \
+    } while (0)
+
 void launch_div_rhs(const LevelDims& L, float cell, const float* Y, size_t cs, float* b, int scrub,
                     unsigned int* nonfinite_count, cudaStream_t s) {
     k_div_rhs<<<nblk(L.n()), kT, 0, s>>>(L, cell, Y, cs, b, scrub, nonfinite_count);
     POST();
 }
 void launch_stencil_dot(const LevelDims& L, const float* p, float* q, double* acc, cudaStream_t s) {
-    unsigned int nb = nblk(L.n());
-    k_stencil_dot<<<nb, kT, 0, s>>>(L, p, q, red_scratch(nb, 1), acc);
+    VDISPATCH(L, k_stencil_dot, L, p, q, red_scratch(), acc);
     POST();
 }
 void launch_update_xr(const LevelDims& L, float* x, float* r, const float* p, const float* q, const double* rho,
                       const double* pq, double* acc_sum_r, cudaStream_t s) {
-    unsigned int nb = nblk(L.n());
-    k_update_xr<<<nb, kT, 0, s>>>(L.n(), x, r, p, q, rho, pq, red_scratch(nb, 1), acc_sum_r);
+    VDISPATCH(L, k_update_xr, L, x, r, p, q, rho, pq, red_scratch(), acc_sum_r);
     POST();
 }
 void launch_dot_rz(const LevelDims& L, const float* r, const float* z, double* acc, cudaStream_t s) {
-    unsigned int nb = nblk(L.n());
-    k_dot_rz<<<nb, kT, 0, s>>>(L.n(), r, z, red_scratch(nb, 2), acc);
+    VDISPATCH(L, k_dot_rz, L, r, z, red_scratch(), acc);
     POST();
 }
 void launch_update_p(const LevelDims& L, float* p, const float* z, const double* sum_z, double n_global,
                      const double* rho_new, const double* rho_old, int first, cudaStream_t s) {
-    k_update_p<<<nblk(L.n()), kT, 0, s>>>(L.n(), p, z, sum_z, n_global, rho_new, rho_old, first);
+    VDISPATCH(L, k_update_p, L, p, z, sum_z, n_global, rho_new, rho_old, first);
     POST();
 }
 void launch_fill(float* p, size_t n, float v, cudaStream_t s) {
@@ -399,8 +494,7 @@ void launch_copy(float* dst, const float* src, size_t n, cudaStream_t s) {
     POST();
 }
 void launch_vec_sum(const float* v, size_t n, double* acc, cudaStream_t s) {
-    unsigned int nb = nblk(n);
-    k_vec_sum<<<nb, kT, 0, s>>>(v, n, red_scratch(nb, 1), acc);
+    k_vec_sum<<<nblk(n), kT, 0, s>>>(v, n, red_scratch(), acc);
     POST();
 }
 void launch_axpy_const(float* v, size_t n, const double* num, double den, float sign, cudaStream_t s) {
@@ -409,17 +503,17 @@ void launch_axpy_const(float* v, size_t n, const double* num, double den, float 
 }
 void launch_mg_smooth0(const LevelDims& L, float* x, const float* b, const double* sum_b, double n_global, float omega,
                        cudaStream_t s) {
-    k_mg_smooth0<<<nblk(L.n()), kT, 0, s>>>(L, x, b, sum_b, n_global, omega);
+    VDISPATCH(L, k_mg_smooth0, L, x, b, sum_b, n_global, omega);
     POST();
 }
 void launch_mg_smooth(const LevelDims& L, float* xo, const float* x, const float* b, const double* sum_b,
                       double n_global, float omega, cudaStream_t s) {
-    k_mg_smooth<<<nblk(L.n()), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega);
+    VDISPATCH(L, k_mg_smooth, L, xo, x, b, sum_b, n_global, omega);
     POST();
 }
 void launch_mg_residual(const LevelDims& L, const float* x, const float* b, const double* sum_b, double n_global,
                         float* r, cudaStream_t s) {
-    k_mg_residual<<<nblk(L.n()), kT, 0, s>>>(L, x, b, sum_b, n_global, r);
+    VDISPATCH(L, k_mg_residual, L, x, b, sum_b, n_global, r);
     POST();
 }
 void launch_mg_restrict(const LevelDims& Lf, const LevelDims& Lc, const float* r, float* bc, cudaStream_t s) {
@@ -427,7 +521,7 @@ void launch_mg_restrict(const LevelDims& Lf, const LevelDims& Lc, const float* r
     POST();
 }
 void launch_mg_prolong_add(const LevelDims& Lf, const LevelDims& Lc, float* x, const float* ec, cudaStream_t s) {
-    k_mg_prolong_add<<<nblk(Lf.n()), kT, 0, s>>>(Lf, Lc, x, ec);
+    VDISPATCH(Lf, k_mg_prolong_add, Lf, Lc, x, ec);
     POST();
 }
 void launch_mg_coarse_solve(int n3, const float* pinv, const float* b, float* x, cudaStream_t s) {

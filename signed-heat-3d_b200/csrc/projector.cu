@@ -10,6 +10,8 @@
 #include <thread>
 #include <unordered_map>
 
+#include <cooperative_groups.h>
+
 #include "projector.cuh"
 
 namespace shm3d {
@@ -339,6 +341,100 @@ __global__ void k_proj_scatter(int n_touched, const int64_t* __restrict__ tnode,
     v[n] = (float)((double)v[n] - acc);
 }
 
+
+// Single-launch projector application: gather, forward sweep, backward sweep and scatter in one cooperative
+// kernel, with grid-wide barriers between the levels of the elimination tree (replaces ~2*height+2 launches).
+struct FusedArgs {
+    int m, n_touched, n_levels;
+    const int64_t* rnode;
+    const double* rw;
+    const int* rperm;
+    const ProjLevelInfo* levels;
+    const int* rowmaps;
+    const ProjNodeDesc* nodes;
+    const double* mat;
+    const int* bidx;
+    const int64_t* tnode;
+    const int* tptr;
+    const int* trow;
+    const double* tw;
+    double *rhs, *y, *sol;
+};
+
+__global__ void __launch_bounds__(512, 1) k_proj_fused(FusedArgs A, float* v, const float* w, const double* shift_num,
+                                                        double shift_den) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, gwarp = tid >> 5, nwarps = nthreads >> 5;
+    // gather: rhs = A (v - w - shift)
+    const double shift = shift_num ? *shift_num / shift_den : 0.0;
+    for (int r = tid; r < A.m; r += nthreads) {
+        double acc = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            int64_t n = A.rnode[(size_t)r * 8 + c];
+            if (n >= 0) {
+                double val = (double)v[n] - shift;
+                if (w) val -= (double)w[n];
+                acc += A.rw[(size_t)r * 8 + c] * val;
+            }
+        }
+        A.rhs[A.rperm[r]] = acc;
+    }
+    grid.sync();
+    // forward sweep, leaves first
+    for (int h = 0; h < A.n_levels; h++) {
+        const ProjLevelInfo li = A.levels[h];
+        const int* row_node = A.rowmaps + li.fwd_node;
+        const int* row_local = A.rowmaps + li.fwd_local;
+        for (int R = gwarp; R < li.n_fwd; R += nwarps) {
+            const ProjNodeDesc nd = A.nodes[row_node[R]];
+            const int rl = row_local[R];
+            const double* row = A.mat + nd.fwd + (long long)rl * nd.s;
+            const double* x = A.rhs + nd.s0;
+            double acc = 0;
+            const int cend = rl < nd.s ? rl + 1 : nd.s;
+            for (int c = lane; c < cend; c += 32) acc += row[c] * x[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                if (rl < nd.s)
+                    A.y[nd.s0 + rl] = acc;
+                else
+                    atomicAdd(&A.rhs[A.bidx[nd.bidx + rl - nd.s]], -acc);
+            }
+        }
+        grid.sync();
+    }
+    // backward sweep, root first
+    for (int h = A.n_levels - 1; h >= 0; h--) {
+        const ProjLevelInfo li = A.levels[h];
+        const int* row_node = A.rowmaps + li.bwd_node;
+        const int* row_local = A.rowmaps + li.bwd_local;
+        for (int R = gwarp; R < li.n_bwd; R += nwarps) {
+            const ProjNodeDesc nd = A.nodes[row_node[R]];
+            const int rl = row_local[R];
+            const int f = nd.s + nd.b;
+            const double* row = A.mat + nd.bwd + (long long)rl * f;
+            double acc = 0;
+            for (int c = rl + lane; c < nd.s; c += 32) acc += row[c] * A.y[nd.s0 + c];
+            const int* bi = A.bidx + nd.bidx;
+            for (int c = lane; c < nd.b; c += 32) acc += row[nd.s + c] * A.sol[bi[c]];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) A.sol[nd.s0 + rl] = acc;
+        }
+        grid.sync();
+    }
+    // scatter: v -= D^-1 A^T sol
+    for (int t = tid; t < A.n_touched; t += nthreads) {
+        double acc = 0;
+        for (int e = A.tptr[t]; e < A.tptr[t + 1]; e++) acc += A.tw[e] * A.sol[A.trow[e]];
+        int64_t n = A.tnode[t];
+        v[n] = (float)((double)v[n] - acc);
+    }
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -358,6 +454,7 @@ Projector::~Projector() {
     cudaFree(d_rhs_);
     cudaFree(d_y_);
     cudaFree(d_sol_);
+    cudaFree(d_levels_);
 }
 
 template <typename T>
@@ -625,7 +722,9 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
     if (m_ == 0) return;
     const int m = m_;
     HostFactor hf;
+    const double tb0 = wall();
     factor_constraints(rows, L.nx, L.ny, L.nz, uniform, hf);
+    const double tb1 = wall();
     all_interior_ = hf.all_interior;
     perm_ = hf.perm;
     factor_bytes_ = hf.mat.size() * sizeof(double);
@@ -667,6 +766,25 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
         fwd_levels_[h].row_local = d_rowmaps_ + offs[4 * h + 1];
     }
     bwd_off_.assign(offs.begin(), offs.end());
+    {
+        std::vector<ProjLevelInfo> li(max_h + 1);
+        for (int h = 0; h <= max_h; h++) {
+            li[h].n_fwd = fwd_levels_[h].n_rows;
+            li[h].n_bwd = fwd_levels_[h].n_nodes;
+            li[h].fwd_node = (long long)offs[4 * h];
+            li[h].fwd_local = (long long)offs[4 * h + 1];
+            li[h].bwd_node = (long long)offs[4 * h + 2];
+            li[h].bwd_local = (long long)offs[4 * h + 3];
+        }
+        d_levels_ = to_device(li, stream);
+        n_levels_ = max_h + 1;
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proj_fused, 512, 0);
+        coop_blocks_ = (coop && per_sm > 0 && !getenv("SHM3D_NO_FUSED_PROJ")) ? sms : 0;
+    }
 
     // ---- upload rows (local node indices), transpose, factor
     const int64_t lo = (int64_t)L.k0 * pl, hi = (int64_t)L.k1 * pl;
@@ -709,7 +827,11 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
     SHM3D_CUDA_CHECK(cudaMalloc((void**)&d_rhs_, (size_t)m * sizeof(double)));
     SHM3D_CUDA_CHECK(cudaMalloc((void**)&d_y_, (size_t)m * sizeof(double)));
     SHM3D_CUDA_CHECK(cudaMalloc((void**)&d_sol_, (size_t)m * sizeof(double)));
+    const double tb2 = wall();
     SHM3D_CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors go out of scope
+    if (getenv("SHM3D_DEBUG"))
+        fprintf(stderr, "[shm3d] projector m=%d: factor %.1f ms, maps+upload issue %.1f ms, sync %.1f ms\n", m,
+                (tb1 - tb0) * 1e3, (tb2 - tb1) * 1e3, (wall() - tb2) * 1e3);
 }
 
 void Projector::gather(const float* v, const float* w, const double* shift_num, double shift_den,
@@ -749,8 +871,35 @@ void Projector::scatter_sub(float* v, cudaStream_t s) const {
     SHM3D_LAUNCHED();
 }
 
+void Projector::apply_fused(float* v, const float* w, const double* shift_num, double shift_den,
+                            cudaStream_t s) const {
+    FusedArgs A;
+    A.m = m_;
+    A.n_touched = n_touched_;
+    A.n_levels = n_levels_;
+    A.rnode = d_rnode_;
+    A.rw = d_rw_;
+    A.rperm = d_rperm_;
+    A.levels = d_levels_;
+    A.rowmaps = d_rowmaps_;
+    A.nodes = d_nodes_;
+    A.mat = d_mat_;
+    A.bidx = d_bidx_;
+    A.tnode = d_tnode_;
+    A.tptr = d_tptr_;
+    A.trow = d_trow_;
+    A.tw = d_tw_;
+    A.rhs = d_rhs_;
+    A.y = d_y_;
+    A.sol = d_sol_;
+    void* args[] = {(void*)&A, (void*)&v, (void*)&w, (void*)&shift_num, (void*)&shift_den};
+    SHM3D_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_proj_fused, dim3(coop_blocks_), dim3(512), args, 0, s));
+    SHM3D_LAUNCHED();
+}
+
 void Projector::apply(float* v, cudaStream_t s) const {
     if (!m_) return;
+    if (coop_blocks_ && !reduce_hook_) return apply_fused(v, nullptr, nullptr, 1.0, s);
     gather(v, nullptr, nullptr, 1.0, s);
     solve(s);
     scatter_sub(v, s);
@@ -758,7 +907,16 @@ void Projector::apply(float* v, cudaStream_t s) const {
 
 void Projector::apply_update(float* v, const float* w, cudaStream_t s) const {
     if (!m_) return;
+    if (coop_blocks_ && !reduce_hook_) return apply_fused(v, w, nullptr, 1.0, s);
     gather(v, w, nullptr, 1.0, s);
+    solve(s);
+    scatter_sub(v, s);
+}
+
+void Projector::apply_shifted(float* v, const double* shift_num, double shift_den, cudaStream_t s) const {
+    if (!m_) return;
+    if (coop_blocks_ && !reduce_hook_) return apply_fused(v, nullptr, shift_num, shift_den, s);
+    gather(v, nullptr, shift_num, shift_den, s);
     solve(s);
     scatter_sub(v, s);
 }

@@ -52,6 +52,12 @@ struct HostFactor {
 };
 void factor_constraints(const ConstraintRows& rows, int nx, int ny, int nz, bool uniform, HostFactor& out);
 
+// per tree height: row maps of the forward (f rows per supernode) and backward (s rows) sweeps
+struct ProjLevelInfo {
+    int n_fwd, n_bwd;
+    long long fwd_node, fwd_local, bwd_node, bwd_local;  // offsets into the row-map array
+};
+
 // Device-resident projector for one level.
 class Projector {
   public:
@@ -73,6 +79,8 @@ class Projector {
     void apply(float* v, cudaStream_t s) const;
     // v <- v - D^-1 A^T (A D^-1 A^T)^-1 A (v - w): projects the UPDATE v - w (w = previous iterate)
     void apply_update(float* v, const float* w, cudaStream_t s) const;
+    // v <- v - D^-1 A^T (A D^-1 A^T)^-1 A (v - shift), shift = *shift_num / shift_den (rows of A sum to one)
+    void apply_shifted(float* v, const double* shift_num, double shift_den, cudaStream_t s) const;
     // lam <- (A D^-1 A^T)^-1 (A v): multipliers only (diagnostics / tests); lam_host has m entries in row order
     void multipliers(const float* v, std::vector<double>& lam_host, cudaStream_t s) const;
     // weighted source average helper is elsewhere (solver.cu)
@@ -115,6 +123,10 @@ class Projector {
     mutable double* d_sol_ = nullptr;
     std::vector<int> perm_;  // row -> permuted index
     std::vector<size_t> bwd_off_;
+    ProjLevelInfo* d_levels_ = nullptr;  // [tree height] for the fused single-launch path
+    int n_levels_ = 0;
+    int coop_blocks_ = 0;                // co-resident grid size of k_proj_fused (0: unavailable)
+    void apply_fused(float* v, const float* w, const double* shift_num, double shift_den, cudaStream_t s) const;
 
   public:
     // multi-GPU: called on the gathered partial sums A v (m doubles on device) before the solve (allreduce)

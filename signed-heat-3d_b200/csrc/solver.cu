@@ -6,6 +6,7 @@
 //   Step 3     constrained multigrid-PCG    <- :80-108 (same KKT system, solved in the null space of A)
 //   shift      k_source_average             <- :110-111, :466-496
 // No CPU fallback exists: every entry point needs a CUDA device.
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -433,47 +434,63 @@ struct Solver {
     // ---------------------------------------------------------------- multigrid hierarchy + constraints
     void build_levels() {
         double t0 = now_ms();
+        const bool dbg = getenv("SHM3D_DEBUG") != nullptr;
         std::vector<MGLevel>& lv = c->levels;
-        lv.clear();
-        lv.emplace_back();
-        lv[0].L = L0;
-        for (int a = 0; a < 3; a++) lv[0].bmin[a] = G.bmin[a];
-        lv[0].cell = G.cell;
+        // level geometry (buffers of a previous call with the same shape are reused)
+        std::vector<LevelDims> dims;
+        std::vector<std::array<double, 4>> geo;  // bmin xyz, cell
+        dims.push_back(L0);
+        geo.push_back({G.bmin[0], G.bmin[1], G.bmin[2], G.cell});
         if (use_mg) {
             while (true) {
-                const LevelDims Lf = lv.back().L;
+                const LevelDims Lf = dims.back();
                 if ((size_t)Lf.nx * Lf.ny * Lf.nz <= 64) break;  // small enough for the dense coarse solve
                 if ((Lf.nx | Lf.ny | Lf.nz) & 1) break;
                 if (Lf.nx / 2 < 4 || Lf.ny / 2 < 4 || Lf.nz / 2 < 4) break;
                 if ((Lf.k0 & 1) || (Lf.k1 & 1)) break;  // slab boundaries must coarsen cleanly
-                MGLevel cl;
-                cl.L = LevelDims{Lf.nx / 2, Lf.ny / 2, Lf.nz / 2, Lf.k0 / 2, Lf.k1 / 2};
-                for (int a = 0; a < 3; a++) cl.bmin[a] = lv.back().bmin[a] + 0.5 * lv.back().cell;
-                cl.cell = 2 * lv.back().cell;
-                lv.push_back(std::move(cl));
+                dims.push_back(LevelDims{Lf.nx / 2, Lf.ny / 2, Lf.nz / 2, Lf.k0 / 2, Lf.k1 / 2});
+                const std::array<double, 4> gf = geo.back();
+                geo.push_back({gf[0] + 0.5 * gf[3], gf[1] + 0.5 * gf[3], gf[2] + 0.5 * gf[3], 2 * gf[3]});
             }
-            const LevelDims Lc = lv.back().L;
-            if (lv.size() == 1 || (size_t)Lc.nx * Lc.ny * Lc.nz > 512 || c->world > 1) {
+            const LevelDims Lc = dims.back();
+            if (dims.size() == 1 || (size_t)Lc.nx * Lc.ny * Lc.nz > 512 || c->world > 1) {
                 // no usable hierarchy (odd sizes); distributed multigrid is not wired up yet -> plain projected CG
-                lv.resize(1);
+                dims.resize(1);
+                geo.resize(1);
                 use_mg = false;
             }
         }
+        bool same = lv.size() == dims.size();
+        for (size_t l = 0; same && l < dims.size(); l++)
+            same = lv[l].L.nx == dims[l].nx && lv[l].L.ny == dims[l].ny && lv[l].L.nz == dims[l].nz &&
+                   lv[l].L.k0 == dims[l].k0 && lv[l].L.k1 == dims[l].k1 && lv[l].x.buf.p != nullptr;
+        if (!same) {
+            lv.clear();
+            lv.resize(dims.size());
+            for (size_t l = 0; l < dims.size(); l++) {
+                lv[l].L = dims[l];
+                lv[l].x.alloc(dims[l], s);
+                lv[l].tmp.alloc(dims[l], s);
+                lv[l].r.alloc(dims[l], s);
+                if (l > 0) lv[l].b.alloc(dims[l], s);
+            }
+        }
+        double t1 = now_ms();
         // constraints per level
         for (size_t l = 0; l < lv.size(); l++) {
             MGLevel& Lv = lv[l];
+            for (int a = 0; a < 3; a++) Lv.bmin[a] = geo[l][a];
+            Lv.cell = geo[l][3];
             build_constraint_rows(Lv.L.nx, Lv.L.ny, Lv.L.nz, Lv.bmin, Lv.cell, M, pos, l == 0, Lv.rows);
             bool last = use_mg && (l + 1 == lv.size());
+            Lv.proj.reset();
             if (!last || lv.size() == 1) {
                 Lv.proj.reset(new Projector());
                 Lv.proj->build(Lv.rows, Lv.L, /*uniform=*/l == 0, s);
                 if (c->dist) c->dist->attach(*Lv.proj);
             }
-            Lv.x.alloc(Lv.L, s);
-            Lv.tmp.alloc(Lv.L, s);
-            Lv.r.alloc(Lv.L, s);
-            if (l > 0) Lv.b.alloc(Lv.L, s);
         }
+        double t2 = now_ms();
         st.m_constraints = lv[0].rows.m;
         if (use_mg) {
             std::vector<float> B;
@@ -481,6 +498,9 @@ struct Solver {
             c->d_pinv.upload(B, s);
         }
         st.ms_constraints = now_ms() - t0;
+        if (dbg)
+            fprintf(stderr, "[shm3d] build_levels: buffers %.1f ms, constraints+factor+upload %.1f ms, coarse %.1f ms\n",
+                    t1 - t0, t2 - t1, now_ms() - t2);
     }
 
     // one projected-Jacobi sweep: xo = x + Pi w D^-1 (b - K x)
@@ -537,18 +557,18 @@ struct Solver {
         double rel = 1.0;
         for (;; it++) {
             // z = V(r - mean r)
-            const float* z;
+            float* z;
             if (use_mg) {
                 vcycle(0, r, sc + kSumR, Ng);
                 z = lv[0].x.ip();
             } else {
-                z = r;
+                launch_copy(lv[0].x.ip(), r, n, s);  // z = r (identity preconditioner); keep r intact
+                z = lv[0].x.ip();
             }
             launch_dot_rz(L0, r, z, sc + kRZ, s);  // writes kRZ, kSumZ
             if (c->dist) c->dist->allreduce(sc + kRZ, 2, s);
-            // g = P (z - mean z): multipliers first, the scatter is applied to p after the axpy
-            P.gather(z, nullptr, sc + kSumZ, Ng, s);
-            P.solve(s);
+            // g = P (z - mean z): z <- z - A^T (A A^T)^-1 A (z - mean z); the mean itself is removed in update_p
+            P.apply_shifted(z, sc + kSumZ, Ng, s);
             k_scalars_after_dot<<<1, 1, 0, s>>>(sc, Ng);
             SHM3D_LAUNCHED();
             k_scalars_commit<<<1, 1, 0, s>>>(sc, it == 0);
@@ -569,7 +589,6 @@ struct Solver {
                 if (++bad > 2) break;
             }
             launch_update_p(L0, pv, z, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
-            P.scatter_sub(pv, s);
             if (c->dist) c->dist->exchange_halo(pv, L0, s);
             // q = K p ; alpha = rho / p.q ; x += alpha p ; r -= alpha P q
             launch_stencil_dot(L0, pv, q, sc + kPQ, s);
