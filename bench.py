@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- grid-nodes/sec end-to-end (Steps 1-2 heat-kernel summation + Step 3 constrained solve + shift) of the
+B200-native signed-heat grid solver, and the reference arm beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+One "step" = one complete computeDistance over the workload (BASELINE.json metric):
+  value  : N_grid_nodes * K / device-event time of K steps, sources already resident in HBM (shm3d_solve_device),
+           result left on the device as float32 -- max over ranks;
+  e2e    : the same through the reference-facing interface (SignedHeatGridSolver.computeDistance mirror ->
+           shm3d_solve) with HOST buffers: H2D of the sources and D2H of the double field inside the timed region;
+  roofline     : the PCG fused stencil-apply+dot kernel (HBM-bound; 8 B/node/launch algorithmic: read p, write Kp)
+  roofline_sum : the Step 1-2 summation kernel (SFU-bound: 2 MUFU per evaluated pair at 16/clk/SM)
+  cpu_baseline : the fp64 oracle port of the reference's Step 1-2 loop on the host cores, bounded sample.
+N > 1: the grid is z-slab partitioned over the ranks (NCCL halo exchange + all-reduces) -> "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "signed-heat-3d_b200"), os.path.join(ROOT, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "grid_nodes_per_sec_end_to_end"
+UNIT = "grid-nodes/s"
+
+WORKLOADS = {
+    # name: (generator, hCoef, description)
+    "sphere512": ("sphere", 5, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 512^3 grid (hCoef 5)"),
+    "sphere1024": ("sphere", 6, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 1024^3 grid (hCoef 6)"),
+    "sphere256": ("sphere", 4, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 256^3 grid (hCoef 4)"),
+    "sphere128": ("sphere", 3, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 128^3 grid (hCoef 3)"),
+    "knot128": ("knot", 3, "data/knot.obj (30504 faces, from tests/golden/knot.npz), 128^3 grid (hCoef 3)"),
+}
+
+
+def make_workload(name):
+    gen, hc, desc = WORKLOADS[name]
+    if gen == "sphere":
+        from synth import fibonacci_sphere
+        V, F = fibonacci_sphere(100000)
+    else:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "knot.npz"))
+        fo, fv = z["face_offsets"], z["face_vertices"]
+        V, F = z["V"], [fv[fo[i]:fo[i + 1]].tolist() for i in range(len(fo) - 1)]
+    return V, F, hc, desc
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 8:
+                continue
+            try:
+                sm.append(float(t[1]))
+                mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, t[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            busy = [s for s in sm if s >= 0.5 * max(sm)] or sm  # samples under load
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's Step 1-2 loop on the host cores
+# --------------------------------------------------------------------------------------------------------
+def cpu_sample_plan(p, M, threads, seconds=8.0):
+    """rows of one mid-domain plane such that the sample is ~`seconds` of CPU work (7e7 pair evaluations/s/thread
+    assumed; every node costs the same M evaluations in the reference's brute-force loop)."""
+    pairs = 7e7 * threads * seconds
+    rows = int(max(1, min(p.ny, round(pairs / (p.nx * float(M))))))
+    return rows
+
+
+def cpu_step12_sample(p, pos, nrm, area, rows, threads):
+    from oracle import shm_oracle as o
+    g = o.Grid(p.nx, p.ny, p.nz, np.array(p.bbox_min), p.cell)
+    k = p.nz // 2
+    j0 = max(0, p.ny // 2 - rows // 2)
+    t0 = time.perf_counter()
+    Y = o.step12_box(g, p.lambda_, pos, nrm, area, j0, j0 + rows, k, k + 1, threads=threads)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(Y).all()
+    return rows * p.nx, dt
+
+
+def cpu_baseline_obj(p, M, pos, nrm, area, seconds=8.0):
+    from oracle import shm_oracle as o
+    threads = o.max_threads()
+    rows = cpu_sample_plan(p, M, threads, seconds)
+    nodes, dt = cpu_step12_sample(p, pos, nrm, area, rows, threads)
+    return {"value": nodes / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"Steps 1-2 only (fp64 oracle port of src/signed_heat_grid_solver.cpp:48-65, OpenMP over rows), "
+                       f"{rows} rows of plane k={p.nz // 2} = {nodes} nodes x {M} sources in {dt:.2f} s; Step 3 "
+                       f"excluded (the reference's sparse LU of the KKT system is infeasible beyond 64^3: 945 s at "
+                       f"64^3) -> an UPPER bound on the CPU path's end-to-end nodes/s")}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import shm3d
+    V, F, hc, desc = make_workload(args.workload)
+    p, pos, nrm, area, _ = shm3d.prepare_mesh(V, F, hCoef=hc)  # host-only call (no device code)
+    from oracle import shm_oracle as o
+    threads = o.max_threads()
+    M = len(area)
+    rows = cpu_sample_plan(p, M, threads, seconds=6.0)
+    for _ in range(args.warmup):
+        cpu_step12_sample(p, pos, nrm, area, max(1, rows // 8), threads)
+    t_tot, n_tot = 0.0, 0
+    for _ in range(args.steps):
+        n, dt = cpu_step12_sample(p, pos, nrm, area, rows, threads)
+        n_tot += n
+        t_tot += dt
+    v = n_tot / t_tot
+    sample = (f"per step: Steps 1-2 (fp64 oracle port of the reference loop, OpenMP, {threads} threads) on {rows} rows "
+              f"of one plane = {rows * p.nx} nodes x {M} sources; Step 3 excluded (reference sparse LU infeasible "
+              f"beyond 64^3) -> upper bound on the CPU path's nodes/s; the reference itself is single-threaded and "
+              f"cannot be compiled here (Eigen not vendored)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "grid": [p.nx, p.ny, p.nz], "sources": M},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import shm3d
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000),
+                   os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- workload (host) and contexts
+    V, F, hc, desc = make_workload(args.workload)
+    p, pos, nrm, area, h = shm3d.prepare_mesh(V, F, hCoef=hc)
+    M = len(area)
+    N = p.N
+    if world > 1:
+        ids = [shm3d.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = shm3d.Context(local, rank, world, ids[0])
+    else:
+        ctx = shm3d.Context(local)
+    n_local = ctx.local_n(p)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    d_pos = torch.from_numpy(pos).to(dev)
+    d_nrm = torch.from_numpy(nrm).to(dev)
+    d_area = torch.from_numpy(area).to(dev)
+    d_phi = torch.empty(n_local, dtype=torch.float32, device=dev)
+
+    def step_device(flags=0):
+        q = shm3d.Params.from_buffer_copy(p)
+        q.flags |= flags
+        return ctx.solve_device(q, d_pos.data_ptr(), d_nrm.data_ptr(), d_area.data_ptr(), d_phi.data_ptr(), M)
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    launches = 0
+    stats = None
+    for _ in range(args.steps):
+        stats = step_device()
+        launches += stats.kernel_launches
+    e1.record(stream)
+    torch.cuda.synchronize()
+    stream.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms, wall * 1e3, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    else:
+        wall_ms = wall * 1e3
+    value = N * args.steps / (dev_ms * 1e-3)
+
+    # ---- one profiled step for the per-kernel roofline numbers (CUDA events on the solver's stream)
+    prof = step_device(shm3d.FLAG_PROFILE)
+    hbm_peak, sm_max, peak_src = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("pcg_stencil_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = None
+    if prof.pcg_stencil_launches > 0 and prof.ms_pcg_stencil > 0:
+        bytes_per_launch = 8.0 * n_local  # read p (4 B) + write K p (4 B) per node: SURVEY.md section 8(d)
+        ach = bytes_per_launch * prof.pcg_stencil_launches / (prof.ms_pcg_stencil * 1e-3) / 1e9
+        roofline = {"kernel": "k_stencil_dot (PCG: q = K p fused with p.q)", "bound": "hbm", "achieved": ach,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                    "peak_source": peak_src, "launches": int(prof.pcg_stencil_launches),
+                    "avg_launch_us": 1e3 * prof.ms_pcg_stencil / prof.pcg_stencil_launches,
+                    "algorithmic_bytes_per_launch": bytes_per_launch}
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+    sfu_peak = 16.0 * 148 * sm_mhz * 1e6  # MUFU ops/s at the clock observed under load
+    roofline_sum = {"kernel": "k_sum (Steps 1-2)", "bound": "sfu", "achieved": 2.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3),
+                    "peak": sfu_peak, "unit": "MUFU op/s", "frac": 2.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3) / sfu_peak,
+                    "pairs_evaluated": int(prof.pairs_evaluated), "pairs_bruteforce": int(prof.pairs_bruteforce),
+                    "bruteforce_equivalent_pairs_per_s": prof.pairs_bruteforce / (prof.ms_sum * 1e-3),
+                    "fp32_flops_per_s": 17.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3), "ms": prof.ms_sum,
+                    "note": "rank 0 slab" if world > 1 else ""}
+
+    # ---- end-to-end arm through the reference-facing interface, host buffers (pinned result buffer owned by the solver)
+    solver = shm3d.SignedHeatGridSolver(context=ctx)
+    opts = shm3d.SignedHeat3DOptions(hCoef=hc)
+    h_pos, h_nrm, h_area = np.ascontiguousarray(pos), np.ascontiguousarray(nrm), np.ascontiguousarray(area)
+
+    def step_host():
+        # the mesh-level host work of the adapter (areas/normals/barycentres, rows a4-a6) is done once above, like the
+        # device arm; each step uploads the flat source arrays and downloads the double field
+        q = shm3d.Params.from_buffer_copy(p)
+        return solver._finish(q, h_pos, h_nrm, h_area, opts)
+
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for _ in range(args.steps):
+        phi = step_host()
+        checksum += float(phi[::max(1, len(phi) // 1024)].sum())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = N * args.steps / float(te[0])
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(7 * 8 * M * world),
+           "d2h_bytes_per_step": int(8 * N), "ms_per_step": 1e3 * float(te[0]) / args.steps,
+           "api": "shm3d.SignedHeatGridSolver -> shm3d_solve (host double arrays in, double field out)"}
+
+    if rank == 0:
+        cpu = cpu_baseline_obj(p, M, pos, nrm, area) if world == 1 and not args.no_cpu else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "grid": [p.nx, p.ny, p.nz], "sources": M, "l2": "working set "
+                           f"{4 * N / 1e6:.0f} MB per grid vector >> 126 MB L2 (no explicit flush needed)"
+                           if 4 * N > 4 * 126e6 else "L2 flushed implicitly by the 3-component Y write of Steps 1-2",
+                           "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+                           "cull_tau": 12.0, "timing": "CUDA events on the solver's stream, max over ranks"},
+                "wall_ms_per_step": wall_ms / args.steps, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "roofline": roofline, "roofline_sum": roofline_sum, "cpu_baseline": cpu,
+                "stages_ms": {"h2d+cluster": stats.ms_h2d, "sum(step1-2)": stats.ms_sum, "rhs": stats.ms_rhs,
+                              "constraints+factor(host, overlapped with sum)": stats.ms_constraints,
+                              "pcg": stats.ms_pcg, "shift": stats.ms_shift, "total": stats.ms_total},
+                "pcg": {"iters": int(stats.cg_iters), "rel_residual": stats.cg_rel_residual,
+                        "m_constraints": int(stats.m_constraints),
+                        "profiled_ms": {"stencil": prof.ms_pcg_stencil, "vcycle": prof.ms_pcg_vcycle,
+                                        "projector": prof.ms_pcg_projector, "update": prof.ms_pcg_update}},
+                "checksum": checksum}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sphere512", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ extern "C" {
 #define SHM3D_FLAG_SCRUB_NONFINITE 2u  /* mesh overload zeroes non-finite rhs entries (:72-74); point overload does not */
 #define SHM3D_FLAG_VERBOSE 4u          /* SignedHeatGridSolver::VERBOSE */
 #define SHM3D_FLAG_NO_MG 8u            /* diagnostics: plain projected CG (no multigrid preconditioner) */
+#define SHM3D_FLAG_PROFILE 32u         /* time selected kernels with CUDA events on the solver's stream (fills the ms_pcg_* stats) */
+#define SHM3D_FLAG_PLAIN_MG 16u        /* unconstrained Poisson V-cycle as preconditioner, projector on the fine level only */
 
 typedef struct shm3d_ctx shm3d_ctx;
 
@@ -85,6 +87,9 @@ typedef struct shm3d_stats {
     double ms_pcg_stencil;    /* device time inside the fused stencil-apply+dot kernel, summed */
     int64_t pcg_stencil_launches;
     double ms_pcg_vcycle;     /* device time inside multigrid V-cycles, summed */
+    double ms_pcg_projector;  /* device time inside fine-level projector applications, summed */
+    int64_t pcg_projector_applies;
+    double ms_pcg_update;     /* device time inside the fused x/r update kernel, summed */
 } shm3d_stats;
 
 /* Context: one per GPU.  device = CUDA ordinal.  Returns SHM3D_ERR_CUDA when no usable device. */
@@ -100,6 +105,14 @@ const char* shm3d_last_error(const shm3d_ctx* ctx);
 int shm3d_slab_range(int32_t rank, int32_t world, int32_t nz, int32_t* k0, int32_t* k1);
 /* z-slab [k0,k1) this context owns for a grid of nz planes. */
 int shm3d_slab(const shm3d_ctx* ctx, int32_t nz, int32_t* k0, int32_t* k1);
+
+/* The CUDA stream (cudaStream_t, returned as void*) every kernel of this context is launched on -- for callers that
+ * time the path with their own CUDA events or order their own device work against it. */
+void* shm3d_ctx_stream(const shm3d_ctx* ctx);
+/* Page-locked host buffers (cudaHostAlloc) for the phi_out / source arrays of shm3d_solve: the D2H copy of a 512^3
+ * double field is ~10x faster into pinned memory.  NULL on failure. */
+void* shm3d_host_alloc(size_t bytes);
+void shm3d_host_free(void* p);
 
 /* computeDistance: Steps 1-3 + shift.  phi_out: double[nx*ny*(k1-k0)]. stats may be NULL. */
 int shm3d_solve(shm3d_ctx* ctx, const shm3d_params* p, int64_t n_sources, const double* pos, const double* nrm,

@@ -64,6 +64,40 @@ void oracle_step12(int nx, int ny, int nz, int k0, int k1, const double* bmin, d
 }
 
 /*
+ * Same loop restricted to rows [j0,j1) of planes [k0,k1): the bounded sample bench.py's cpu_baseline / --impl
+ * reference legs time (every node costs the same M kernel evaluations, so any sub-box is representative).
+ * Y_box is packed [(k-k0)][(j-j0)][i][3].  OpenMP over (k,j) rows.
+ */
+void oracle_step12_box(int nx, int ny, int j0, int j1, int k0, int k1, const double* bmin, double cell,
+                       double lambda, int64_t M, const double* pos, const double* nrm, const double* area,
+                       double* Y_box, int threads) {
+    (void)ny;
+    const int nj = j1 - j0, nk = k1 - k0;
+#ifdef _OPENMP
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+#endif
+    for (int row = 0; row < nj * nk; row++) {
+        const int k = k0 + row / nj, j = j0 + row % nj;
+        for (int i = 0; i < nx; i++) {
+            double px = bmin[0] + i * cell, py = bmin[1] + j * cell, pz = bmin[2] + k * cell;
+            double X0 = 0, X1 = 0, X2 = 0;
+            for (int64_t s = 0; s < M; s++) {
+                double w = area[s] * yukawa(px - pos[3 * s], py - pos[3 * s + 1], pz - pos[3 * s + 2], lambda);
+                X0 += nrm[3 * s] * w;
+                X1 += nrm[3 * s + 1] * w;
+                X2 += nrm[3 * s + 2] * w;
+            }
+            double n = sqrt(X0 * X0 + X1 * X1 + X2 * X2);
+            double* o = Y_box + 3 * ((size_t)row * nx + i);
+            o[0] = X0 / n;
+            o[1] = X1 / n;
+            o[2] = X2 / n;
+        }
+    }
+}
+
+/*
  * "As written" variant for the CPU baseline: the reference recomputes each face's
  * barycentre inside the inner loop (src/signed_heat_grid_solver.cpp:55 -> :498-503, a
  * halfedge walk).  Approximated by an indexed 3-vertex gather + average per pair.

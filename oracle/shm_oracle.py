@@ -55,6 +55,8 @@ def _lib():
                                                             dp, dp, dp, dp, ctypes.c_int]
         _LIB.oracle_step12_aswritten.argtypes = [ctypes.c_int] * 5 + [dp, ctypes.c_double, ctypes.c_double,
                                                                       ctypes.c_int64, dp, ip, dp, dp, dp, ctypes.c_int]
+        _LIB.oracle_step12_box.argtypes = [ctypes.c_int] * 6 + [dp, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                                                                dp, dp, dp, dp, ctypes.c_int]
         _LIB.oracle_apply_K.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double, dp, dp, ctypes.c_int]
         _LIB.oracle_max_threads.restype = ctypes.c_int
     return _LIB
@@ -202,6 +204,20 @@ def step12(g: Grid, lam, pos, nrm, area, threads=None, k0=0, k1=None):
     bmin = np.ascontiguousarray(g.bmin, dtype=np.float64)
     _lib().oracle_step12(g.nx, g.ny, g.nz, k0, k1, _dp(bmin), g.cell, lam, len(area), _dp(pos), _dp(nrm), _dp(area),
                          _dp(Y), int(threads))
+    return Y
+
+
+def step12_box(g: Grid, lam, pos, nrm, area, j0, j1, k0, k1, threads=None):
+    """Steps 1-2 on rows [j0,j1) of planes [k0,k1) only -> Y[(k1-k0),(j1-j0),nx,3] (bounded CPU-baseline sample)."""
+    if threads is None:
+        threads = max_threads()
+    Y = np.zeros((k1 - k0, j1 - j0, g.nx, 3), dtype=np.float64)
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    nrm = np.ascontiguousarray(nrm, dtype=np.float64)
+    area = np.ascontiguousarray(area, dtype=np.float64)
+    bmin = np.ascontiguousarray(g.bmin, dtype=np.float64)
+    _lib().oracle_step12_box(g.nx, g.ny, j0, j1, k0, k1, _dp(bmin), g.cell, lam, len(area), _dp(pos), _dp(nrm),
+                             _dp(area), _dp(Y), int(threads))
     return Y
 
 

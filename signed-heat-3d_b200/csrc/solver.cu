@@ -280,6 +280,39 @@ struct Timer {
     }
 };
 
+// Per-kernel device timing for the roofline report (SHM3D_FLAG_PROFILE): event pairs recorded on the solver's
+// stream around selected launches, resolved after the stream has drained.
+struct EventProfiler {
+    struct Rec { cudaEvent_t a, b; int slot; };
+    std::vector<Rec> recs;
+    bool on = false;
+    void begin(cudaStream_t s, int slot) {
+        if (!on) return;
+        Rec r;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        r.slot = slot;
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t s) {
+        if (on) cudaEventRecord(recs.back().b, s);
+    }
+    void resolve(double* ms /*[nslots]*/, int64_t* count) {
+        for (Rec& r : recs) {
+            cudaEventSynchronize(r.b);
+            float t = 0;
+            cudaEventElapsedTime(&t, r.a, r.b);
+            ms[r.slot] += t;
+            count[r.slot]++;
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        recs.clear();
+    }
+};
+enum ProfSlot { kProfStencil = 0, kProfVcycle, kProfProjector, kProfUpdate, kNumProf };
+
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -294,6 +327,9 @@ struct Solver {
     float omega = 0.8f;
     int nu = 2;
     bool use_mg = true;
+    EventProfiler prof;
+    int cmg_from = 0;            // experiment: first level whose smoothers are projected
+    bool constrained_mg = true;  // project inside the multigrid smoothers (every level) vs. plain Poisson V-cycle
 
     Solver(shm3d_ctx* ctx, const shm3d_params* prm) : c(ctx), p(prm), s(ctx->stream) {
         memset(&st, 0, sizeof(st));
@@ -314,6 +350,9 @@ struct Solver {
         if (L0.nzl() < 1) throw Error(SHM3D_ERR_INVALID_ARG, "more ranks than grid planes");
         nu = prm->mg_smooth > 0 ? prm->mg_smooth : 2;
         use_mg = !(prm->flags & SHM3D_FLAG_NO_MG);
+        prof.on = (prm->flags & SHM3D_FLAG_PROFILE) != 0;
+        constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
+        if (const char* e = getenv("SHM3D_CMG_FROM")) cmg_from = atoi(e);
         if (c->sc.n < kNumSc) c->sc.alloc(kNumSc);
         if (c->counters.n < 4) c->counters.alloc(4);
         if (c->nonfinite.n < 1) c->nonfinite.alloc(1);
@@ -481,9 +520,11 @@ struct Solver {
             MGLevel& Lv = lv[l];
             for (int a = 0; a < 3; a++) Lv.bmin[a] = geo[l][a];
             Lv.cell = geo[l][3];
+            Lv.proj.reset();
+            Lv.rows = ConstraintRows();
+            if (l > 0 && !constrained_mg) continue;
             build_constraint_rows(Lv.L.nx, Lv.L.ny, Lv.L.nz, Lv.bmin, Lv.cell, M, pos, l == 0, Lv.rows);
             bool last = use_mg && (l + 1 == lv.size());
-            Lv.proj.reset();
             if (!last || lv.size() == 1) {
                 Lv.proj.reset(new Projector());
                 Lv.proj->build(Lv.rows, Lv.L, /*uniform=*/l == 0, s);
@@ -506,7 +547,7 @@ struct Solver {
     // one projected-Jacobi sweep: xo = x + Pi w D^-1 (b - K x)
     void smooth_sweep(MGLevel& Lv, const float* b, const double* sum_b, double n_global) {
         launch_mg_smooth(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, s);
-        if (Lv.proj) Lv.proj->apply_update(Lv.tmp.ip(), Lv.x.ip(), s);
+        if (Lv.proj && constrained_mg && (int)(&Lv - c->levels.data()) >= cmg_from) Lv.proj->apply_update(Lv.tmp.ip(), Lv.x.ip(), s);
         std::swap(Lv.x, Lv.tmp);
         if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
     }
@@ -520,7 +561,7 @@ struct Solver {
             return;
         }
         launch_mg_smooth0(Lv.L, Lv.x.ip(), b, sum_b, n_global, omega, s);
-        if (Lv.proj) Lv.proj->apply(Lv.x.ip(), s);
+        if (Lv.proj && constrained_mg && l >= cmg_from) Lv.proj->apply(Lv.x.ip(), s);
         if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
         for (int k = 1; k < nu; k++) smooth_sweep(Lv, b, sum_b, n_global);
         MGLevel& Lc = lv[l + 1];
@@ -559,7 +600,9 @@ struct Solver {
             // z = V(r - mean r)
             float* z;
             if (use_mg) {
+                prof.begin(s, kProfVcycle);
                 vcycle(0, r, sc + kSumR, Ng);
+                prof.end(s);
                 z = lv[0].x.ip();
             } else {
                 launch_copy(lv[0].x.ip(), r, n, s);  // z = r (identity preconditioner); keep r intact
@@ -568,7 +611,9 @@ struct Solver {
             launch_dot_rz(L0, r, z, sc + kRZ, s);  // writes kRZ, kSumZ
             if (c->dist) c->dist->allreduce(sc + kRZ, 2, s);
             // g = P (z - mean z): z <- z - A^T (A A^T)^-1 A (z - mean z); the mean itself is removed in update_p
+            prof.begin(s, kProfProjector);
             P.apply_shifted(z, sc + kSumZ, Ng, s);
+            prof.end(s);
             k_scalars_after_dot<<<1, 1, 0, s>>>(sc, Ng);
             SHM3D_LAUNCHED();
             k_scalars_commit<<<1, 1, 0, s>>>(sc, it == 0);
@@ -591,14 +636,31 @@ struct Solver {
             launch_update_p(L0, pv, z, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
             if (c->dist) c->dist->exchange_halo(pv, L0, s);
             // q = K p ; alpha = rho / p.q ; x += alpha p ; r -= alpha P q
+            prof.begin(s, kProfStencil);
             launch_stencil_dot(L0, pv, q, sc + kPQ, s);
+            prof.end(s);
             if (c->dist) c->dist->allreduce(sc + kPQ, 1, s);
+            prof.begin(s, kProfProjector);
             P.apply(q, s);
+            prof.end(s);
+            prof.begin(s, kProfUpdate);
             launch_update_xr(L0, x, r, pv, q, sc + kRho, sc + kPQ, sc + kSumR, s);
+            prof.end(s);
             if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
         }
         t.stop();
         st.ms_pcg = t.ms();
+        {
+            double ms[kNumProf] = {0, 0, 0, 0};
+            int64_t cnt[kNumProf] = {0, 0, 0, 0};
+            prof.resolve(ms, cnt);
+            st.ms_pcg_stencil = ms[kProfStencil];
+            st.pcg_stencil_launches = cnt[kProfStencil];
+            st.ms_pcg_vcycle = ms[kProfVcycle];
+            st.ms_pcg_projector = ms[kProfProjector];
+            st.pcg_projector_applies = cnt[kProfProjector];
+            st.ms_pcg_update = ms[kProfUpdate];
+        }
         st.cg_iters = it;
         st.cg_rel_residual = rel;
         if (it >= maxit && rel >= tol)
@@ -721,6 +783,20 @@ void shm3d_ctx_destroy(shm3d_ctx* ctx) {
     ctx->dist.reset();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+void* shm3d_ctx_stream(const shm3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+void* shm3d_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void shm3d_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 const char* shm3d_last_error(const shm3d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }

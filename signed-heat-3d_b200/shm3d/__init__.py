@@ -18,7 +18,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libshm3d_grid.so")
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_FACTORIZATION, ERR_NO_CONVERGENCE, ERR_NCCL = range(7)
-FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG = 1, 2, 4, 8
+FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_PROFILE = 1, 2, 4, 8, 16, 32
 
 
 class Params(C.Structure):
@@ -37,7 +37,8 @@ class Stats(C.Structure):
                 ("ms_d2h", C.c_double), ("pairs_evaluated", C.c_int64), ("pairs_bruteforce", C.c_int64),
                 ("n_clusters", C.c_int32), ("m_constraints", C.c_int32), ("cg_iters", C.c_int32),
                 ("cg_rel_residual", C.c_double), ("shift", C.c_double), ("kernel_launches", C.c_int64),
-                ("ms_pcg_stencil", C.c_double), ("pcg_stencil_launches", C.c_int64), ("ms_pcg_vcycle", C.c_double)]
+                ("ms_pcg_stencil", C.c_double), ("pcg_stencil_launches", C.c_int64), ("ms_pcg_vcycle", C.c_double),
+                ("ms_pcg_projector", C.c_double), ("pcg_projector_applies", C.c_int64), ("ms_pcg_update", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -52,7 +53,7 @@ class Shm3dError(RuntimeError):
 EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm3d_nccl_unique_id", "shm3d_ctx_destroy",
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
-           "shm3d_debug_factor_solve", "shm3d_version"]
+           "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free"]
 
 _lib = None
 
@@ -87,6 +88,12 @@ def lib():
         L.shm3d_debug_constraints.argtypes = [PP, C.c_int64, dp, i32p, i64p, dp, i64p, C.c_int64]
         L.shm3d_debug_factor_solve.argtypes = [PP, C.c_int64, dp, C.c_int32, dp, C.c_int32, dp, i32p]
         L.shm3d_version.restype = C.c_char_p
+        L.shm3d_ctx_stream.argtypes = [vp]
+        L.shm3d_ctx_stream.restype = vp
+        L.shm3d_host_alloc.argtypes = [C.c_size_t]
+        L.shm3d_host_alloc.restype = vp
+        L.shm3d_host_free.argtypes = [vp]
+        L.shm3d_host_free.restype = None
         _lib = L
     return _lib
 
@@ -169,6 +176,28 @@ def debug_factor_solve(p: Params, pos, v, uniform=True):
     return v, mb.value, th.value
 
 
+class PinnedArray:
+    """numpy view of a page-locked host buffer (shm3d_host_alloc); freed with the object."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(np.atleast_1d(shape))
+        n = int(np.prod(self.shape)) * np.dtype(dtype).itemsize
+        self._p = lib().shm3d_host_alloc(n)
+        if not self._p:
+            raise Shm3dError(ERR_CUDA, f"cudaHostAlloc of {n} bytes failed")
+        buf = (C.c_char * n).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            p, self._p = self._p, None
+            if p:
+                self.array = None
+                lib().shm3d_host_free(p)
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU context (shm3d_ctx).  rank/world/nccl_id select the slab-partitioned multi-GPU mode."""
 
@@ -198,6 +227,11 @@ class Context:
     def _check(self, rc):
         if rc != OK:
             raise Shm3dError(rc, lib().shm3d_last_error(self._h).decode())
+
+    @property
+    def stream(self):
+        """cudaStream_t handle (int) of the stream this context launches on."""
+        return int(lib().shm3d_ctx_stream(self._h) or 0)
 
     def slab(self, nz):
         k0, k1 = C.c_int32(), C.c_int32()
@@ -282,20 +316,32 @@ class SignedHeatGridSolver:
     computeDistancePoints(P, N, areas, h) the point-cloud overload (the tufted-triangulation areas and mean edge
     length are the caller's: SURVEY.md section 8f row N1)."""
 
-    def __init__(self, device=0, context: Context | None = None):
+    def __init__(self, device=0, context: Context | None = None, reuse_output: bool = True):
         self.VERBOSE = False
+        # True: computeDistance returns a view of a solver-owned page-locked buffer that the NEXT call overwrites
+        # (fast D2H, no per-call 1 GB allocation); False: every call returns a freshly allocated array it owns.
+        self.reuse_output = reuse_output
         self.ctx = context if context is not None else Context(device)
         self.params = None   # grid of the last solve (the reference caches nx, bbox, cellSize)
         self.stats = None
+        self._out = None     # page-locked result buffer, reused while the grid size stays the same
 
     def _finish(self, p, pos, nrm, area, options):
         if self.VERBOSE:
             p.flags |= FLAG_VERBOSE
         if options.fastIntegration:
             p.flags |= FLAG_FAST
-        phi, st = self.ctx.solve(p, pos, nrm, area)
+        n = self.ctx.local_n(p)
+        if not self.reuse_output:
+            phi, st = self.ctx.solve(p, pos, nrm, area)
+            self.params, self.stats = p, st
+            return phi
+        if self._out is None or self._out.array.size != n:
+            self._out = None
+            self._out = PinnedArray(n)
+        phi, st = self.ctx.solve(p, pos, nrm, area, out=self._out.array)
         self.params, self.stats = p, st
-        return phi
+        return phi  # view of the solver-owned pinned buffer: valid until the next computeDistance call
 
     def computeDistance(self, V, faces, options: SignedHeat3DOptions = SignedHeat3DOptions()):
         if self.params is not None and not options.rebuild:
