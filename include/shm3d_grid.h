@@ -65,6 +65,9 @@ typedef struct shm3d_params {
     double cg_rel_tol;    /* <=0: default 1e-6 (relative preconditioned residual) */
     int32_t cg_max_iters; /* <=0: default 2000 */
     int32_t mg_smooth;    /* Jacobi sweeps per multigrid leg; <=0: default 2 */
+    int32_t mg_constrained_from; /* first multigrid level (0 = finest) whose smoothers are projected onto that level's
+                             constraints; finer levels run the plain Poisson smoother.  0: default (2); <0: every level */
+    int32_t reserved;
 } shm3d_params;
 
 typedef struct shm3d_stats {

@@ -45,7 +45,10 @@ struct HostFactor {
     std::vector<int> perm;                 // row -> permuted index
     std::vector<ProjNodeDesc> nodes;       // supernodes, children before parents
     std::vector<std::vector<int>> by_height;  // node ids per tree height
-    std::vector<double> mat;               // per node: FWD [f x s] then BWD [s x f]
+    double* mat = nullptr;                 // per node: FWD [f x s] then BWD [s x f]
+    size_t mat_size = 0;
+    std::vector<double> mat_own;           // backing store when no external allocator is given
+    std::function<double*(size_t)> mat_alloc;  // optional: storage for `mat` (e.g. page-locked staging memory)
     std::vector<int> bidx;                 // boundary index lists
     std::vector<double> dinv;              // [m*8] 1/d of each corner node (1 when uniform)
     void solve_host(std::vector<double>& v) const;  // v (permuted order) <- (A D^-1 A^T)^-1 v, same algorithm as the GPU
@@ -102,6 +105,14 @@ class Projector {
     bool all_interior_ = true;
     size_t factor_bytes_ = 0;
     LevelDims L_{};
+    // All device arrays live in two grow-only arenas (factor blocks / everything else) filled from two page-locked
+    // staging buffers by one cudaMemcpyAsync each: no cudaMalloc / cudaFree (device-synchronising) in a steady-state
+    // solve, so the host-side factorisation really overlaps the summation kernel running on the stream.
+    DevBuf<unsigned char> d_arena_, d_matbuf_;
+    unsigned char* h_arena_ = nullptr;  // cudaHostAlloc
+    size_t h_arena_cap_ = 0;
+    double* h_mat_ = nullptr;           // cudaHostAlloc
+    size_t h_mat_cap_ = 0;
     // constraint rows on device (row-major, permuted row order)
     int64_t* d_rnode_ = nullptr;  // [m*8] LOCAL node index (interior-relative), or -1 if not on this rank
     double* d_rw_ = nullptr;      // [m*8]

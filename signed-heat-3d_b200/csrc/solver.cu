@@ -66,7 +66,8 @@ struct shm3d_ctx {
     DevBuf<float> Ybuf;
     PVec vx, vr, vp, vq;
     DevBuf<float> d_pinv;
-    DevBuf<double> d_phi64;
+    DevBuf<double> d_phi64, shift_part;
+    DevBuf<long long> d_coinc;
     std::vector<MGLevel> levels;
 };
 
@@ -125,6 +126,14 @@ __global__ void k_source_average(LevelDims L, double bx, double by, double bz, d
         out[2 * blockIdx.x] = s0[0];
         out[2 * blockIdx.x + 1] = s1[0];
     }
+}
+__global__ void k_poison_nodes(int n, const long long* __restrict__ idx, float* Y, size_t comp_stride) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float q = __int_as_float(0x7fc00000);
+    Y[idx[t]] = q;
+    Y[idx[t] + comp_stride] = q;
+    Y[idx[t] + 2 * comp_stride] = q;
 }
 __global__ void k_fold_pairs(const double* part, int nb, double* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -328,7 +337,7 @@ struct Solver {
     int nu = 2;
     bool use_mg = true;
     EventProfiler prof;
-    int cmg_from = 0;            // experiment: first level whose smoothers are projected
+    int cmg_from = 2;            // first level whose smoothers are projected (finer ones: plain Poisson smoother)
     bool constrained_mg = true;  // project inside the multigrid smoothers (every level) vs. plain Poisson V-cycle
 
     Solver(shm3d_ctx* ctx, const shm3d_params* prm) : c(ctx), p(prm), s(ctx->stream) {
@@ -352,6 +361,7 @@ struct Solver {
         use_mg = !(prm->flags & SHM3D_FLAG_NO_MG);
         prof.on = (prm->flags & SHM3D_FLAG_PROFILE) != 0;
         constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
+        cmg_from = prm->mg_constrained_from == 0 ? 2 : std::max(0, prm->mg_constrained_from);
         if (const char* e = getenv("SHM3D_CMG_FROM")) cmg_from = atoi(e);
         if (c->sc.n < kNumSc) c->sc.alloc(kNumSc);
         if (c->counters.n < 4) c->counters.alloc(4);
@@ -395,9 +405,33 @@ struct Solver {
         st.ms_h2d += now_ms() - t0;
     }
 
+    // Sources that coincide EXACTLY (in the reference's double arithmetic) with a grid node: the reference evaluates
+    // exp(-lambda*0)/0 = Inf there, Y becomes NaN and the mesh overload later scrubs the affected
+    // rhs entries.  The fp32 kernel cannot see an exact coincidence, so those nodes are found here and poisoned.
+    std::vector<long long> coincident;
+    void find_coincident_nodes() {
+        coincident.clear();
+        for (int64_t s_ = 0; s_ < M; s_++) {
+            long long id[3];
+            bool hit = true;
+            for (int a = 0; a < 3 && hit; a++) {
+                const double y = pos[3 * s_ + a];
+                const double t = std::floor((y - G.bmin[a]) / G.cell + 0.5);
+                const int n = a == 0 ? G.nx : (a == 1 ? G.ny : G.nz);
+                // nodeIndicesToPosition (reference :510-514) evaluates bboxMin + cell*i; whether the compiler contracts that
+                // into an FMA is build-dependent, so coincidence is accepted within a few ulp
+                hit = t >= 0 && t < n && std::fabs((G.bmin[a] + G.cell * t) - y) <= 8.9e-16 * (std::fabs(y) + G.cell);
+                id[a] = (long long)t;
+            }
+            if (hit && id[2] >= G.k0 && id[2] < G.k1)
+                coincident.push_back(id[0] + id[1] * (long long)G.nx + (id[2] - G.k0) * (long long)G.nx * G.ny);
+        }
+    }
+
     void cluster_and_upload() {
         double t0 = now_ms();
         if (!nrm) throw Error(SHM3D_ERR_INVALID_ARG, "normals are required for Steps 1-2");
+        find_coincident_nodes();
         double origin[3];
         origin[0] = G.bmin[0] + 0.5 * G.cell * (G.nx - 1);
         origin[1] = G.bmin[1] + 0.5 * G.cell * (G.ny - 1);
@@ -437,6 +471,12 @@ struct Solver {
         pending_sum_timer->start();
         // Y is written component-major with the padded component stride
         launch_heat_sum(P, c->d_cbounds.p, c->d_crange.p, c->d_spos.p, c->d_swn.p, Ycomp(0), ycomp(), c->counters.p, s);
+        if (!coincident.empty()) {
+            c->d_coinc.upload(coincident, s);
+            k_poison_nodes<<<(unsigned)((coincident.size() + 127) / 128), 128, 0, s>>>(
+                (int)coincident.size(), c->d_coinc.p, Ycomp(0), ycomp());
+            SHM3D_LAUNCHED();
+        }
         pending_sum_timer->stop();
         st.pairs_bruteforce = (int64_t)L0.n() * M;
     }
@@ -520,13 +560,16 @@ struct Solver {
             MGLevel& Lv = lv[l];
             for (int a = 0; a < 3; a++) Lv.bmin[a] = geo[l][a];
             Lv.cell = geo[l][3];
-            Lv.proj.reset();
             Lv.rows = ConstraintRows();
-            if (l > 0 && !constrained_mg) continue;
+            if (l > 0 && (!constrained_mg || (int)l < cmg_from)) {
+                Lv.proj.reset();
+                continue;
+            }
             build_constraint_rows(Lv.L.nx, Lv.L.ny, Lv.L.nz, Lv.bmin, Lv.cell, M, pos, l == 0, Lv.rows);
             bool last = use_mg && (l + 1 == lv.size());
+            if (last && lv.size() > 1) Lv.proj.reset();
             if (!last || lv.size() == 1) {
-                Lv.proj.reset(new Projector());
+                if (!Lv.proj) Lv.proj.reset(new Projector());  // kept across solves: its arenas are reused
                 Lv.proj->build(Lv.rows, Lv.L, /*uniform=*/l == 0, s);
                 if (c->dist) c->dist->attach(*Lv.proj);
             }
@@ -584,7 +627,9 @@ struct Solver {
         const double Ng = (double)G.nglobal();
         const size_t n = L0.n();
         float *x = c->vx.ip(), *r = c->vr.ip(), *pv = c->vp.ip(), *q = c->vq.ip();
-        const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : 3e-6;
+        // relative preconditioned residual; the unpreconditioned fallback (odd grids) needs a tighter bar for the same
+        // error in phi because its residual norm under-weights the smooth error components
+        const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : (use_mg ? 3e-6 : 3e-7);
         const int maxit = p->cg_max_iters > 0 ? p->cg_max_iters : 2000;
         Timer t(s);
         t.start();
@@ -674,7 +719,8 @@ struct Solver {
         Timer t(s);
         t.start();
         const int nb = 128;
-        DevBuf<double> part(2 * nb);
+        DevBuf<double>& part = c->shift_part;
+        part.alloc(2 * nb);
         k_source_average<<<nb, 256, 0, s>>>(L0, G.bmin[0], G.bmin[1], G.bmin[2], G.cell, M, c->d_pos.p, c->d_area.p,
                                             c->vx.ip(), part.p);
         SHM3D_LAUNCHED();
@@ -949,7 +995,7 @@ int shm3d_debug_factor_solve(const shm3d_params* p, int64_t M, const double* pos
         for (int r = 0; r < rows.m; r++) pv[hf.perm[r]] = v[r];
         hf.solve_host(pv);
         for (int r = 0; r < rows.m; r++) v[r] = pv[hf.perm[r]];
-        if (factor_megabytes) *factor_megabytes = hf.mat.size() * sizeof(double) / 1048576.0;
+        if (factor_megabytes) *factor_megabytes = hf.mat_size * sizeof(double) / 1048576.0;
         if (tree_height) *tree_height = (int)hf.by_height.size();
     } catch (const shm3d::Error& e) {
         g_create_error = e.what();

@@ -24,7 +24,8 @@ FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_P
 class Params(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("bbox_min", C.c_double * 3),
                 ("cell", C.c_double), ("lambda_", C.c_double), ("flags", C.c_uint32), ("cull_tau", C.c_double),
-                ("cg_rel_tol", C.c_double), ("cg_max_iters", C.c_int32), ("mg_smooth", C.c_int32)]
+                ("cg_rel_tol", C.c_double), ("cg_max_iters", C.c_int32), ("mg_smooth", C.c_int32),
+                ("mg_constrained_from", C.c_int32), ("reserved", C.c_int32)]
 
     @property
     def N(self):

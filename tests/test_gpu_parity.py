@@ -157,7 +157,9 @@ def test_large_grid_properties_sphere_128(gpu_ctx):
 
 
 def test_non_power_of_two_grid_uses_plain_projected_cg(gpu_ctx):
-    V, F = icosphere(2)
+    # off-centre: with cell = 0.2 a centred sphere would put a node exactly at its centre, where X cancels by
+    # symmetry and the direction Y = X/|X| is rounding noise in ANY arithmetic (fp64 oracle included)
+    V, F = icosphere(2, center=(0.013, -0.021, 0.007))
     p, pos, nrm, area, _ = shm3d.prepare_mesh(V, F, hCoef=0)
     p.nx, p.ny, p.nz = 18, 21, 17           # odd sizes: no multigrid hierarchy
     p.cell = 4.0 / 20
@@ -169,7 +171,7 @@ def test_non_power_of_two_grid_uses_plain_projected_cg(gpu_ctx):
     ref = o.solve_kkt_lu(g, b, idx, w)
     ref = ref - o.source_average(g, ref, s["pos"], s["area"])
     phi, st = gpu_ctx.solve(p, pos, nrm, area)
-    assert rel(phi, ref) < PHI_TOL
+    assert rel(phi, ref) < PHI_TOL, (rel(phi, ref), st.cg_iters, st.cg_rel_residual)
 
 
 # ---------------------------------------------------------------- error behaviour

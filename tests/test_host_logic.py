@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     # sizes the C compiler produces for the two ABI structs (natural alignment)
-    assert ctypes.sizeof(shm3d.Params) == 88
+    assert ctypes.sizeof(shm3d.Params) == 96
     assert ctypes.sizeof(shm3d.Stats) == 168
 
 

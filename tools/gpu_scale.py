@@ -18,7 +18,7 @@ for c in cases:
         VV = z["V"]; FF = [fv[fo[i]:fo[i+1]].tolist() for i in range(len(fo) - 1)]
     t = time.time(); p, pos, nrm, area, h = shm3d.prepare_mesh(VV, FF, hCoef=hc); tp = time.time() - t
     p.flags |= int(os.environ.get("FLAGS", "0")); p.mg_smooth = int(os.environ.get("SMOOTH", "0"))
-    p.cg_rel_tol = float(os.environ.get("TOL", "0")); p.cull_tau = float(os.environ.get("TAU", "0"))
+    p.cg_rel_tol = float(os.environ.get("TOL", "0")); p.cull_tau = float(os.environ.get("TAU", "0")); p.mg_constrained_from = int(os.environ.get("CMG", "0"))
     for rep in range(int(os.environ.get("REPS", "2"))):
         t = time.time(); phi, st = ctx.solve(p, pos, nrm, area); wall = time.time() - t
         d = st.asdict()
