@@ -11,3 +11,7 @@ nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
      k_sum.cu grid_ops.cu projector.cu sources.cu dist.cu solver.cu host_api.cu \
      -ldl -lpthread "$@"
 echo "built $OUT"
+# headless driver on top of the C++ mirror (include/shm3d/signed_heat_grid_solver.hpp)
+mkdir -p ../bin
+g++ -std=c++11 -O2 -Wall -o ../bin/shm3d_cli ../../tools/shm3d_cli.cpp -L../lib -lshm3d_grid -Wl,-rpath,'$ORIGIN/../lib'
+echo "built ../bin/shm3d_cli"

@@ -1,0 +1,97 @@
+"""The headless driver (tools/shm3d_cli.cpp, built on the C++ mirror include/shm3d/signed_heat_grid_solver.hpp):
+CPU: its OBJ / .pc readers and host set-up agree with the oracle (--dry-run, no device work);
+GPU: a full solve through the C++ class reproduces the golden field."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import shm_oracle as o
+
+CLI = os.path.join(ROOT, "signed-heat-3d_b200", "bin", "shm3d_cli")
+
+
+def write_obj(path, V, F, junk_vertices=0):
+    with open(path, "w") as fh:
+        fh.write("# written by tests/test_cli.py\n")
+        for _ in range(junk_vertices):  # unreferenced vertices must be stripped (meshio.cpp:22-29)
+            fh.write("v 1000.0 1000.0 1000.0\n")
+        for v in V:
+            fh.write("v %.17g %.17g %.17g\n" % tuple(v))
+        for f in F:
+            fh.write("f " + " ".join(f"{i + 1 + junk_vertices}/1/1" for i in f) + "\n")
+
+
+def test_cli_exists_and_prints_usage():
+    r = subprocess.run([CLI, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage: shm3d_cli" in r.stderr
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 1 and "Please specify a mesh file" in r.stderr  # src/main.cpp:253-256
+
+
+@pytest.mark.parametrize("name,hc", [("bunny_small", 1), ("polygon-bear", 0)])
+def test_cli_dry_run_matches_oracle(tmp_path, name, hc):
+    z, F = load_golden(name)
+    path = str(tmp_path / (name + ".obj"))
+    write_obj(path, z["V"], F, junk_vertices=3)
+    r = subprocess.run([CLI, path, "--grid", "--h", str(hc), "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout)
+    s = o.mesh_sources(z["V"], F)
+    g = o.make_grid(s["centroid"], s["radius"], hc)
+    assert d["nx"] == g.nx and d["sources"] == len(F) and d["vertices"] == len(z["V"])
+    assert abs(d["h"] - s["h"]) < 1e-12 and abs(d["cell"] - g.cell) < 1e-12
+    assert abs(d["lambda"] - o.lambda_from_h(s["h"])) < 1e-9
+    assert np.abs(np.array(d["bbox_min"]) - g.bmin).max() < 1e-12
+
+
+def test_cli_reads_pc_files(tmp_path):
+    z, F = load_golden("bunny_small")
+    s = o.mesh_sources(z["V"], F)
+    path = str(tmp_path / "cloud.pc")
+    with open(path, "w") as fh:
+        for q, n in zip(s["pos"], s["nrm"]):
+            fh.write("v %.17g %.17g %.17g\nvn %.17g %.17g %.17g\n" % (*q, *n))
+    r = subprocess.run([CLI, path, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout)
+    assert d["sources"] == len(F) and d["nx"] == 16
+    # surrogate h = mean nearest-neighbour distance (brute force check)
+    P = s["pos"]
+    d2 = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, np.inf)
+    assert abs(d["h"] - np.sqrt(d2.min(axis=1)).mean()) < 1e-12
+
+
+def test_cli_bad_input_fails_cleanly(tmp_path):
+    r = subprocess.run([CLI, str(tmp_path / "missing.obj"), "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 3 and "cannot read mesh" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_solve_matches_golden(tmp_path):
+    z, F = load_golden("bunny_small")
+    path = str(tmp_path / "bunny_small.obj")
+    out = str(tmp_path / "phi.npy")
+    write_obj(path, z["V"], F)
+    r = subprocess.run([CLI, path, "--grid", "--h", "1", "-V", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "min:" in r.stderr and "Solve time (s)" in r.stderr
+    phi = np.load(out)
+    assert phi.shape == (32, 32, 32)
+    ref = z["h1_phi"]
+    assert np.linalg.norm(phi.ravel() - ref) / np.linalg.norm(ref) < 1e-4
+
+
+@pytest.mark.gpu
+def test_cli_fast_flag_is_reported_unsupported_or_runs(tmp_path):
+    z, F = load_golden("bunny_small")
+    path = str(tmp_path / "b.obj")
+    write_obj(path, z["V"], F)
+    r = subprocess.run([CLI, path, "--fast"], capture_output=True, text=True)
+    assert r.returncode in (0, 3)
+    if r.returncode == 3:
+        assert "fastIntegration" in r.stderr
