@@ -268,18 +268,69 @@ __global__ void __launch_bounds__(kT) k_dot_rz(LevelDims L, const float* __restr
 }
 
 template <int V>
-__global__ void __launch_bounds__(kT) k_update_p(LevelDims L, float* __restrict__ p, const float* __restrict__ z,
+__global__ void __launch_bounds__(kT) k_update_p(LevelDims L, float* p, const float* pin, const float* __restrict__ z,
                                                  const double* sum_z, double n_global, const double* rho_new,
                                                  const double* rho_old, int first) {
     const float mean = (float)(*sum_z / n_global);
     const float beta = first ? 0.f : (float)(*rho_new / *rho_old);
     GRID_STRIDE_GROUPS(L, V) {
         const unsigned int e = _g * V;
-        Vec<V> zv = Vec<V>::ld(z + e), pv = first ? vzero<V>() : Vec<V>::ld(p + e);
+        Vec<V> zv = Vec<V>::ld(z + e), pv = first ? vzero<V>() : Vec<V>::ld(pin + e);
 #pragma unroll
         for (int t = 0; t < V; t++) pv.v[t] = fmaf(beta, pv.v[t], zv.v[t] - mean);
         pv.st(p + e);
     }
+}
+
+// p <- (z - mean) + beta p ;  q = K'p ;  out = sum p q   in one pass: the new p at the six neighbours is recomputed from
+// z and the old p there (cache hits), so the iteration reads z, p and writes p, q: 4 words instead of 3 + 2.
+// p is updated in place, which is safe only because neighbours are recomputed from p_old -- hence the separate output pn.
+template <int V>
+__global__ void __launch_bounds__(kT) k_update_p_stencil(LevelDims L, float* __restrict__ pn, const float* __restrict__ p,
+                                                         const float* __restrict__ z, float* __restrict__ q,
+                                                         const double* sum_z, double n_global, const double* rho_new,
+                                                         const double* rho_old, int first, RedScratch rs, double* out) {
+    const float mean = (float)(*sum_z / n_global);
+    const float beta = first ? 0.f : (float)(*rho_new / *rho_old);
+    const unsigned int pl = (unsigned int)L.nx * (unsigned int)L.ny;
+    double acc[1] = {0.0};
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        int i0, j, kl;
+        decode(e, L.nx, L.ny, i0, j, kl);
+        const int k = L.k0 + kl;
+        const bool ym = j > 0, yp = j < L.ny - 1, zm = k > 0, zp = k < L.nz - 1;
+        auto comb = [&](const Vec<V>& zv, const Vec<V>& pv) {
+            Vec<V> r;
+#pragma unroll
+            for (int t = 0; t < V; t++) r.v[t] = fmaf(beta, pv.v[t], zv.v[t] - mean);
+            return r;
+        };
+        auto ldp = [&](ptrdiff_t off) { return first ? vzero<V>() : Vec<V>::ld(p + off); };
+        const Vec<V> c = comb(Vec<V>::ld(z + e), ldp(e));
+        const Vec<V> a = ym ? comb(Vec<V>::ld(z + e - L.nx), ldp((ptrdiff_t)e - L.nx)) : vzero<V>();
+        const Vec<V> bq = yp ? comb(Vec<V>::ld(z + e + L.nx), ldp((ptrdiff_t)e + L.nx)) : vzero<V>();
+        const Vec<V> d = zm ? comb(Vec<V>::ld(z + (ptrdiff_t)e - (ptrdiff_t)pl), ldp((ptrdiff_t)e - (ptrdiff_t)pl)) : vzero<V>();
+        const Vec<V> f = zp ? comb(Vec<V>::ld(z + e + pl), ldp((ptrdiff_t)e + pl)) : vzero<V>();
+        const float left = (i0 > 0) ? fmaf(beta, first ? 0.f : p[e - 1], z[e - 1] - mean) : 0.f;
+        const float right = (i0 + V < L.nx) ? fmaf(beta, first ? 0.f : p[e + V], z[e + V] - mean) : 0.f;
+        const int cyz = (int)ym + (int)yp + (int)zm + (int)zp;
+        Vec<V> Ku;
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            const int i = i0 + t;
+            const float xl = (t > 0) ? c.v[t > 0 ? t - 1 : 0] : left;
+            const float xr = (t < V - 1) ? c.v[t < V - 1 ? t + 1 : 0] : right;
+            const float cnt = (float)(cyz + (i > 0) + (i < L.nx - 1));
+            Ku.v[t] = cnt * c.v[t] - (xl + xr + a.v[t] + bq.v[t] + d.v[t] + f.v[t]);
+            s = fmaf(c.v[t], Ku.v[t], s);
+        }
+        c.st(pn + e);
+        Ku.st(q + e);
+        acc[0] += (double)s;
+    }
+    block_reduce_commit<1>(acc, rs, out);
 }
 
 __global__ void __launch_bounds__(kT) k_fill(float* p, size_t n, float v) {
@@ -319,19 +370,88 @@ __global__ void __launch_bounds__(kT) k_mg_smooth0(LevelDims L, float* __restric
     }
 }
 
-template <int V>
+// xo = x + omega ((b - shift) - K'x) / d.  DOT: also acc = { sum b*xo, sum xo } (the r.z and sum z of the PCG when this
+// is the last sweep of the fine level: saves a full read of r and z).
+template <int V, bool DOT>
 __global__ void __launch_bounds__(kT) k_mg_smooth(LevelDims L, float* __restrict__ xo, const float* __restrict__ x,
                                                   const float* __restrict__ b, const double* sum_b, double n_global,
-                                                  float omega) {
+                                                  float omega, RedScratch rs, double* out) {
     const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
+    double acc[2] = {0.0, 0.0};
     GRID_STRIDE_GROUPS(L, V) {
         const unsigned int e = _g * V;
         int i0, j, kl;
         decode(e, L.nx, L.ny, i0, j, kl);
         Vec<V> c = Vec<V>::ld(x + e), bv = Vec<V>::ld(b + e), Ku, dg, o;
         stencil<V>(x, e, c, i0, j, L.k0 + kl, L, Ku, dg);
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int t = 0; t < V; t++) o.v[t] = c.v[t] + omega * ((bv.v[t] - shift) - Ku.v[t]) / dg.v[t];
+        for (int t = 0; t < V; t++) {
+            o.v[t] = c.v[t] + omega * ((bv.v[t] - shift) - Ku.v[t]) / dg.v[t];
+            if (DOT) {
+                s0 = fmaf(bv.v[t], o.v[t], s0);
+                s1 += o.v[t];
+            }
+        }
+        o.st(xo + e);
+        if (DOT) {
+            acc[0] += (double)s0;
+            acc[1] += (double)s1;
+        }
+    }
+    if (DOT) block_reduce_commit<2>(acc, rs, out);
+}
+
+// First two damped-Jacobi sweeps from a zero guess in ONE pass over b:
+//   x1 = omega (b - shift)/d ;  x2 = x1 + omega ((b - shift) - K'x1)/d
+// x1 at the six neighbours is recomputed from b (their d from their coordinates): 2 words of traffic instead of 5.
+template <int V>
+__global__ void __launch_bounds__(kT) k_mg_smooth01(LevelDims L, float* __restrict__ xo, const float* __restrict__ b,
+                                                    const double* sum_b, double n_global, float omega) {
+    const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
+    const unsigned int pl = (unsigned int)L.nx * (unsigned int)L.ny;
+    GRID_STRIDE_GROUPS(L, V) {
+        const unsigned int e = _g * V;
+        int i0, j, kl;
+        decode(e, L.nx, L.ny, i0, j, kl);
+        const int k = L.k0 + kl;
+        const bool ym = j > 0, yp = j < L.ny - 1, zm = k > 0, zp = k < L.nz - 1;
+        // neighbour counts along y and z of this row and of the adjacent rows / planes
+        const int cy = (int)ym + (int)yp, cz = (int)zm + (int)zp;
+        const int cy_m = (int)(j - 1 > 0) + 1, cy_p = 1 + (int)(j + 1 < L.ny - 1);  // rows j-1 / j+1 (when they exist)
+        const int cz_m = (int)(k - 1 > 0) + 1, cz_p = 1 + (int)(k + 1 < L.nz - 1);
+        const Vec<V> bc = Vec<V>::ld(b + e);
+        const Vec<V> ba = ym ? Vec<V>::ld(b + e - L.nx) : vzero<V>();
+        const Vec<V> bb = yp ? Vec<V>::ld(b + e + L.nx) : vzero<V>();
+        const Vec<V> bd = zm ? Vec<V>::ld(b + (ptrdiff_t)e - (ptrdiff_t)pl) : vzero<V>();
+        const Vec<V> bf = zp ? Vec<V>::ld(b + e + pl) : vzero<V>();
+        const bool has_l = i0 > 0, has_r = i0 + V < L.nx;
+        const float bl = has_l ? b[e - 1] : 0.f, br = has_r ? b[e + V] : 0.f;
+        // x1 of the two x-end neighbours
+        const int cxl = (int)(i0 - 1 > 0) + 1, cxr = 1 + (int)(i0 + V < L.nx - 1);
+        const float x1l = has_l ? omega * (bl - shift) / (float)(cxl + cy + cz) : 0.f;
+        const float x1r = has_r ? omega * (br - shift) / (float)(cxr + cy + cz) : 0.f;
+        float x1c[V];
+        int cx[V];
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            const int i = i0 + t;
+            cx[t] = (int)(i > 0) + (int)(i < L.nx - 1);
+            x1c[t] = omega * (bc.v[t] - shift) / (float)(cx[t] + cy + cz);
+        }
+        Vec<V> o;
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            const float d = (float)(cx[t] + cy + cz);
+            const float xl = (t > 0) ? x1c[t > 0 ? t - 1 : 0] : x1l;
+            const float xr = (t < V - 1) ? x1c[t < V - 1 ? t + 1 : 0] : x1r;
+            const float xa = ym ? omega * (ba.v[t] - shift) / (float)(cx[t] + cy_m + cz) : 0.f;
+            const float xb = yp ? omega * (bb.v[t] - shift) / (float)(cx[t] + cy_p + cz) : 0.f;
+            const float xd = zm ? omega * (bd.v[t] - shift) / (float)(cx[t] + cy + cz_m) : 0.f;
+            const float xf = zp ? omega * (bf.v[t] - shift) / (float)(cx[t] + cy + cz_p) : 0.f;
+            const float Kx = d * x1c[t] - (xl + xr + xa + xb + xd + xf);
+            o.v[t] = x1c[t] + omega * ((bc.v[t] - shift) - Kx) / d;
+        }
         o.st(xo + e);
     }
 }
@@ -441,6 +561,13 @@ __global__ void __launch_bounds__(512) k_mg_coarse(int n3, const float* __restri
     }
 }
 
+#include "grid_rows.cuh"
+
+inline unsigned int nblk_rows(const LevelDims& L) {
+    size_t rows = (size_t)L.ny * (size_t)L.nzl();
+    size_t b = (rows + kT / 32 - 1) / (kT / 32);
+    return (unsigned int)std::max<size_t>(1, std::min<size_t>(b, kMaxBlocks));
+}
 inline unsigned int nblk(size_t groups) {
     size_t b = (groups + kT - 1) / kT;
     return (unsigned int)std::max<size_t>(1, std::min<size_t>(b, kMaxBlocks));
@@ -466,7 +593,8 @@ void launch_div_rhs(const LevelDims& L, float cell, const float* Y, size_t cs, f
     POST();
 }
 void launch_stencil_dot(const LevelDims& L, const float* p, float* q, double* acc, cudaStream_t s) {
-    VDISPATCH(L, k_stencil_dot, L, p, q, red_scratch(), acc);
+    if (vec4(L)) k_row_stencil_dot<<<nblk_rows(L), kT, 0, s>>>(L, p, q, red_scratch(), acc);
+    else k_stencil_dot<1><<<nblk(L.n()), kT, 0, s>>>(L, p, q, red_scratch(), acc);
     POST();
 }
 void launch_update_xr(const LevelDims& L, float* x, float* r, const float* p, const float* q, const double* rho,
@@ -478,9 +606,9 @@ void launch_dot_rz(const LevelDims& L, const float* r, const float* z, double* a
     VDISPATCH(L, k_dot_rz, L, r, z, red_scratch(), acc);
     POST();
 }
-void launch_update_p(const LevelDims& L, float* p, const float* z, const double* sum_z, double n_global,
+void launch_update_p(const LevelDims& L, float* p, const float* pin, const float* z, const double* sum_z, double n_global,
                      const double* rho_new, const double* rho_old, int first, cudaStream_t s) {
-    VDISPATCH(L, k_update_p, L, p, z, sum_z, n_global, rho_new, rho_old, first);
+    VDISPATCH(L, k_update_p, L, p, pin, z, sum_z, n_global, rho_new, rho_old, first);
     POST();
 }
 void launch_fill(float* p, size_t n, float v, cudaStream_t s) {
@@ -508,20 +636,47 @@ void launch_mg_smooth0(const LevelDims& L, float* x, const float* b, const doubl
 }
 void launch_mg_smooth(const LevelDims& L, float* xo, const float* x, const float* b, const double* sum_b,
                       double n_global, float omega, cudaStream_t s) {
-    VDISPATCH(L, k_mg_smooth, L, xo, x, b, sum_b, n_global, omega);
+    if (vec4(L)) k_row_smooth<false><<<nblk_rows(L), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, RedScratch{}, nullptr);
+    else k_mg_smooth<1, false><<<nblk(L.n()), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, RedScratch{}, nullptr);
+    POST();
+}
+void launch_mg_smooth_dot(const LevelDims& L, float* xo, const float* x, const float* b, const double* sum_b,
+                          double n_global, float omega, double* acc, cudaStream_t s) {
+    if (vec4(L)) k_row_smooth<true><<<nblk_rows(L), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, red_scratch(), acc);
+    else k_mg_smooth<1, true><<<nblk(L.n()), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, red_scratch(), acc);
+    POST();
+}
+void launch_mg_smooth01(const LevelDims& L, float* xo, const float* b, const double* sum_b, double n_global, float omega,
+                        cudaStream_t s) {
+    if (vec4(L)) k_row_smooth01<<<nblk_rows(L), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega);
+    else k_mg_smooth01<1><<<nblk(L.n()), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega);
+    POST();
+}
+void launch_update_p_stencil(const LevelDims& L, float* p_new, const float* p_old, const float* z, float* q,
+                             const double* sum_z, double n_global, const double* rho_new, const double* rho_old, int first,
+                             double* acc, cudaStream_t s) {
+    if (vec4(L))
+        k_row_update_p_stencil<<<nblk_rows(L), kT, 0, s>>>(L, p_new, p_old, z, q, sum_z, n_global, rho_new, rho_old, first,
+                                                           red_scratch(), acc);
+    else
+        k_update_p_stencil<1><<<nblk(L.n()), kT, 0, s>>>(L, p_new, p_old, z, q, sum_z, n_global, rho_new, rho_old, first,
+                                                         red_scratch(), acc);
     POST();
 }
 void launch_mg_residual(const LevelDims& L, const float* x, const float* b, const double* sum_b, double n_global,
                         float* r, cudaStream_t s) {
-    VDISPATCH(L, k_mg_residual, L, x, b, sum_b, n_global, r);
+    if (vec4(L)) k_row_residual<<<nblk_rows(L), kT, 0, s>>>(L, x, b, sum_b, n_global, r);
+    else k_mg_residual<1><<<nblk(L.n()), kT, 0, s>>>(L, x, b, sum_b, n_global, r);
     POST();
 }
 void launch_mg_restrict(const LevelDims& Lf, const LevelDims& Lc, const float* r, float* bc, cudaStream_t s) {
-    k_mg_restrict<<<nblk(Lc.n()), kT, 0, s>>>(Lf, Lc, r, bc);
+    if (vec4(Lc) && Lf.nx == 2 * Lc.nx) k_row_restrict<<<nblk_rows(Lc), kT, 0, s>>>(Lf, Lc, r, bc);
+    else k_mg_restrict<<<nblk(Lc.n()), kT, 0, s>>>(Lf, Lc, r, bc);
     POST();
 }
 void launch_mg_prolong_add(const LevelDims& Lf, const LevelDims& Lc, float* x, const float* ec, cudaStream_t s) {
-    VDISPATCH(Lf, k_mg_prolong_add, Lf, Lc, x, ec);
+    if (vec4(Lf) && Lf.nx == 2 * Lc.nx) k_row_prolong_add<<<nblk_rows(Lf), kT, 0, s>>>(Lf, Lc, x, ec);
+    else k_mg_prolong_add<1><<<nblk(Lf.n()), kT, 0, s>>>(Lf, Lc, x, ec);
     POST();
 }
 void launch_mg_coarse_solve(int n3, const float* pinv, const float* b, float* x, cudaStream_t s) {

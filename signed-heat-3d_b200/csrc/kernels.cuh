@@ -48,8 +48,8 @@ void launch_update_xr(const LevelDims& L, float* x, float* r_padded, const float
 // acc[0] += sum r*z ; acc[1] += sum z
 void launch_dot_rz(const LevelDims& L, const float* r_padded, const float* z_padded, double* acc, cudaStream_t s);
 
-// p = (z - mean_z) + beta p, with mean_z = sums[1]/N and beta = rho_new/rho_old from device scalars
-void launch_update_p(const LevelDims& L, float* p_padded, const float* z_padded, const double* sum_z, double n_global,
+// p = (z - mean_z) + beta p_in, with mean_z = sums[1]/N and beta = rho_new/rho_old from device scalars (p may alias p_in)
+void launch_update_p(const LevelDims& L, float* p, const float* p_in, const float* z, const double* sum_z, double n_global,
                      const double* rho_new, const double* rho_old, int first, cudaStream_t s);
 
 // generic helpers
@@ -65,6 +65,16 @@ void launch_mg_smooth0(const LevelDims& L, float* x_padded, const float* b_padde
 // xout = x + omega * ((b - shift) - K' x) / diag
 void launch_mg_smooth(const LevelDims& L, float* xout_padded, const float* x_padded, const float* b_padded,
                       const double* sum_b, double n_global, float omega, cudaStream_t s);
+// same, and acc[0] = sum b*xout, acc[1] = sum xout (fused r.z / sum z of the PCG on the last fine sweep)
+void launch_mg_smooth_dot(const LevelDims& L, float* xout_padded, const float* x_padded, const float* b_padded,
+                          const double* sum_b, double n_global, float omega, double* acc, cudaStream_t s);
+// the first two sweeps from a zero guess in one pass over b (b must have valid ghost planes in slab-parallel runs)
+void launch_mg_smooth01(const LevelDims& L, float* xout_padded, const float* b_padded, const double* sum_b,
+                        double n_global, float omega, cudaStream_t s);
+// p_new = (z - mean_z) + beta p_old ; q = K' p_new ; acc[0] = sum p_new q  (p_new != p_old: neighbours are recomputed)
+void launch_update_p_stencil(const LevelDims& L, float* p_new_padded, const float* p_old_padded, const float* z_padded,
+                             float* q_padded, const double* sum_z, double n_global, const double* rho_new,
+                             const double* rho_old, int first, double* acc, cudaStream_t s);
 // bc = 0.5 * P^T (b - shift - K' x)   (P = cell-centred trilinear prolongation, clamped at the boundary)
 // r = (b - shift) - K' x   (r needs ghost planes before the restriction in slab-parallel runs)
 void launch_mg_residual(const LevelDims& L, const float* x_padded, const float* b, const double* sum_b, double n_global,

@@ -361,7 +361,7 @@ struct FusedArgs {
     double *rhs, *y, *sol;
 };
 
-__global__ void __launch_bounds__(512, 1) k_proj_fused(FusedArgs A, float* v, const float* w, const double* shift_num,
+__global__ void __launch_bounds__(256) k_proj_fused(FusedArgs A, float* v, const float* w, const double* shift_num,
                                                         double shift_den) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
@@ -876,8 +876,11 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proj_fused, 512, 0);
-        coop_blocks_ = (coop && per_sm > 0) ? sms : 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proj_fused, 256, 0);
+        if (const char* e = getenv("SHM3D_PROJ_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
+        // all co-resident CTAs: the sweeps are bound by the latency of ~5e5 short dependent row products, so the
+        // kernel wants every warp slot of the machine
+        coop_blocks_ = (coop && per_sm > 0) ? sms * per_sm : 0;
     }
     if (getenv("SHM3D_DEBUG"))
         fprintf(stderr, "[shm3d] projector m=%d: factor %.1f ms, maps+upload issue %.1f ms\n", m, (tb1 - tb0) * 1e3,
@@ -945,7 +948,7 @@ void Projector::apply_fused(float* v, const float* w, const double* shift_num, d
     A.y = d_y_;
     A.sol = d_sol_;
     void* args[] = {(void*)&A, (void*)&v, (void*)&w, (void*)&shift_num, (void*)&shift_den};
-    SHM3D_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_proj_fused, dim3(coop_blocks_), dim3(512), args, 0, s));
+    SHM3D_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_proj_fused, dim3(coop_blocks_), dim3(256), args, 0, s));
     SHM3D_LAUNCHED();
 }
 

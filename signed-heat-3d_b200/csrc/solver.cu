@@ -64,7 +64,8 @@ struct shm3d_ctx {
     DevBuf<double> d_pos, d_area, d_nrm;
     PVec Y[1];  // component-major: 3 padded components stored back to back
     DevBuf<float> Ybuf;
-    PVec vx, vr, vp, vq;
+    PVec vx, vr, vp, vp2, vq;
+    double* h_rho = nullptr;  // pinned ring of the PCG's rho values (lagged convergence check)
     DevBuf<float> d_pinv;
     DevBuf<double> d_phi64, shift_part;
     DevBuf<long long> d_coinc;
@@ -73,6 +74,7 @@ struct shm3d_ctx {
 
 namespace shm3d {
 
+constexpr int kRhoRing = 64;
 enum Sc { kRho = 0, kPQ, kSumR, kRZ, kSumZ, kRhoNew, kRho0, kShiftNum, kShiftDen, kTmp, kNumSc = 16 };
 
 // ------------------------------------------------------------------------------------------------
@@ -337,6 +339,7 @@ struct Solver {
     int nu = 2;
     bool use_mg = true;
     EventProfiler prof;
+    int nu_coarse = 0;           // experiment: sweeps on the projected levels (0 = same as nu)
     int cmg_from = 2;            // first level whose smoothers are projected (finer ones: plain Poisson smoother)
     bool constrained_mg = true;  // project inside the multigrid smoothers (every level) vs. plain Poisson V-cycle
 
@@ -363,6 +366,7 @@ struct Solver {
         constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
         cmg_from = prm->mg_constrained_from == 0 ? 2 : std::max(0, prm->mg_constrained_from);
         if (const char* e = getenv("SHM3D_CMG_FROM")) cmg_from = atoi(e);
+        if (const char* e = getenv("SHM3D_NU_COARSE")) nu_coarse = atoi(e);
         if (c->sc.n < kNumSc) c->sc.alloc(kNumSc);
         if (c->counters.n < 4) c->counters.alloc(4);
         if (c->nonfinite.n < 1) c->nonfinite.alloc(1);
@@ -587,50 +591,75 @@ struct Solver {
                     t1 - t0, t2 - t1, now_ms() - t2);
     }
 
-    // one projected-Jacobi sweep: xo = x + Pi w D^-1 (b - K x)
-    void smooth_sweep(MGLevel& Lv, const float* b, const double* sum_b, double n_global) {
-        launch_mg_smooth(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, s);
-        if (Lv.proj && constrained_mg && (int)(&Lv - c->levels.data()) >= cmg_from) Lv.proj->apply_update(Lv.tmp.ip(), Lv.x.ip(), s);
+    bool level_projected(int l) const { return constrained_mg && l >= cmg_from && c->levels[l].proj; }
+
+    // one (projected-)Jacobi sweep: xo = x + Pi w D^-1 (b - K x).  dot_acc: also r.z and sum z (last fine sweep).
+    void smooth_sweep(int l, const float* b, const double* sum_b, double n_global, double* dot_acc = nullptr) {
+        MGLevel& Lv = c->levels[l];
+        if (dot_acc) launch_mg_smooth_dot(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, dot_acc, s);
+        else launch_mg_smooth(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, s);
+        if (level_projected(l)) Lv.proj->apply_update(Lv.tmp.ip(), Lv.x.ip(), s);
         std::swap(Lv.x, Lv.tmp);
         if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
     }
 
-    // V-cycle: levels[l].x = V(b - mean)   (mean only at level 0, passed as device scalar)
-    void vcycle(int l, const float* b, const double* sum_b, double n_global) {
+    // V-cycle: levels[l].x = V(b - mean)   (mean only at level 0, passed as device scalar).
+    // dot_acc (level 0 only, when its smoothers are unprojected): the last sweep also produces r.z and sum z.
+    // b needs valid ghost planes in slab-parallel runs (the fused first sweeps read its z-neighbours).
+    void vcycle(int l, const float* b, const double* sum_b, double n_global, double* dot_acc = nullptr) {
         std::vector<MGLevel>& lv = c->levels;
         MGLevel& Lv = lv[l];
         if (l + 1 == (int)lv.size()) {
             launch_mg_coarse_solve((int)Lv.L.n(), c->d_pinv.p, b, Lv.x.ip(), s);
             return;
         }
-        launch_mg_smooth0(Lv.L, Lv.x.ip(), b, sum_b, n_global, omega, s);
-        if (Lv.proj && constrained_mg && l >= cmg_from) Lv.proj->apply(Lv.x.ip(), s);
+        const bool proj = level_projected(l);
+        const int nul = (l >= cmg_from && nu_coarse > 0) ? nu_coarse : nu;
+        int done = 1;
+        if (!proj && nul >= 2) {
+            launch_mg_smooth01(Lv.L, Lv.x.ip(), b, sum_b, n_global, omega, s);  // sweeps 1 and 2 in one pass over b
+            done = 2;
+        } else {
+            launch_mg_smooth0(Lv.L, Lv.x.ip(), b, sum_b, n_global, omega, s);
+            if (proj) Lv.proj->apply(Lv.x.ip(), s);
+        }
         if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
-        for (int k = 1; k < nu; k++) smooth_sweep(Lv, b, sum_b, n_global);
+        for (int k = done; k < nul; k++) smooth_sweep(l, b, sum_b, n_global);
         MGLevel& Lc = lv[l + 1];
         launch_mg_residual(Lv.L, Lv.x.ip(), b, sum_b, n_global, Lv.r.ip(), s);
         if (c->dist) c->dist->exchange_halo(Lv.r.ip(), Lv.L, s);
         launch_mg_restrict(Lv.L, Lc.L, Lv.r.ip(), Lc.b.ip(), s);
+        if (c->dist) c->dist->exchange_halo(Lc.b.ip(), Lc.L, s);
         vcycle(l + 1, Lc.b.ip(), nullptr, 1.0);
         if (c->dist) c->dist->exchange_halo(Lc.x.ip(), Lc.L, s);
         launch_mg_prolong_add(Lv.L, Lc.L, Lv.x.ip(), Lc.x.ip(), s);
         if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
-        for (int k = 0; k < nu; k++) smooth_sweep(Lv, b, sum_b, n_global);
+        for (int k = 0; k < nul; k++) smooth_sweep(l, b, sum_b, n_global, (k + 1 == nul) ? dot_acc : nullptr);
     }
 
     // ---------------------------------------------------------------- constrained PCG
     // On entry c->vr holds b' = cell^2 D^T Y.  On exit c->vx holds phi (unshifted).
+    //
+    // Projected PCG in the null space of A:  g = Pi Q V Q r,  r <- r - alpha Pi K p.
+    // Per iteration on the fine level: V-cycle (last sweep fused with r.z / sum z), Pi z, fused [p update + K p + p.q],
+    // Pi q, fused [x, r update + sum r].  Convergence is checked on the host every kCheck iterations from a pinned
+    // ring of rho values, so the stream never drains inside the loop.
     void run_pcg() {
         std::vector<MGLevel>& lv = c->levels;
         Projector& P = *lv[0].proj;
         double* sc = c->sc.p;
         const double Ng = (double)G.nglobal();
         const size_t n = L0.n();
-        float *x = c->vx.ip(), *r = c->vr.ip(), *pv = c->vp.ip(), *q = c->vq.ip();
+        float *x = c->vx.ip(), *r = c->vr.ip(), *q = c->vq.ip();
+        float* pbuf[2] = {c->vp.ip(), c->vp2.ip()};
         // relative preconditioned residual; the unpreconditioned fallback (odd grids) needs a tighter bar for the same
         // error in phi because its residual norm under-weights the smooth error components
         const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : (use_mg ? 3e-6 : 3e-7);
         const int maxit = p->cg_max_iters > 0 ? p->cg_max_iters : 2000;
+        const bool verbose = (p->flags & SHM3D_FLAG_VERBOSE) != 0;
+        const int kCheck = (verbose || prof.on) ? 1 : 4;
+        const bool fuse_dot = use_mg && !level_projected(0) && lv.size() > 1 && nu >= 1;
+        if (!c->h_rho) SHM3D_CUDA_CHECK(cudaHostAlloc((void**)&c->h_rho, kRhoRing * sizeof(double), cudaHostAllocDefault));
         Timer t(s);
         t.start();
         SHM3D_CUDA_CHECK(cudaMemsetAsync(sc, 0, kNumSc * sizeof(double), s));
@@ -639,23 +668,25 @@ struct Solver {
         launch_vec_sum(r, n, sc + kSumR, s);
         if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
         double rho0 = 0, rho = 0;
-        int it = 0, bad = 0;
+        int it = 0, bad = 0, checked = 0;
         double rel = 1.0;
+        bool stop = false;
         for (;; it++) {
             // z = V(r - mean r)
-            float* z;
+            float* z = lv[0].x.ip();
             if (use_mg) {
+                if (c->dist) c->dist->exchange_halo(r, L0, s);
                 prof.begin(s, kProfVcycle);
-                vcycle(0, r, sc + kSumR, Ng);
+                vcycle(0, r, sc + kSumR, Ng, fuse_dot ? sc + kRZ : nullptr);
                 prof.end(s);
-                z = lv[0].x.ip();
+                z = lv[0].x.ip();  // (the sweeps swap x and tmp)
+                if (!fuse_dot) launch_dot_rz(L0, r, z, sc + kRZ, s);  // writes kRZ, kSumZ
             } else {
-                launch_copy(lv[0].x.ip(), r, n, s);  // z = r (identity preconditioner); keep r intact
-                z = lv[0].x.ip();
+                launch_copy(z, r, n, s);  // z = r (identity preconditioner); keep r intact
+                launch_dot_rz(L0, r, z, sc + kRZ, s);
             }
-            launch_dot_rz(L0, r, z, sc + kRZ, s);  // writes kRZ, kSumZ
             if (c->dist) c->dist->allreduce(sc + kRZ, 2, s);
-            // g = P (z - mean z): z <- z - A^T (A A^T)^-1 A (z - mean z); the mean itself is removed in update_p
+            // g = P (z - mean z): z <- z - A^T (A A^T)^-1 A (z - mean z); the mean itself is removed in the p update
             prof.begin(s, kProfProjector);
             P.apply_shifted(z, sc + kSumZ, Ng, s);
             prof.end(s);
@@ -663,33 +694,44 @@ struct Solver {
             SHM3D_LAUNCHED();
             k_scalars_commit<<<1, 1, 0, s>>>(sc, it == 0);
             SHM3D_LAUNCHED();
-            double h[2];
-            SHM3D_CUDA_CHECK(cudaMemcpyAsync(h, sc + kRho, sizeof(double), cudaMemcpyDeviceToHost, s));
-            SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
-            rho = h[0];
-            if (it == 0) rho0 = rho;
-            if (!(rho0 > 0) || !std::isfinite(rho)) {
-                if (rho0 == 0) { rel = 0; break; }  // zero right-hand side: phi = 0
-                throw Error(SHM3D_ERR_NONFINITE, "constrained PCG broke down (non-finite or non-positive r.z)");
+            SHM3D_CUDA_CHECK(cudaMemcpyAsync(c->h_rho + (it % kRhoRing), sc + kRho, sizeof(double), cudaMemcpyDeviceToHost, s));
+            if ((it + 1) % kCheck == 0 || it == 0 || it >= maxit) {
+                SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+                for (; checked <= it; checked++) {
+                    rho = c->h_rho[checked % kRhoRing];
+                    if (checked == 0) rho0 = rho;
+                    if (!(rho0 > 0) || !std::isfinite(rho)) {
+                        if (rho0 == 0) { rel = 0; stop = true; break; }  // zero right-hand side: phi = 0
+                        throw Error(SHM3D_ERR_NONFINITE, "constrained PCG broke down (non-finite or non-positive r.z)");
+                    }
+                    rel = std::sqrt(std::fabs(rho) / rho0);
+                    if (verbose) fprintf(stderr, "[shm3d] pcg it %d rel %.3e\n", checked, rel);
+                    if (rel < tol) stop = true;           // x of iteration `checked` was good enough; the few extra
+                    if (rho <= 0 && ++bad > 2) stop = true;  // iterations already in flight only improve it
+                }
+                if (stop || it >= maxit) break;
             }
-            rel = std::sqrt(std::fabs(rho) / rho0);
-            if (p->flags & SHM3D_FLAG_VERBOSE) fprintf(stderr, "[shm3d] pcg it %d rel %.3e\n", it, rel);
-            if (rel < tol || it >= maxit) break;
-            if (rho <= 0) {
-                if (++bad > 2) break;
-            }
-            launch_update_p(L0, pv, z, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
-            if (c->dist) c->dist->exchange_halo(pv, L0, s);
-            // q = K p ; alpha = rho / p.q ; x += alpha p ; r -= alpha P q
+            if (c->dist) c->dist->exchange_halo(z, L0, s);
+            // p = (z - mean z) + beta p ; q = K p ; p.q   (one pass; p ping-pongs between two buffers)
+            float* pn = pbuf[(it + 1) & 1];
+            const float* po = pbuf[it & 1];
             prof.begin(s, kProfStencil);
-            launch_stencil_dot(L0, pv, q, sc + kPQ, s);
+            launch_update_p_stencil(L0, pn, po, z, q, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, sc + kPQ, s);
             prof.end(s);
-            if (c->dist) c->dist->allreduce(sc + kPQ, 1, s);
+            if (c->dist) {
+                // the ghost planes of the new p follow from the ghost planes of z and the old p: no extra exchange
+                LevelDims G1{L0.nx, L0.ny, 1, 0, 1};
+                const size_t pl = L0.plane();
+                if (L0.k0 > 0) launch_update_p(G1, pn - pl, po - pl, z - pl, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
+                if (L0.k1 < L0.nz) launch_update_p(G1, pn + n, po + n, z + n, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
+                c->dist->allreduce(sc + kPQ, 1, s);
+            }
+            // alpha = rho / p.q ; x += alpha p ; r -= alpha P q
             prof.begin(s, kProfProjector);
             P.apply(q, s);
             prof.end(s);
             prof.begin(s, kProfUpdate);
-            launch_update_xr(L0, x, r, pv, q, sc + kRho, sc + kPQ, sc + kSumR, s);
+            launch_update_xr(L0, x, r, pn, q, sc + kRho, sc + kPQ, sc + kSumR, s);
             prof.end(s);
             if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
         }
@@ -748,6 +790,7 @@ struct Solver {
         c->vx.alloc(L0, s);
         c->vr.alloc(L0, s);
         c->vp.alloc(L0, s);
+        c->vp2.alloc(L0, s);
         c->vq.alloc(L0, s);
     }
 };
@@ -827,6 +870,7 @@ void shm3d_ctx_destroy(shm3d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->levels.clear();
     ctx->dist.reset();
+    if (ctx->h_rho) cudaFreeHost(ctx->h_rho);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

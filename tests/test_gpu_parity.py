@@ -157,10 +157,12 @@ def test_large_grid_properties_sphere_128(gpu_ctx):
 
 
 def test_non_power_of_two_grid_uses_plain_projected_cg(gpu_ctx):
-    # off-centre: with cell = 0.2 a centred sphere would put a node exactly at its centre, where X cancels by
-    # symmetry and the direction Y = X/|X| is rounding noise in ANY arithmetic (fp64 oracle included)
-    V, F = icosphere(2, center=(0.013, -0.021, 0.007))
+    V, F = icosphere(2)
     p, pos, nrm, area, _ = shm3d.prepare_mesh(V, F, hCoef=0)
+    # shift the lattice off the sphere centre: with cell = 0.2 a node would sit exactly at the centre, where X cancels
+    # by symmetry (|X| ~ 1e-15 of its terms) and the direction Y = X/|X| is rounding noise in ANY arithmetic
+    for a in range(3):
+        p.bbox_min[a] -= 0.031 * (a + 1)
     p.nx, p.ny, p.nz = 18, 21, 17           # odd sizes: no multigrid hierarchy
     p.cell = 4.0 / 20
     g = oracle_grid(p)

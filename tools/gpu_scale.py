@@ -25,7 +25,7 @@ for c in cases:
         print(f"{name} {p.nx}^3 M={len(area)} h={h:.4f} prep={tp*1e3:.0f}ms wall={wall*1e3:.0f}ms nodes/s={p.N/wall:.3e} "
               f"sum={d['ms_sum']:.1f} kept={d['pairs_evaluated']/d['pairs_bruteforce']:.3f} pairs/s={d['pairs_evaluated']/d['ms_sum']*1e3:.3e} "
               f"constr={d['ms_constraints']:.0f} m={d['m_constraints']} pcg={d['ms_pcg']:.1f} its={d['cg_iters']} "
-              f"ms/it={d['ms_pcg']/max(1,d['cg_iters']):.2f} h2d={d['ms_h2d']:.0f} d2h={d['ms_d2h']:.0f} launches={d['kernel_launches']}")
+              f"ms/it={d['ms_pcg']/max(1,d['cg_iters']):.2f} prof[vc={d['ms_pcg_vcycle']:.0f} pr={d['ms_pcg_projector']:.0f}/{d['pcg_projector_applies']} st={d['ms_pcg_stencil']:.0f} up={d['ms_pcg_update']:.0f}] h2d={d['ms_h2d']:.0f} d2h={d['ms_d2h']:.0f} launches={d['kernel_launches']}")
     if name == "sphere":
         g_cell = p.cell
         # accuracy vs analytic distance near the surface
