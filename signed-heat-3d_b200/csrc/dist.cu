@@ -16,6 +16,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -45,6 +46,7 @@ NcclApi& api() {
         BIND(CommInitRank, "ncclCommInitRank")
         BIND(CommDestroy, "ncclCommDestroy")
         BIND(AllReduce, "ncclAllReduce")
+        BIND(AllGather, "ncclAllGather")
         BIND(Send, "ncclSend")
         BIND(Recv, "ncclRecv")
         BIND(GroupStart, "ncclGroupStart")
@@ -130,6 +132,11 @@ void Dist::exchange_halo3(float* v, size_t cs, const LevelDims& L, cudaStream_t 
 
 void Dist::allreduce(double* dev, int n, cudaStream_t s) {
     NCCL_CHECK(api().AllReduce(dev, dev, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)comm_, s));
+}
+
+void Dist::allgather(float* full, size_t count_per_rank, cudaStream_t s) {
+    // in place: rank r's contribution already sits at full + r * count_per_rank
+    NCCL_CHECK(api().AllGather(full + (size_t)rank_ * count_per_rank, full, count_per_rank, ncclFloat32, (ncclComm_t)comm_, s));
 }
 
 unsigned int Dist::allreduce_max_host(unsigned int v) {

@@ -32,6 +32,7 @@ class Dist {
     // three component-major padded vectors at once (stride between components)
     void exchange_halo3(float* v, size_t comp_stride, const LevelDims& L, cudaStream_t s);
     void allreduce(double* dev, int n, cudaStream_t s);  // in-place sum
+    void allgather(float* full, size_t count_per_rank, cudaStream_t s);  // in place, rank r owns [r*count, (r+1)*count)
     unsigned int allreduce_max_host(unsigned int v);
     void attach(Projector& P);  // hook the projector's gather to an all-reduce
 

@@ -44,6 +44,7 @@ struct MGLevel {
     PVec b;          // right-hand side (level >= 1)
     std::unique_ptr<Projector> proj;
     ConstraintRows rows;
+    bool replicated = false;  // slab-parallel runs: this (coarse) level is held in full by every rank
 };
 
 }  // namespace shm3d
@@ -524,22 +525,41 @@ struct Solver {
         std::vector<std::array<double, 4>> geo;  // bmin xyz, cell
         dims.push_back(L0);
         geo.push_back({G.bmin[0], G.bmin[1], G.bmin[2], G.cell});
+        std::vector<char> repl(1, 0);
         if (use_mg) {
+            // Slab-parallel runs: a level stays z-partitioned while the slab boundaries coarsen cleanly and every rank
+            // keeps at least two planes; below that (<= 32^3-ish grids) every rank holds the whole level ("replicated":
+            // the restricted right-hand side is all-gathered once, everything further down needs no communication).
+            bool replicated = false;
             while (true) {
                 const LevelDims Lf = dims.back();
                 if ((size_t)Lf.nx * Lf.ny * Lf.nz <= 64) break;  // small enough for the dense coarse solve
                 if ((Lf.nx | Lf.ny | Lf.nz) & 1) break;
                 if (Lf.nx / 2 < 4 || Lf.ny / 2 < 4 || Lf.nz / 2 < 4) break;
-                if ((Lf.k0 & 1) || (Lf.k1 & 1)) break;  // slab boundaries must coarsen cleanly
-                dims.push_back(LevelDims{Lf.nx / 2, Lf.ny / 2, Lf.nz / 2, Lf.k0 / 2, Lf.k1 / 2});
+                LevelDims Lc{Lf.nx / 2, Lf.ny / 2, Lf.nz / 2, Lf.k0 / 2, Lf.k1 / 2};
+                if (c->world > 1 && !replicated) {
+                    const int per = Lc.nz / c->world;
+                    const bool clean = !(Lf.k0 & 1) && !(Lf.k1 & 1) && Lc.nz % c->world == 0 && Lc.k0 == c->rank * per &&
+                                       Lc.k1 == (c->rank + 1) * per;
+                    if (!clean) break;  // uneven slabs: no hierarchy below this level
+                    if (per < 2 || (size_t)Lc.nx * Lc.ny * Lc.nz <= 32768) replicated = true;
+                }
+                if (c->world == 1 && ((Lf.k0 & 1) || (Lf.k1 & 1))) break;
+                if (replicated) {
+                    Lc.k0 = 0;
+                    Lc.k1 = Lc.nz;
+                }
+                dims.push_back(Lc);
+                repl.push_back(replicated ? 1 : 0);
                 const std::array<double, 4> gf = geo.back();
                 geo.push_back({gf[0] + 0.5 * gf[3], gf[1] + 0.5 * gf[3], gf[2] + 0.5 * gf[3], 2 * gf[3]});
             }
             const LevelDims Lc = dims.back();
-            if (dims.size() == 1 || (size_t)Lc.nx * Lc.ny * Lc.nz > 512 || c->world > 1) {
-                // no usable hierarchy (odd sizes); distributed multigrid is not wired up yet -> plain projected CG
+            if (dims.size() == 1 || (size_t)Lc.nx * Lc.ny * Lc.nz > 512 || (c->world > 1 && !repl.back())) {
+                // no usable hierarchy (odd sizes, uneven slabs) -> plain projected CG
                 dims.resize(1);
                 geo.resize(1);
+                repl.resize(1);
                 use_mg = false;
             }
         }
@@ -552,6 +572,7 @@ struct Solver {
             lv.resize(dims.size());
             for (size_t l = 0; l < dims.size(); l++) {
                 lv[l].L = dims[l];
+                lv[l].replicated = repl[l] != 0;
                 lv[l].x.alloc(dims[l], s);
                 lv[l].tmp.alloc(dims[l], s);
                 lv[l].r.alloc(dims[l], s);
@@ -575,7 +596,8 @@ struct Solver {
             if (!last || lv.size() == 1) {
                 if (!Lv.proj) Lv.proj.reset(new Projector());  // kept across solves: its arenas are reused
                 Lv.proj->build(Lv.rows, Lv.L, /*uniform=*/l == 0, s);
-                if (c->dist) c->dist->attach(*Lv.proj);
+                if (c->dist && !Lv.replicated) c->dist->attach(*Lv.proj);
+                else Lv.proj->reduce_hook_ = nullptr;
             }
         }
         double t2 = now_ms();
@@ -591,6 +613,7 @@ struct Solver {
                     t1 - t0, t2 - t1, now_ms() - t2);
     }
 
+    bool dist_level(int l) const { return c->dist && !c->levels[l].replicated; }
     bool level_projected(int l) const { return constrained_mg && l >= cmg_from && c->levels[l].proj; }
 
     // one (projected-)Jacobi sweep: xo = x + Pi w D^-1 (b - K x).  dot_acc: also r.z and sum z (last fine sweep).
@@ -600,7 +623,7 @@ struct Solver {
         else launch_mg_smooth(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, s);
         if (level_projected(l)) Lv.proj->apply_update(Lv.tmp.ip(), Lv.x.ip(), s);
         std::swap(Lv.x, Lv.tmp);
-        if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
+        if (dist_level(l)) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
     }
 
     // V-cycle: levels[l].x = V(b - mean)   (mean only at level 0, passed as device scalar).
@@ -623,17 +646,25 @@ struct Solver {
             launch_mg_smooth0(Lv.L, Lv.x.ip(), b, sum_b, n_global, omega, s);
             if (proj) Lv.proj->apply(Lv.x.ip(), s);
         }
-        if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
+        const bool dl = dist_level(l);
+        if (dl) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
         for (int k = done; k < nul; k++) smooth_sweep(l, b, sum_b, n_global);
         MGLevel& Lc = lv[l + 1];
         launch_mg_residual(Lv.L, Lv.x.ip(), b, sum_b, n_global, Lv.r.ip(), s);
-        if (c->dist) c->dist->exchange_halo(Lv.r.ip(), Lv.L, s);
-        launch_mg_restrict(Lv.L, Lc.L, Lv.r.ip(), Lc.b.ip(), s);
-        if (c->dist) c->dist->exchange_halo(Lc.b.ip(), Lc.L, s);
+        if (dl) c->dist->exchange_halo(Lv.r.ip(), Lv.L, s);
+        if (dl && Lc.replicated) {
+            // this rank restricts its own planes into the full coarse vector, then the slabs are all-gathered
+            const LevelDims Ls{Lc.L.nx, Lc.L.ny, Lc.L.nz, Lv.L.k0 / 2, Lv.L.k1 / 2};
+            launch_mg_restrict(Lv.L, Ls, Lv.r.ip(), Lc.b.ip() + (size_t)Ls.k0 * Ls.plane(), s);
+            c->dist->allgather(Lc.b.ip(), Ls.n(), s);
+        } else {
+            launch_mg_restrict(Lv.L, Lc.L, Lv.r.ip(), Lc.b.ip(), s);
+            if (dl) c->dist->exchange_halo(Lc.b.ip(), Lc.L, s);
+        }
         vcycle(l + 1, Lc.b.ip(), nullptr, 1.0);
-        if (c->dist) c->dist->exchange_halo(Lc.x.ip(), Lc.L, s);
+        if (dist_level(l + 1)) c->dist->exchange_halo(Lc.x.ip(), Lc.L, s);
         launch_mg_prolong_add(Lv.L, Lc.L, Lv.x.ip(), Lc.x.ip(), s);
-        if (c->dist) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
+        if (dl) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
         for (int k = 0; k < nul; k++) smooth_sweep(l, b, sum_b, n_global, (k + 1 == nul) ? dot_acc : nullptr);
     }
 

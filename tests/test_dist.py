@@ -1,0 +1,79 @@
+"""N > 1 path.  CPU (gloo, world_size 2): the host-side plumbing bench.py / tools/check_dist.py rely on -- unique-id
+broadcast, slab ownership, max-over-ranks timing reduction, rank-0-only reporting.  GPU (needs >= 2 devices, skipped on
+a one-GPU box): slab-partitioned solve == single-GPU solve through tools/check_dist.py."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "signed-heat-3d_b200"))
+import numpy as np, torch, torch.distributed as dist
+import shm3d
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# 1. the 128-byte communicator id travels from rank 0 to everyone (bench.py does the same with the real ncclUniqueId)
+ids = [bytes(range(128)) if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+assert ids[0] == bytes(range(128)) and len(ids[0]) == 128
+# 2. slabs tile the grid and every plane has exactly one owner; each rank contributes only its slab
+for nz in (16, 64, 100, 512):
+    k0, k1 = shm3d.slab_range(rank, world, nz)
+    own = torch.zeros(nz, dtype=torch.int32)
+    own[k0:k1] = 1
+    dist.all_reduce(own)
+    assert bool((own == 1).all()), (nz, own)
+    # a slab-distributed field reassembles to the full field
+    full = np.arange(nz * 6, dtype=np.float64).reshape(nz, 6)
+    parts = [None] * world
+    dist.all_gather_object(parts, (k0, full[k0:k1].copy()))
+    out = np.concatenate([p for _, p in sorted(parts, key=lambda t: t[0])])
+    assert np.array_equal(out, full)
+# 3. the bench's timing reduction: value = N * steps / max over ranks
+t = torch.tensor([10.0 + rank], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert float(t[0]) == 10.0 + world - 1
+# 4. without a GPU the distributed context must fail loudly too (no CPU fallback in the N > 1 path)
+if not torch.cuda.is_available():
+    try:
+        shm3d.Context(0, rank, world, bytes(128))
+        raise SystemExit("distributed context was created without a GPU")
+    except shm3d.Shm3dError as e:
+        assert e.code == shm3d.ERR_CUDA
+if rank == 0:
+    print("GLOO_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_world2_gloo_plumbing(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_OK" in r.stdout
+
+
+def test_bench_reference_arm_runs_on_rank0_only(tmp_path):
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--workload", "sphere128"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""  # other ranks exit 0 without work
+
+
+@pytest.mark.gpu
+def test_slab_partitioned_solve_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29618", os.path.join(ROOT, "tools", "check_dist.py"), "bunny_small:0", "bunny_small:1", "knot:2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
