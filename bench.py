@@ -11,7 +11,7 @@ One "step" = one complete computeDistance over the workload (BASELINE.json metri
            result left on the device as float32 -- max over ranks;
   e2e    : the same through the reference-facing interface (SignedHeatGridSolver.computeDistance mirror ->
            shm3d_solve) with HOST buffers: H2D of the sources and D2H of the double field inside the timed region;
-  roofline     : the PCG fused stencil-apply+dot kernel (HBM-bound; 8 B/node/launch algorithmic: read p, write Kp)
+  roofline     : the PCG fused p-update + stencil-apply + dot kernel (HBM-bound; 16 B/node/launch algorithmic)
   roofline_sum : the Step 1-2 summation kernel (SFU-bound: 2 MUFU per evaluated pair at 16/clk/SM)
   cpu_baseline : the fp64 oracle port of the reference's Step 1-2 loop on the host cores, bounded sample.
 N > 1: the grid is z-slab partitioned over the ranks (NCCL halo exchange + all-reduces) -> "scaling": "strong".
@@ -282,14 +282,16 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("pcg_stencil_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("pcg_update_p_stencil_dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = None
     if prof.pcg_stencil_launches > 0 and prof.ms_pcg_stencil > 0:
-        bytes_per_launch = 8.0 * n_local  # read p (4 B) + write K p (4 B) per node: SURVEY.md section 8(d)
+        # fused PCG kernel: p <- (z - mean) + beta p ; q = K p ; p.q  -- reads z, p and writes p, q: 4 words = 16 B per node
+        # (SURVEY.md section 8(d) counts the unfused pair as 2 + 3 words)
+        bytes_per_launch = 16.0 * n_local
         ach = bytes_per_launch * prof.pcg_stencil_launches / (prof.ms_pcg_stencil * 1e-3) / 1e9
-        roofline = {"kernel": "k_stencil_dot (PCG: q = K p fused with p.q)", "bound": "hbm", "achieved": ach,
+        roofline = {"kernel": "k_row_update_p_stencil (PCG: p update + q = K p + p.q in one pass)", "bound": "hbm", "achieved": ach,
                     "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                     "peak_source": peak_src, "launches": int(prof.pcg_stencil_launches),
                     "avg_launch_us": 1e3 * prof.ms_pcg_stencil / prof.pcg_stencil_launches,
