@@ -45,7 +45,8 @@ extern "C" {
 #define SHM3D_ERR_NO_CONVERGENCE 5  /* constrained PCG hit cg_max_iters */
 #define SHM3D_ERR_NCCL 6
 
-#define SHM3D_FLAG_FAST 1u             /* SignedHeat3DOptions.fastIntegration (include/signed_heat_3d.h:27) */
+#define SHM3D_FLAG_FAST 1u             /* SignedHeat3DOptions.fastIntegration (include/signed_heat_3d.h:27): greedy BFS integration
+                                          (src/signed_heat_grid_solver.cpp:224-275) instead of the constrained solve */
 #define SHM3D_FLAG_SCRUB_NONFINITE 2u  /* mesh overload zeroes non-finite rhs entries (:72-74); point overload does not */
 #define SHM3D_FLAG_VERBOSE 4u          /* SignedHeatGridSolver::VERBOSE */
 #define SHM3D_FLAG_NO_MG 8u            /* diagnostics: plain projected CG (no multigrid preconditioner) */

@@ -463,6 +463,25 @@ def integrate_greedily(g: Grid, Y):
     return phi
 
 
+def integrate_greedily_prefix(g: Grid, Y):
+    """The same field as integrate_greedily, computed without the queue: on the full box the FIFO order makes
+    (i,j,k-1) the first visitor of (i,j,k) for k > 0, (i,j-1,0) for k = 0 < j and (i-1,0,0) on the x axis, so phi is
+    three prefix sums (x on the line j=k=0, y on the plane k=0, z everywhere).  This is the form the CUDA kernels use;
+    tests/test_oracle.py checks it against the literal BFS above."""
+    nx, ny, nz = g.nx, g.ny, g.nz
+    Y3 = np.asarray(Y, dtype=np.float64).reshape(nz, ny, nx, 3)
+    phi = np.zeros((nz, ny, nx))
+
+    def step(a, b, axis):
+        s = a + b
+        return s[..., axis] / np.linalg.norm(s, axis=-1) * g.cell
+
+    phi[0, 0, 1:] = np.cumsum(step(Y3[0, 0, :-1], Y3[0, 0, 1:], 0))
+    phi[0, 1:, :] = phi[0, 0, :][None, :] + np.cumsum(step(Y3[0, :-1], Y3[0, 1:], 1), axis=0)
+    phi[1:] = phi[0][None] + np.cumsum(step(Y3[:-1], Y3[1:], 2), axis=0)
+    return phi.ravel()
+
+
 # --------------------------------------------------------------------------------------
 # End-to-end restatement of computeDistance
 # --------------------------------------------------------------------------------------

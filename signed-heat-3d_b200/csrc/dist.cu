@@ -139,6 +139,13 @@ void Dist::allgather(float* full, size_t count_per_rank, cudaStream_t s) {
     NCCL_CHECK(api().AllGather(full + (size_t)rank_ * count_per_rank, full, count_per_rank, ncclFloat32, (ncclComm_t)comm_, s));
 }
 
+void Dist::send_plane(const float* p, size_t n, int peer, cudaStream_t s) {
+    NCCL_CHECK(api().Send(p, n, ncclFloat32, peer, (ncclComm_t)comm_, s));
+}
+void Dist::recv_plane(float* p, size_t n, int peer, cudaStream_t s) {
+    NCCL_CHECK(api().Recv(p, n, ncclFloat32, peer, (ncclComm_t)comm_, s));
+}
+
 unsigned int Dist::allreduce_max_host(unsigned int v) {
     SHM3D_CUDA_CHECK(cudaMemcpyAsync(d_tmp_, &v, sizeof(v), cudaMemcpyHostToDevice, stream_));
     NCCL_CHECK(api().AllReduce(d_tmp_, d_tmp_, 1, ncclUint32, ncclMax, (ncclComm_t)comm_, stream_));

@@ -33,6 +33,8 @@ class Dist {
     void exchange_halo3(float* v, size_t comp_stride, const LevelDims& L, cudaStream_t s);
     void allreduce(double* dev, int n, cudaStream_t s);  // in-place sum
     void allgather(float* full, size_t count_per_rank, cudaStream_t s);  // in place, rank r owns [r*count, (r+1)*count)
+    void send_plane(const float* p, size_t n, int peer, cudaStream_t s);  // point-to-point (chained prefix sums)
+    void recv_plane(float* p, size_t n, int peer, cudaStream_t s);
     unsigned int allreduce_max_host(unsigned int v);
     void attach(Projector& P);  // hook the projector's gather to an all-reduce
 

@@ -568,6 +568,83 @@ inline unsigned int nblk_rows(const LevelDims& L) {
     size_t b = (rows + kT / 32 - 1) / (kT / 32);
     return (unsigned int)std::max<size_t>(1, std::min<size_t>(b, kMaxBlocks));
 }
+// ---------------------------------------------------------------- fastIntegration (reference integrateGreedily, :224-275)
+// The reference runs a FIFO breadth-first search from node (0,0,0), visiting neighbours in the order -x,+x,-y,+y,-z,+z,
+// and sets phi[q] = phi[p] + normalize(Y_p + Y_q) . (q - p) for the first p that reaches q.  On the full box the BFS
+// levels are the planes i+j+k = const and, by induction, each level is dequeued in descending lexicographic (i,j,k)
+// order, so the first visitor of q = (i,j,k) is (i,j,k-1) if k > 0, else (i,j-1,0) if j > 0, else (i-1,0,0)
+// (checked against the literal BFS in tests/test_oracle.py).  The whole integration is therefore three prefix sums:
+// along x on the line j=k=0, along y on the plane k=0, along z everywhere.
+__device__ __forceinline__ float fast_step(float ax, float ay, float az, float bx, float by, float bz, int axis, float cell) {
+    const float sx = ax + bx, sy = ay + by, sz = az + bz;
+    const float n = sqrtf(sx * sx + sy * sy + sz * sz);
+    const float c = axis == 0 ? sx : (axis == 1 ? sy : sz);
+    return c / n * cell;
+}
+
+// plane k = 0 of the global grid (one CTA; only the rank that owns plane 0 runs it)
+__global__ void __launch_bounds__(1024) k_fast_base(LevelDims L, float cell, const float* __restrict__ Y, size_t cs,
+                                                    float* __restrict__ phi) {
+    const float* Yx = Y;
+    const float* Yy = Y + cs;
+    const float* Yz = Y + 2 * cs;
+    if (threadIdx.x == 0) {
+        float acc = 0.f;
+        phi[0] = 0.f;
+        for (int i = 1; i < L.nx; i++) {
+            acc += fast_step(Yx[i - 1], Yy[i - 1], Yz[i - 1], Yx[i], Yy[i], Yz[i], 0, cell);
+            phi[i] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L.nx; i += blockDim.x) {
+        float acc = phi[i];
+        for (int j = 1; j < L.ny; j++) {
+            const size_t a = (size_t)i + (size_t)(j - 1) * L.nx, b = a + L.nx;
+            acc += fast_step(Yx[a], Yy[a], Yz[a], Yx[b], Yy[b], Yz[b], 1, cell);
+            phi[b] = acc;
+        }
+    }
+}
+
+// z prefix sums of this rank's slab: one thread per (i,j) column.  phi and Y are padded (ghost plane below holds the
+// previous rank's last plane in slab-parallel runs); plane 0 of the global grid must already be filled.
+__global__ void __launch_bounds__(kT) k_fast_z(LevelDims L, float cell, const float* __restrict__ Y, size_t cs,
+                                               float* __restrict__ phi) {
+    const size_t pl = L.plane();
+    const size_t col = (size_t)blockIdx.x * kT + threadIdx.x;
+    if (col >= pl) return;
+    const float* Yx = Y + col;
+    const float* Yy = Y + cs + col;
+    const float* Yz = Y + 2 * cs + col;
+    float* ph = phi + col;
+    int kl = 0;
+    float acc, px, py, pz;
+    if (L.k0 == 0) {  // global plane 0: given
+        acc = ph[0];
+        px = Yx[0];
+        py = Yy[0];
+        pz = Yz[0];
+        kl = 1;
+    } else {  // continue from the ghost plane below
+        acc = *(ph - (ptrdiff_t)pl);
+        px = *(Yx - (ptrdiff_t)pl);
+        py = *(Yy - (ptrdiff_t)pl);
+        pz = *(Yz - (ptrdiff_t)pl);
+    }
+    const int nzl = L.nzl();
+#pragma unroll 4
+    for (; kl < nzl; kl++) {
+        const size_t o = (size_t)kl * pl;
+        const float qx = Yx[o], qy = Yy[o], qz = Yz[o];
+        acc += fast_step(px, py, pz, qx, qy, qz, 2, cell);
+        ph[o] = acc;
+        px = qx;
+        py = qy;
+        pz = qz;
+    }
+}
+
 inline unsigned int nblk(size_t groups) {
     size_t b = (groups + kT - 1) / kT;
     return (unsigned int)std::max<size_t>(1, std::min<size_t>(b, kMaxBlocks));
@@ -677,6 +754,14 @@ void launch_mg_restrict(const LevelDims& Lf, const LevelDims& Lc, const float* r
 void launch_mg_prolong_add(const LevelDims& Lf, const LevelDims& Lc, float* x, const float* ec, cudaStream_t s) {
     if (vec4(Lf) && Lf.nx == 2 * Lc.nx) k_row_prolong_add<<<nblk_rows(Lf), kT, 0, s>>>(Lf, Lc, x, ec);
     else k_mg_prolong_add<1><<<nblk(Lf.n()), kT, 0, s>>>(Lf, Lc, x, ec);
+    POST();
+}
+void launch_fast_integrate_base(const LevelDims& L, float cell, const float* Y, size_t cs, float* phi, cudaStream_t s) {
+    k_fast_base<<<1, 1024, 0, s>>>(L, cell, Y, cs, phi);
+    POST();
+}
+void launch_fast_integrate_z(const LevelDims& L, float cell, const float* Y, size_t cs, float* phi, cudaStream_t s) {
+    k_fast_z<<<(unsigned)((L.plane() + kT - 1) / kT), kT, 0, s>>>(L, cell, Y, cs, phi);
     POST();
 }
 void launch_mg_coarse_solve(int n3, const float* pinv, const float* b, float* x, cudaStream_t s) {

@@ -52,6 +52,13 @@ void launch_dot_rz(const LevelDims& L, const float* r_padded, const float* z_pad
 void launch_update_p(const LevelDims& L, float* p, const float* p_in, const float* z, const double* sum_z, double n_global,
                      const double* rho_new, const double* rho_old, int first, cudaStream_t s);
 
+// fastIntegration (reference integrateGreedily, src/signed_heat_grid_solver.cpp:224-275) as prefix sums; Y, phi padded.
+// base: global plane k = 0 (rank owning it only); z: this rank's slab, continuing from the ghost plane below.
+void launch_fast_integrate_base(const LevelDims& L, float cell, const float* Y_padded, size_t comp_stride, float* phi_padded,
+                                cudaStream_t s);
+void launch_fast_integrate_z(const LevelDims& L, float cell, const float* Y_padded, size_t comp_stride, float* phi_padded,
+                             cudaStream_t s);
+
 // generic helpers
 void launch_fill(float* p, size_t n, float v, cudaStream_t s);
 void launch_copy(float* dst, const float* src, size_t n, cudaStream_t s);

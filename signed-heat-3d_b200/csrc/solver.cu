@@ -766,6 +766,9 @@ struct Solver {
             prof.end(s);
             if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
         }
+        // x = sum alpha_k p_k left null(A) only by fp32 rounding (|A x| ~ 1e-4 after ~100 iterations at 512^3):
+        // one last projection restores the zero level set at the pinned sources to rounding
+        P.apply(x, s);
         t.stop();
         st.ms_pcg = t.ms();
         {
@@ -784,6 +787,25 @@ struct Solver {
         if (it >= maxit && rel >= tol)
             throw Error(SHM3D_ERR_NO_CONVERGENCE, "constrained PCG did not converge in " + std::to_string(maxit) +
                                                       " iterations (rel " + std::to_string(rel) + ")");
+    }
+
+    // ---------------------------------------------------------------- fastIntegration (:77-78, :224-275)
+    // phi (c->vx) from Y by the reference's greedy breadth-first integration, restated as prefix sums (grid_ops.cu).
+    // Slab-parallel: the z prefix sums form a chain over the ranks -- each rank receives the plane below its slab from
+    // rank-1, integrates its planes, and passes its top plane on.
+    void run_fast_integration() {
+        Timer t(s);
+        t.start();
+        float* phi = c->vx.ip();
+        const size_t pl = L0.plane(), n = L0.n();
+        if (c->dist) c->dist->exchange_halo3(Ycomp(0), ycomp(), L0, s);
+        if (L0.k0 == 0) launch_fast_integrate_base(L0, (float)G.cell, Ycomp(0), ycomp(), phi, s);
+        else c->dist->recv_plane(phi - pl, pl, c->rank - 1, s);
+        launch_fast_integrate_z(L0, (float)G.cell, Ycomp(0), ycomp(), phi, s);
+        if (c->dist && L0.k1 < L0.nz) c->dist->send_plane(phi + n - pl, pl, c->rank + 1, s);
+        t.stop();
+        st.ms_pcg = t.ms();
+        st.cg_iters = 0;
     }
 
     // ---------------------------------------------------------------- shift + output
@@ -947,16 +969,22 @@ static int solve_impl(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const do
     double t0 = now_ms();
     int64_t l0 = g_kernel_launches;
     Solver S(ctx, p);
-    if (p->flags & SHM3D_FLAG_FAST)
-        throw Error(SHM3D_ERR_INVALID_ARG, "fastIntegration (greedy BFS) is not implemented in this build");
     S.prepare_sources(M, pos, nrm, area, on_device);
     S.cluster_and_upload();
-    S.alloc_pcg_vectors();
-    S.run_step12();       // asynchronous on the GPU ...
-    S.build_levels();     // ... while the host builds and factorises the constraint systems
-    S.finish_step12_stats();
-    S.run_rhs(ctx->vr.ip());
-    S.run_pcg();
+    if (p->flags & SHM3D_FLAG_FAST) {
+        // SignedHeat3DOptions.fastIntegration: Steps 1-2, then the greedy integration instead of the constrained solve
+        ctx->vx.alloc(S.L0, ctx->stream);
+        S.run_step12();
+        S.finish_step12_stats();
+        S.run_fast_integration();
+    } else {
+        S.alloc_pcg_vectors();
+        S.run_step12();       // asynchronous on the GPU ...
+        S.build_levels();     // ... while the host builds and factorises the constraint systems
+        S.finish_step12_stats();
+        S.run_rhs(ctx->vr.ip());
+        S.run_pcg();
+    }
     S.run_shift_and_output(phi_host, phi_dev);
     SHM3D_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     S.st.kernel_launches = g_kernel_launches - l0;

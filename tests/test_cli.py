@@ -87,11 +87,13 @@ def test_cli_solve_matches_golden(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cli_fast_flag_is_reported_unsupported_or_runs(tmp_path):
+def test_cli_fast_flag(tmp_path):
     z, F = load_golden("bunny_small")
     path = str(tmp_path / "b.obj")
+    out = str(tmp_path / "phi.npy")
     write_obj(path, z["V"], F)
-    r = subprocess.run([CLI, path, "--fast"], capture_output=True, text=True)
-    assert r.returncode in (0, 3)
-    if r.returncode == 3:
-        assert "fastIntegration" in r.stderr
+    r = subprocess.run([CLI, path, "--fast", "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = o.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
+    phi = np.load(out).ravel()
+    assert np.linalg.norm(phi - ref) / np.linalg.norm(ref) < 1e-4

@@ -1,0 +1,121 @@
+"""GPU tests at the BASELINE.json configuration sizes.
+
+config[1] knot.obj 128^3     : against the fp64 oracle (C loop + projected CG, tests/golden/make_golden_large.py)
+config[2] bunny.pc 256^3     : point overload; size-independent properties (the tufted-cover weights are row N1 -- the
+                               test uses the CLI's stated surrogate: uniform area h^2, h = mean nearest-neighbour distance)
+config[3] SprayBottle 512^3  : lambda*r up to 580 (fp32 range stress); properties
+config[4] 1e5-triangle sphere 512^3 : the bench workload; analytic distance in a band, constraint / shift identities
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import shm3d
+from conftest import GOLDEN, ROOT, load_golden
+from oracle import shm_oracle as o
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+PHI_TOL = 1e-4
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b)
+
+
+def trilinear_at(p, phi, q):
+    g = o.Grid(p.nx, p.ny, p.nz, np.array(p.bbox_min), p.cell)
+    return o.evaluate_function(g, phi, q)
+
+
+def test_config1_knot_128_matches_oracle(gpu_ctx):
+    z, F = load_golden("knot")
+    gl = np.load(os.path.join(GOLDEN, "knot_h3.npz"))
+    p, pos, nrm, area, _ = shm3d.prepare_mesh(z["V"], F, hCoef=3)
+    assert p.nx == int(gl["nx"]) == 128 and abs(p.cell - float(gl["cell"])) < 1e-12
+    Y, st12 = gpu_ctx.step12(p, pos, nrm, area)
+    sub = gl["sub_index"]
+    assert np.abs(Y[:, sub].T - gl["Y_sub"]).max() < 3e-5
+    phi, st = gpu_ctx.solve(p, pos, nrm, area)
+    assert st.m_constraints == int(gl["m"]) == 12155          # SURVEY section 8(d) input 2
+    assert rel(phi[sub], gl["sub_phi"]) < PHI_TOL
+    lo, hi, l2 = gl["phi_stats"]
+    assert abs(phi.min() - lo) < 1e-3 * hi and abs(phi.max() - hi) < 1e-3 * hi
+    assert abs(np.linalg.norm(phi) / l2 - 1) < PHI_TOL
+    assert st.cg_iters < 80
+
+
+def test_config2_bunny_point_cloud_256(gpu_ctx):
+    d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
+    P, N = d["P"], d["N"]
+    # surrogate weights (same rule as tools/shm3d_cli.cpp): h = mean nearest-neighbour distance, area = h^2
+    d2 = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, np.inf)
+    h = float(np.sqrt(d2.min(axis=1)).mean())
+    areas = np.full(len(P), h * h)
+    solver = shm3d.SignedHeatGridSolver(context=gpu_ctx)
+    phi = solver.computeDistancePoints(P, N, areas, h, shm3d.SignedHeat3DOptions(hCoef=4))
+    p, st = solver.params, solver.stats
+    assert p.nx == 256 and np.isfinite(phi).all()
+    assert not (p.flags & shm3d.FLAG_SCRUB_NONFINITE)                   # the point overload does not scrub (:180)
+    # zero area-weighted mean on the sources (the shift, :216-217) and the pinned cells interpolate to -shift
+    v = trilinear_at(p, phi, P)
+    assert abs((areas * v).sum() / areas.sum()) < 1e-5
+    src, _, _ = shm3d.debug_constraints(p, P)
+    assert len(src) == st.m_constraints
+    assert np.abs(v[src] + st.shift).max() < 2e-4 * np.abs(phi).max()
+    # sign: positive far outside, negative at the centroid (the bunny's centroid is inside the surface)
+    assert phi[0] > 0 and phi[-1] > 0
+    c = P.mean(axis=0)
+    assert trilinear_at(p, phi, c[None, :])[0] < 0
+
+
+def test_config3_spraybottle_512_range_stress(gpu_ctx):
+    d = np.load(os.path.join(GOLDEN, "spraybottle_mesh.npz"))
+    V, F = d["V"], d["F"].astype(np.int64)
+    p, pos, nrm, area, h = shm3d.prepare_mesh(V, F, hCoef=5)
+    assert p.nx == 512 and abs(p.lambda_ - 9.7438) < 1e-3
+    phi, st = gpu_ctx.solve(p, pos, nrm, area)
+    assert np.isfinite(phi).all()                                   # exp(-lambda r) spans e^-580: no under/overflow
+    assert st.m_constraints == 35887                                # SURVEY section 8(d) input 4
+    assert st.cg_iters < 250
+    v = trilinear_at(p, phi, pos)
+    assert abs((area * v).sum() / area.sum()) < 1e-4 * np.abs(phi).max()
+    src, _, _ = shm3d.debug_constraints(p, pos)
+    assert np.abs(v[src] + st.shift).max() < 2e-4 * np.abs(phi).max()
+    assert phi[0] > 0 and phi[-1] > 0
+    # |grad phi| ~ 1 away from the surface: central differences on a coarse sample of interior nodes
+    n = p.nx
+    g3 = phi.reshape(n, n, n)
+    s = slice(8, n - 8, 16)
+    gx = (g3[s, s, 9:n - 7:16] - g3[s, s, 7:n - 9:16]) / (2 * p.cell)
+    gy = (g3[s, 9:n - 7:16, s] - g3[s, 7:n - 9:16, s]) / (2 * p.cell)
+    gz = (g3[9:n - 7:16, s, s] - g3[7:n - 9:16, s, s]) / (2 * p.cell)
+    gn = np.sqrt(gx ** 2 + gy ** 2 + gz ** 2)
+    assert abs(np.median(gn) - 1) < 0.05
+
+
+def test_config4_sphere_1e5_triangles_512(gpu_ctx):
+    from synth import fibonacci_sphere
+    V, F = fibonacci_sphere(100000)
+    p, pos, nrm, area, h = shm3d.prepare_mesh(V, F, hCoef=5)
+    assert p.nx == 512 and len(area) == 100000
+    phi, st = gpu_ctx.solve(p, pos, nrm, area)
+    assert np.isfinite(phi).all() and st.cg_iters < 150
+    assert 0 < st.pairs_evaluated < 0.15 * st.pairs_bruteforce       # far-field culling does its job
+    # analytic signed distance |x| - 1 on three mid-planes, within half a cell in a band around the surface
+    n = p.nx
+    ax = [np.array(p.bbox_min)[a] + p.cell * np.arange(n) for a in range(3)]
+    g3 = phi.reshape(n, n, n)
+    k = n // 2
+    X, Yc = np.meshgrid(ax[0], ax[1], indexing="xy")
+    dist = np.sqrt(X ** 2 + Yc ** 2 + ax[2][k] ** 2) - 1
+    band = np.abs(dist) < 0.3
+    assert np.abs(g3[k] - dist)[band].max() < 0.5 * p.cell
+    assert (g3[k][dist > 0.05] > 0).all() and (g3[k][dist < -0.05] < 0).all()
+    v = trilinear_at(p, phi, pos)
+    assert abs((area * v).sum() / area.sum()) < 1e-5
+    src, _, _ = shm3d.debug_constraints(p, pos)
+    assert np.abs(v[src] + st.shift).max() < 1e-4

@@ -176,6 +176,17 @@ def test_non_power_of_two_grid_uses_plain_projected_cg(gpu_ctx):
     assert rel(phi, ref) < PHI_TOL, (rel(phi, ref), st.cg_iters, st.cg_rel_residual)
 
 
+@pytest.mark.parametrize("name,hc", [("bunny_small", 0), ("bunny_small", 1), ("polygon-bear", 0)])
+def test_fast_integration_matches_oracle_bfs(gpu_ctx, name, hc):
+    """SignedHeat3DOptions.fastIntegration: greedy BFS integration (src/signed_heat_grid_solver.cpp:77-78, :224-275)."""
+    z, F = load_golden(name)
+    solver = shm3d.SignedHeatGridSolver(context=gpu_ctx)
+    phi = solver.computeDistance(z["V"], F, shm3d.SignedHeat3DOptions(hCoef=hc, fastIntegration=True))
+    ref = o.compute_distance_mesh(z["V"], F, hCoef=hc, fast=True)
+    assert np.isfinite(phi).all() and solver.stats.cg_iters == 0
+    assert rel(phi, ref) < PHI_TOL
+
+
 # ---------------------------------------------------------------- error behaviour
 def test_nonfinite_source_is_rejected(gpu_ctx):
     V, F = icosphere(1)

@@ -102,3 +102,16 @@ def test_fast_integration_runs():
     V, F = icosphere(1)
     r = o.compute_distance_mesh(V, F, hCoef=0, fast=True)
     assert np.isfinite(r).all()
+
+
+def test_greedy_bfs_equals_prefix_sums():
+    """The reference's FIFO breadth-first integration (src/signed_heat_grid_solver.cpp:224-275) visits every node first
+    from (i,j,k-1) / (i,j-1,0) / (i-1,0,0): the closed form the GPU path uses must reproduce the literal BFS."""
+    rng = np.random.default_rng(3)
+    for dims in [(8, 9, 7), (5, 4, 11), (16, 16, 16)]:
+        g = o.Grid(dims[0], dims[1], dims[2], np.zeros(3), 0.37)
+        Y = rng.standard_normal((g.N, 3))
+        Y /= np.linalg.norm(Y, axis=1, keepdims=True)
+        a = o.integrate_greedily(g, Y.ravel())
+        b = o.integrate_greedily_prefix(g, Y.ravel())
+        assert np.abs(a - b).max() < 1e-12
