@@ -14,7 +14,9 @@ One "step" = one complete computeDistance over the workload (BASELINE.json metri
   roofline     : the PCG fused p-update + stencil-apply + dot kernel (HBM-bound; 16 B/node/launch algorithmic)
   roofline_sum : the Step 1-2 summation kernel (SFU-bound: 2 MUFU per evaluated pair at 16/clk/SM)
   cpu_baseline : the fp64 oracle port of the reference's Step 1-2 loop on the host cores, bounded sample.
-N > 1: the grid is z-slab partitioned over the ranks (NCCL halo exchange + all-reduces) -> "scaling": "strong".
+N > 1: the grid is z-slab partitioned over the ranks (NCCL halo exchange + all-reduces).  Default workloads keep
+~512^3 nodes per GPU (512^3, 640^3, 768^3, 1024^3 at 1, 2, 4, 8 GPUs -> "scaling": "weak"); --workload sphereN fixes
+the grid for strong-scaling runs.
 """
 import argparse
 import json
@@ -36,17 +38,20 @@ METRIC = "grid_nodes_per_sec_end_to_end"
 UNIT = "grid-nodes/s"
 
 WORKLOADS = {
-    # name: (generator, hCoef, description)
-    "sphere512": ("sphere", 5, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 512^3 grid (hCoef 5)"),
-    "sphere1024": ("sphere", 6, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 1024^3 grid (hCoef 6)"),
-    "sphere256": ("sphere", 4, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 256^3 grid (hCoef 4)"),
-    "sphere128": ("sphere", 3, "synthetic unit sphere, 100000 outward triangles (Fibonacci hull), 128^3 grid (hCoef 3)"),
-    "knot128": ("knot", 3, "data/knot.obj (30504 faces, from tests/golden/knot.npz), 128^3 grid (hCoef 3)"),
+    # name: (generator, grid nodes per axis, description).  "sphereN": N^3 grid around the 1e5-triangle unit sphere
+    # (N = 16*2^h reproduces the reference's hCoef grids: 512 = hCoef 5, 1024 = hCoef 6; other N keep the same box).
+    "knot128": ("knot", 128, "data/knot.obj (30504 faces, from tests/golden/knot.npz), 128^3 grid (hCoef 3)"),
 }
+for _n in (128, 256, 512, 640, 768, 1024):
+    WORKLOADS[f"sphere{_n}"] = ("sphere", _n, f"synthetic unit sphere, 100000 outward triangles (Fibonacci hull), {_n}^3 grid")
+
+# default workload per GPU count: ~512^3 nodes per GPU (weak scaling); N = 1 is the configuration BASELINE.json's
+# target is quoted on (512^3, 1e5 triangles, 1 x B200), N = 8 its 1024^3 / 8 x B200 configuration
+DEFAULT_BY_GPUS = {1: "sphere512", 2: "sphere640", 4: "sphere768", 8: "sphere1024"}
 
 
 def make_workload(name):
-    gen, hc, desc = WORKLOADS[name]
+    gen, n, desc = WORKLOADS[name]
     if gen == "sphere":
         from synth import fibonacci_sphere
         V, F = fibonacci_sphere(100000)
@@ -54,7 +59,20 @@ def make_workload(name):
         z = np.load(os.path.join(ROOT, "tests", "golden", "knot.npz"))
         fo, fv = z["face_offsets"], z["face_vertices"]
         V, F = z["V"], [fv[fo[i]:fo[i + 1]].tolist() for i in range(len(fo) - 1)]
-    return V, F, hc, desc
+    return V, F, n, desc
+
+
+def prepare(name):
+    """host half of computeDistance (rows a4-a6) for the workload: (Params, pos, nrm, area, desc)"""
+    import shm3d
+    V, F, n, desc = make_workload(name)
+    hc = int(round(np.log2(n / 16.0)))
+    p, pos, nrm, area, _ = shm3d.prepare_mesh(V, F, hCoef=max(hc, 0))
+    if p.nx != n:  # same box c +- 2r, n nodes per axis (the reference itself only produces 16*2^h)
+        side = p.cell * (p.nx - 1)
+        p.nx = p.ny = p.nz = n
+        p.cell = side / (n - 1)
+    return p, pos, nrm, area, desc
 
 
 def peaks():
@@ -160,8 +178,7 @@ def run_reference(args):
     if rank != 0:
         return
     import shm3d
-    V, F, hc, desc = make_workload(args.workload)
-    p, pos, nrm, area, _ = shm3d.prepare_mesh(V, F, hCoef=hc)  # host-only call (no device code)
+    p, pos, nrm, area, desc = prepare(args.workload)  # host-only calls (no device code)
     from oracle import shm_oracle as o
     threads = o.max_threads()
     M = len(area)
@@ -180,7 +197,8 @@ def run_reference(args):
               f"cannot be compiled here (Eigen not vendored)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if args.workload == DEFAULT_BY_GPUS.get(args.gpus, "sphere512") else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "grid": [p.nx, p.ny, p.nz], "sources": M},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -218,8 +236,7 @@ def run_ours(args):
             dist.barrier()
 
     # ---- workload (host) and contexts
-    V, F, hc, desc = make_workload(args.workload)
-    p, pos, nrm, area, h = shm3d.prepare_mesh(V, F, hCoef=hc)
+    p, pos, nrm, area, desc = prepare(args.workload)
     M = len(area)
     N = p.N
     if world > 1:
@@ -280,7 +297,7 @@ def run_ours(args):
     hbm_peak, sm_max, peak_src = peaks()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:  # the capture is of the single-GPU launch
         try:
             traffic = json.load(open(tpath)).get(args.workload, {}).get("pcg_update_p_stencil_dram_bytes_per_launch")
         except Exception:
@@ -307,7 +324,7 @@ def run_ours(args):
 
     # ---- end-to-end arm through the reference-facing interface, host buffers (pinned result buffer owned by the solver)
     solver = shm3d.SignedHeatGridSolver(context=ctx)
-    opts = shm3d.SignedHeat3DOptions(hCoef=hc)
+    opts = shm3d.SignedHeat3DOptions()
     h_pos, h_nrm, h_area = np.ascontiguousarray(pos), np.ascontiguousarray(nrm), np.ascontiguousarray(area)
 
     def step_host():
@@ -336,15 +353,21 @@ def run_ours(args):
            "d2h_bytes_per_step": int(8 * N), "ms_per_step": 1e3 * float(te[0]) / args.steps,
            "api": "shm3d.SignedHeatGridSolver -> shm3d_solve (host double arrays in, double field out)"}
 
+    default_wl = args.workload == DEFAULT_BY_GPUS.get(world, "sphere512")
+    scaling = "weak" if default_wl else "strong"
+    scaling_note = ("default workloads hold ~512^3 nodes per GPU: 512^3 / 640^3 / 768^3 / 1024^3 at 1 / 2 / 4 / 8 GPUs "
+                    "(1.00 / 0.98 / 0.84 / 1.00 x 512^3 per GPU), same 1e5-triangle sphere" if default_wl else
+                    "fixed grid given by --workload, z-slabs split over the ranks")
     if rank == 0:
         cpu = cpu_baseline_obj(p, M, pos, nrm, area) if world == 1 and not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "grid": [p.nx, p.ny, p.nz], "sources": M, "l2": "working set "
                            f"{4 * N / 1e6:.0f} MB per grid vector >> 126 MB L2 (no explicit flush needed)"
                            if 4 * N > 4 * 126e6 else "L2 flushed implicitly by the 3-component Y write of Steps 1-2",
                            "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+                           "nodes_per_gpu": N // world, "scaling_note": scaling_note,
                            "cull_tau": 12.0, "timing": "CUDA events on the solver's stream, max over ranks"},
                 "wall_ms_per_step": wall_ms / args.steps, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "roofline_sum": roofline_sum, "cpu_baseline": cpu,
@@ -368,9 +391,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sphere512", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: ~512^3 nodes per GPU (sphere512 / 640 / 768 / 1024 at 1 / 2 / 4 / 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = DEFAULT_BY_GPUS.get(args.gpus, "sphere512")
     if args.impl == "reference":
         run_reference(args)
     else:
