@@ -131,6 +131,12 @@ int shm3d_solve_device(shm3d_ctx* ctx, const shm3d_params* p, int64_t n_sources,
 int shm3d_step12(shm3d_ctx* ctx, const shm3d_params* p, int64_t n_sources, const double* pos, const double* nrm,
                  const double* area, float* Y_out, shm3d_stats* stats);
 
+/* Steps 1-2 at arbitrary query points instead of grid nodes -- what the reference's tet solver evaluates at tet
+ * barycentres (src/signed_heat_tet_solver.cpp:54-72, :131-147).  query: double[n_query][3];
+ * Y_out: float[n_query][3] (interleaved unit vectors).  Every source is evaluated at every point (no culling). */
+int shm3d_step12_points(shm3d_ctx* ctx, double lambda, int64_t n_sources, const double* pos, const double* nrm,
+                        const double* area, int64_t n_query, const double* query, float* Y_out);
+
 /* b = cell^2 * D^T Y for a given Y (component-major float[3][local N]) -> b_out float[local N]. */
 int shm3d_rhs(shm3d_ctx* ctx, const shm3d_params* p, const float* Y, float* b_out);
 

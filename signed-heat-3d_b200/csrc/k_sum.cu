@@ -267,7 +267,72 @@ k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Steps 1-2 at ARBITRARY query points (the tet solver evaluates the same sum at tet barycentres,
+// reference src/signed_heat_tet_solver.cpp:54-72, :131-147 -- SURVEY.md section 8f row N4).  One thread per query
+// point, sources tiled through shared memory, two passes: (1) exact nearest-source distance r0, (2) the sum with
+// exp(-lambda (r - r0)) so the exponent is <= 0 whatever lambda*r is.  No culling: every source at every point.
+constexpr int kPtsThreads = 256;
+__global__ void __launch_bounds__(kPtsThreads) k_sum_points(int n_src, const float4* __restrict__ src_pos,
+                                                            const float4* __restrict__ src_wn, float lam2, long long n_q,
+                                                            const float4* __restrict__ qpts, float* __restrict__ Y) {
+    __shared__ float4 s_p[kPtsThreads], s_n[kPtsThreads];
+    const long long qi = (long long)blockIdx.x * kPtsThreads + threadIdx.x;
+    const float4 qp = qi < n_q ? qpts[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float best = 3e38f;
+    for (int base = 0; base < n_src; base += kPtsThreads) {
+        const int cnt = min(kPtsThreads, n_src - base);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) s_p[threadIdx.x] = src_pos[base + threadIdx.x];
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < cnt; t++) {
+            const float dx = qp.x - s_p[t].x, dy = qp.y - s_p[t].y, dz = qp.z - s_p[t].z;
+            best = fminf(best, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        }
+    }
+    const float cm = lam2 * sqrtf(best);
+    float X0 = 0.f, X1 = 0.f, X2 = 0.f;
+    for (int base = 0; base < n_src; base += kPtsThreads) {
+        const int cnt = min(kPtsThreads, n_src - base);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            s_p[threadIdx.x] = src_pos[base + threadIdx.x];
+            s_n[threadIdx.x] = src_wn[base + threadIdx.x];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int t = 0; t < cnt; t++) {
+            const float4 p = s_p[t], n = s_n[t];
+            const float dx = qp.x - p.x, dy = qp.y - p.y, dz = qp.z - p.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float ri = fast_rsqrt(r2);
+            const float w = fast_ex2(fmaf(-lam2, r2 * ri, cm)) * ri;
+            X0 = fmaf(w, n.x, X0);
+            X1 = fmaf(w, n.y, X1);
+            X2 = fmaf(w, n.z, X2);
+        }
+    }
+    if (qi < n_q) {
+        const float s = fmaxf(fmaxf(fabsf(X0), fabsf(X1)), fabsf(X2));
+        const float a = X0 / s, b = X1 / s, c = X2 / s;
+        const float nrm = sqrtf(a * a + b * b + c * c);
+        Y[3 * qi] = a / nrm;
+        Y[3 * qi + 1] = b / nrm;
+        Y[3 * qi + 2] = c / nrm;
+    }
+}
+
 }  // namespace
+
+void launch_heat_sum_points(int n_src, const float4* src_pos, const float4* src_wn, float lam2, long long n_q,
+                            const float4* qpts, float* Y, cudaStream_t stream) {
+    if (n_q <= 0) return;
+    k_sum_points<<<(unsigned)((n_q + kPtsThreads - 1) / kPtsThreads), kPtsThreads, 0, stream>>>(n_src, src_pos, src_wn, lam2,
+                                                                                                  n_q, qpts, Y);
+    SHM3D_LAUNCHED();
+    SHM3D_CUDA_CHECK(cudaGetLastError());
+}
 
 void launch_heat_sum(const SumParams& P, const float4* cl_bounds, const int2* cl_range, const float4* src_pos,
                      const float4* src_wn, float* Y, size_t ystride, unsigned long long* pair_counter,

@@ -19,6 +19,10 @@ void launch_heat_sum(const SumParams& P, const float4* cl_bounds, const int2* cl
                      const float4* src_wn, float* Y, size_t ystride, unsigned long long* pair_counter,
                      cudaStream_t stream);
 
+// Steps 1-2 at arbitrary query points (xyz relative to the source origin, w unused): Y interleaved float[n_q][3]
+void launch_heat_sum_points(int n_src, const float4* src_pos, const float4* src_wn, float lam2, long long n_q,
+                            const float4* qpts, float* Y, cudaStream_t stream);
+
 // ---------------------------------------------------------------- grid operators (grid_ops.cu)
 // A "level" is a cell-centred box grid of nx*ny*nzl local nodes (z-slab [k0,k1) of nz planes).
 struct LevelDims {

@@ -70,6 +70,8 @@ struct shm3d_ctx {
     DevBuf<float> d_pinv;
     DevBuf<double> d_phi64, shift_part;
     DevBuf<long long> d_coinc;
+    DevBuf<float4> d_qpts;
+    DevBuf<float> d_qY;
     std::vector<MGLevel> levels;
 };
 
@@ -1022,6 +1024,38 @@ int shm3d_step12(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double*
     S.st.kernel_launches = g_kernel_launches - l0;
     S.st.ms_total = now_ms() - t0;
     if (stats) *stats = S.st;
+    SHM3D_API_END(ctx)
+}
+
+int shm3d_step12_points(shm3d_ctx* ctx, double lambda, int64_t M, const double* pos, const double* nrm,
+                        const double* area, int64_t nq, const double* query, float* Y_out) {
+    SHM3D_API_BEGIN(ctx)
+    if (!pos || !nrm || !area || !query || !Y_out || M <= 0 || nq <= 0) throw Error(SHM3D_ERR_INVALID_ARG, "NULL / empty input");
+    if (!(lambda > 0) || !std::isfinite(lambda)) throw Error(SHM3D_ERR_INVALID_ARG, "lambda must be positive and finite");
+    if (M > 0x7fffffff) throw Error(SHM3D_ERR_INVALID_ARG, "too many sources");
+    cudaStream_t s = ctx->stream;
+    // origin = centre of the sources' bounding box (fp32 positions are stored relative to it)
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = 0; i < M; i++)
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::min(lo[a], pos[3 * i + a]);
+            hi[a] = std::max(hi[a], pos[3 * i + a]);
+        }
+    const double origin[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+    ClusteredSources cs;
+    build_clusters(M, pos, nrm, area, origin, lambda, 4.0, cs);  // (also validates: non-finite input -> SHM3D_ERR_NONFINITE)
+    ctx->d_spos.upload(cs.pos, s);
+    ctx->d_swn.upload(cs.wn, s);
+    std::vector<float4> q((size_t)nq);
+    for (int64_t i = 0; i < nq; i++)
+        q[i] = make_float4((float)(query[3 * i] - origin[0]), (float)(query[3 * i + 1] - origin[1]),
+                           (float)(query[3 * i + 2] - origin[2]), 0.f);
+    ctx->d_qpts.upload(q, s);
+    ctx->d_qY.alloc((size_t)3 * nq);
+    launch_heat_sum_points((int)M, ctx->d_spos.p, ctx->d_swn.p, (float)(lambda * 1.4426950408889634), nq, ctx->d_qpts.p,
+                           ctx->d_qY.p, s);
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(Y_out, ctx->d_qY.p, (size_t)3 * nq * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
     SHM3D_API_END(ctx)
 }
 

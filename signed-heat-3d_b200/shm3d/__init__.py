@@ -54,7 +54,7 @@ class Shm3dError(RuntimeError):
 EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm3d_nccl_unique_id", "shm3d_ctx_destroy",
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
-           "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free"]
+           "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points"]
 
 _lib = None
 
@@ -82,6 +82,7 @@ def lib():
         L.shm3d_solve_device.argtypes = [vp, PP, C.c_int64, vp, vp, vp, vp, SP]
         L.shm3d_step12.argtypes = [vp, PP, C.c_int64, dp, dp, dp, fp, SP]
         L.shm3d_rhs.argtypes = [vp, PP, fp, fp]
+        L.shm3d_step12_points.argtypes = [vp, C.c_double, C.c_int64, dp, dp, dp, C.c_int64, dp, fp]
         L.shm3d_step3.argtypes = [vp, PP, C.c_int64, dp, dp, fp, dp, SP]
         L.shm3d_prepare_mesh.argtypes = [dp, C.c_int64, i64p, i64p, C.c_int64, C.c_double, C.c_double, C.c_double, PP,
                                          dp, dp, dp, dp]
@@ -265,6 +266,14 @@ class Context:
         self._check(lib().shm3d_step12(self._h, C.byref(p), len(area), _dp(pos), _dp(nrm), _dp(area), _fp(Y),
                                        C.byref(st)))
         return Y, st
+
+    def step12_points(self, lambda_, pos, nrm, area, query):
+        """Steps 1-2 at arbitrary query points [Q,3] -> unit vectors float32[Q,3] (tet-barycentre queries, row N4)."""
+        pos, nrm, area, query = _c64(pos), _c64(nrm), _c64(area), _c64(query)
+        Y = np.empty((len(query), 3), dtype=np.float32)
+        self._check(lib().shm3d_step12_points(self._h, float(lambda_), len(area), _dp(pos), _dp(nrm), _dp(area),
+                                              len(query), _dp(query), _fp(Y)))
+        return Y
 
     def rhs(self, p: Params, Y):
         Y = np.ascontiguousarray(Y, dtype=np.float32)

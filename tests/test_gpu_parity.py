@@ -187,6 +187,24 @@ def test_fast_integration_matches_oracle_bfs(gpu_ctx, name, hc):
     assert rel(phi, ref) < PHI_TOL
 
 
+def test_step12_at_arbitrary_query_points(gpu_ctx):
+    """Row N4: the same Steps 1-2 sum at arbitrary points (the tet solver's barycentre queries,
+    src/signed_heat_tet_solver.cpp:54-72) against a direct fp64 evaluation; lambda*r up to ~600 must not underflow."""
+    z, F = load_golden("bunny_small")
+    s = o.mesh_sources(z["V"], F)
+    rng = np.random.default_rng(5)
+    for lam in (o.lambda_from_h(s["h"]), 120.0):
+        Q = rng.uniform(-1, 1, size=(777, 3)) * 2.0 * s["radius"] + s["centroid"]
+        Y = gpu_ctx.step12_points(lam, s["pos"], s["nrm"], s["area"], Q)
+        d = Q[:, None, :] - s["pos"][None, :, :]
+        r = np.linalg.norm(d, axis=2)
+        w = s["area"][None, :] * np.exp(-lam * (r - r.min(axis=1, keepdims=True))) / r   # shifted: same direction
+        X = (w[:, :, None] * s["nrm"][None, :, :]).sum(axis=1)
+        Yref = X / np.linalg.norm(X, axis=1, keepdims=True)
+        assert np.isfinite(Y).all()
+        assert np.abs(Y - Yref).max() < 3e-5
+
+
 # ---------------------------------------------------------------- error behaviour
 def test_nonfinite_source_is_rejected(gpu_ctx):
     V, F = icosphere(1)
