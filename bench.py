@@ -368,7 +368,7 @@ def run_ours(args):
                            if 4 * N > 4 * 126e6 else "L2 flushed implicitly by the 3-component Y write of Steps 1-2",
                            "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
                            "nodes_per_gpu": N // world, "scaling_note": scaling_note,
-                           "cull_tau": 12.0, "timing": "CUDA events on the solver's stream, max over ranks"},
+                           "cull_tau": 10.0, "timing": "CUDA events on the solver's stream, max over ranks"},
                 "wall_ms_per_step": wall_ms / args.steps, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "roofline_sum": roofline_sum, "cpu_baseline": cpu,
                 "stages_ms": {"h2d+cluster": stats.ms_h2d, "sum(step1-2)": stats.ms_sum, "rhs": stats.ms_rhs,

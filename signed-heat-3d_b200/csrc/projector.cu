@@ -502,7 +502,9 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
     // ---- nested dissection ordering
     ND nd;
     nd.cell = rows.cell.data();
-    nd.leaf = 40;
+    // leaves of ~128 rows: two fewer tree levels (= 4 fewer launches per application) than with 40, for +8 % host time
+    nd.leaf = 128;
+    if (const char* e = getenv("SHM3D_ND_LEAF")) nd.leaf = std::max(8, atoi(e));
     nd.order.reserve(m);
     {
         std::vector<int> all(m);

@@ -469,7 +469,9 @@ struct Solver {
         P.oz = (float)(G.bmin[2] - cs.origin[2]);
         P.cell = (float)G.cell;
         P.lam2 = (float)(p->lambda * 1.4426950408889634);
-        double tau = p->cull_tau > 0 ? p->cull_tau : 12.0;
+        // default 10: measured culling error (tools/tau_probe.py) max|dY| <= 7e-7, phi <= 1e-5 rel-L2 vs brute force on
+        // the coarse meshes (worst case), indistinguishable from tau = inf against the fp64 oracle on knot.obj @128^3
+        double tau = p->cull_tau > 0 ? p->cull_tau : 10.0;
         P.tol = std::isinf(tau) ? INFINITY : (float)(tau / p->lambda);
         P.n_clusters = (int)cs.bounds.size();
         SHM3D_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), s));
@@ -687,6 +689,9 @@ struct Solver {
         float* pbuf[2] = {c->vp.ip(), c->vp2.ip()};
         // relative preconditioned residual; the unpreconditioned fallback (odd grids) needs a tighter bar for the same
         // error in phi because its residual norm under-weights the smooth error components
+        // default 3e-6: on knot.obj @128^3 the distance to the fp64 oracle is ~3e-6 for every tolerance <= 1e-5 (the
+        // floor set by the fp32 Steps 1-2), 4.3e-6 at 3e-5 and 3e-5 at 1e-4 -- against a parity bar of 1e-4; at 512^3
+        // run-to-run differences of ~3e-5 were seen at 1e-5, hence the tighter default
         const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : (use_mg ? 3e-6 : 3e-7);
         const int maxit = p->cg_max_iters > 0 ? p->cg_max_iters : 2000;
         const bool verbose = (p->flags & SHM3D_FLAG_VERBOSE) != 0;
