@@ -78,6 +78,7 @@ struct shm3d_ctx {
 namespace shm3d {
 
 constexpr int kRhoRing = 64;
+constexpr size_t kReplicateBelow = (size_t)128 * 128 * 128;
 enum Sc { kRho = 0, kPQ, kSumR, kRZ, kSumZ, kRhoNew, kRho0, kShiftNum, kShiftDen, kTmp, kNumSc = 16 };
 
 // ------------------------------------------------------------------------------------------------
@@ -531,9 +532,11 @@ struct Solver {
         geo.push_back({G.bmin[0], G.bmin[1], G.bmin[2], G.cell});
         std::vector<char> repl(1, 0);
         if (use_mg) {
-            // Slab-parallel runs: a level stays z-partitioned while the slab boundaries coarsen cleanly and every rank
-            // keeps at least two planes; below that (<= 32^3-ish grids) every rank holds the whole level ("replicated":
-            // the restricted right-hand side is all-gathered once, everything further down needs no communication).
+            // Slab-parallel runs: a level stays z-partitioned while the slab boundaries coarsen cleanly and it is big enough
+            // for the split to pay; from 128^3 down every rank holds the whole level ("replicated": the restricted
+            // right-hand side is all-gathered once, everything further down needs no communication).  Kernels on
+            // <= 128^3 grids are launch-latency-bound on one GPU already, so replicating them costs nothing while it
+            // removes ~7 halo exchanges and 5 constraint all-reduces per level and V-cycle.
             bool replicated = false;
             while (true) {
                 const LevelDims Lf = dims.back();
@@ -546,7 +549,7 @@ struct Solver {
                     const bool clean = !(Lf.k0 & 1) && !(Lf.k1 & 1) && Lc.nz % c->world == 0 && Lc.k0 == c->rank * per &&
                                        Lc.k1 == (c->rank + 1) * per;
                     if (!clean) break;  // uneven slabs: no hierarchy below this level
-                    if (per < 2 || (size_t)Lc.nx * Lc.ny * Lc.nz <= 32768) replicated = true;
+                    if (per < 2 || (size_t)Lc.nx * Lc.ny * Lc.nz <= kReplicateBelow) replicated = true;
                 }
                 if (c->world == 1 && ((Lf.k0 & 1) || (Lf.k1 & 1))) break;
                 if (replicated) {
@@ -621,13 +624,14 @@ struct Solver {
     bool level_projected(int l) const { return constrained_mg && l >= cmg_from && c->levels[l].proj; }
 
     // one (projected-)Jacobi sweep: xo = x + Pi w D^-1 (b - K x).  dot_acc: also r.z and sum z (last fine sweep).
-    void smooth_sweep(int l, const float* b, const double* sum_b, double n_global, double* dot_acc = nullptr) {
+    void smooth_sweep(int l, const float* b, const double* sum_b, double n_global, double* dot_acc = nullptr,
+                      bool exchange = true) {
         MGLevel& Lv = c->levels[l];
         if (dot_acc) launch_mg_smooth_dot(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, dot_acc, s);
         else launch_mg_smooth(Lv.L, Lv.tmp.ip(), Lv.x.ip(), b, sum_b, n_global, omega, s);
         if (level_projected(l)) Lv.proj->apply_update(Lv.tmp.ip(), Lv.x.ip(), s);
         std::swap(Lv.x, Lv.tmp);
-        if (dist_level(l)) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
+        if (exchange && dist_level(l)) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
     }
 
     // V-cycle: levels[l].x = V(b - mean)   (mean only at level 0, passed as device scalar).
@@ -667,9 +671,19 @@ struct Solver {
         }
         vcycle(l + 1, Lc.b.ip(), nullptr, 1.0);
         if (dist_level(l + 1)) c->dist->exchange_halo(Lc.x.ip(), Lc.L, s);
-        launch_mg_prolong_add(Lv.L, Lc.L, Lv.x.ip(), Lc.x.ip(), s);
-        if (dl) c->dist->exchange_halo(Lv.x.ip(), Lv.L, s);
-        for (int k = 0; k < nul; k++) smooth_sweep(l, b, sum_b, n_global, (k + 1 == nul) ? dot_acc : nullptr);
+        if (dl) {
+            // the correction of the two ghost planes follows from the coarse ghost planes: no exchange afterwards
+            LevelDims Le = Lv.L;
+            Le.k0 = std::max(0, Lv.L.k0 - 1);
+            Le.k1 = std::min(Lv.L.nz, Lv.L.k1 + 1);
+            launch_mg_prolong_add(Le, Lc.L, Lv.x.ip() - (size_t)(Lv.L.k0 - Le.k0) * Lv.L.plane(), Lc.x.ip(), s);
+        } else {
+            launch_mg_prolong_add(Lv.L, Lc.L, Lv.x.ip(), Lc.x.ip(), s);
+        }
+        // (the halo of the final iterate is exchanged by whoever reads it next: the parent level before prolongating,
+        // the PCG after projecting z)
+        for (int k = 0; k < nul; k++)
+            smooth_sweep(l, b, sum_b, n_global, (k + 1 == nul) ? dot_acc : nullptr, /*exchange=*/k + 1 < nul);
     }
 
     // ---------------------------------------------------------------- constrained PCG
