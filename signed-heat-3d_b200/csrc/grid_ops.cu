@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kT) k_mg_smooth(LevelDims L, float* __restrict
 // x1 at the six neighbours is recomputed from b (their d from their coordinates): 2 words of traffic instead of 5.
 template <int V>
 __global__ void __launch_bounds__(kT) k_mg_smooth01(LevelDims L, float* __restrict__ xo, const float* __restrict__ b,
-                                                    const double* sum_b, double n_global, float omega) {
+                                                    const double* sum_b, double n_global, float omega, float omega2) {
     const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
     const unsigned int pl = (unsigned int)L.nx * (unsigned int)L.ny;
     GRID_STRIDE_GROUPS(L, V) {
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kT) k_mg_smooth01(LevelDims L, float* __restri
             const float xd = zm ? omega * (bd.v[t] - shift) / (float)(cx[t] + cy + cz_m) : 0.f;
             const float xf = zp ? omega * (bf.v[t] - shift) / (float)(cx[t] + cy + cz_p) : 0.f;
             const float Kx = d * x1c[t] - (xl + xr + xa + xb + xd + xf);
-            o.v[t] = x1c[t] + omega * ((bc.v[t] - shift) - Kx) / d;
+            o.v[t] = x1c[t] + omega2 * ((bc.v[t] - shift) - Kx) / d;
         }
         o.st(xo + e);
     }
@@ -724,9 +724,9 @@ void launch_mg_smooth_dot(const LevelDims& L, float* xo, const float* x, const f
     POST();
 }
 void launch_mg_smooth01(const LevelDims& L, float* xo, const float* b, const double* sum_b, double n_global, float omega,
-                        cudaStream_t s) {
-    if (vec4(L)) k_row_smooth01<<<nblk_rows(L), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega);
-    else k_mg_smooth01<1><<<nblk(L.n()), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega);
+                        float omega2, cudaStream_t s) {
+    if (vec4(L)) k_row_smooth01<<<nblk_rows(L), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega, omega2);
+    else k_mg_smooth01<1><<<nblk(L.n()), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega, omega2);
     POST();
 }
 void launch_update_p_stencil(const LevelDims& L, float* p_new, const float* p_old, const float* z, float* q,

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kT) k_row_residual(LevelDims L, const float* _
 // ---------------------------------------------------------------- first two Jacobi sweeps from a zero guess, one pass over b
 //   x1 = omega (b - shift)/d ;  x2 = x1 + omega ((b - shift) - K'x1)/d, with x1 of the six neighbours recomputed from b
 __global__ void __launch_bounds__(kT) k_row_smooth01(LevelDims L, float* __restrict__ xo, const float* __restrict__ bb,
-                                                     const double* sum_b, double n_global, float omega) {
+                                                     const double* sum_b, double n_global, float omega, float omega2) {
     const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
     ROWS_BEGIN(L)
         // diagonals of this row and of the four adjacent rows (warp-uniform)
@@ -189,10 +189,11 @@ __global__ void __launch_bounds__(kT) k_row_smooth01(LevelDims L, float* __restr
         x_neighbours(c, lane, q, nq, sl, sr, l, r);
         const float4 K = stencil_quad(c, a, b, d, f, l, r, e0 ? ced : cin, cin, e3 ? ced : cin);
         float4 o;
-        o.x = fmaf(e0 ? wc_ed : wc_in, (rhs.x - shift) - K.x, c.x);
-        o.y = fmaf(wc_in, (rhs.y - shift) - K.y, c.y);
-        o.z = fmaf(wc_in, (rhs.z - shift) - K.z, c.z);
-        o.w = fmaf(e3 ? wc_ed : wc_in, (rhs.w - shift) - K.w, c.w);
+        const float w2_in = omega2 / cin, w2_ed = omega2 / ced;  // the second sweep may use another damping (Chebyshev)
+        o.x = fmaf(e0 ? w2_ed : w2_in, (rhs.x - shift) - K.x, c.x);
+        o.y = fmaf(w2_in, (rhs.y - shift) - K.y, c.y);
+        o.z = fmaf(w2_in, (rhs.z - shift) - K.z, c.z);
+        o.w = fmaf(e3 ? w2_ed : w2_in, (rhs.w - shift) - K.w, c.w);
         if (act) st4(xo + e, o);
     ROWS_END()
 }

@@ -81,7 +81,7 @@ void launch_mg_smooth_dot(const LevelDims& L, float* xout_padded, const float* x
                           const double* sum_b, double n_global, float omega, double* acc, cudaStream_t s);
 // the first two sweeps from a zero guess in one pass over b (b must have valid ghost planes in slab-parallel runs)
 void launch_mg_smooth01(const LevelDims& L, float* xout_padded, const float* b_padded, const double* sum_b,
-                        double n_global, float omega, cudaStream_t s);
+                        double n_global, float omega, float omega2, cudaStream_t s);
 // p_new = (z - mean_z) + beta p_old ; q = K' p_new ; acc[0] = sum p_new q  (p_new != p_old: neighbours are recomputed)
 void launch_update_p_stencil(const LevelDims& L, float* p_new_padded, const float* p_old_padded, const float* z_padded,
                              float* q_padded, const double* sum_z, double n_global, const double* rho_new,
