@@ -201,9 +201,17 @@ struct ND {
     }
 };
 
+}  // namespace
+// AVX2 inner kernels (host_blas.cpp)
+void host_transpose_panel(const double* F, int f, int k0, int nb, int k1, double* Bt, int ldb);
+void host_syrk_rows(double* F, int f, int k0, int nb, int k1, int i0, int i1, const double* Bt, int ldb);
+void host_tri_inverse_rows(const double* F, int f, int s, double* W, int c0, int c1);
+namespace {
+
 // blocked partial Cholesky of the leading s columns of the f x f symmetric matrix F (row-major, lower part used)
 bool partial_cholesky(double* F, int f, int s, bool par) {
     const int NB = 48;
+    std::vector<double> Bt;
     for (int k0 = 0; k0 < s; k0 += NB) {
         const int k1 = std::min(s, k0 + NB), nb = k1 - k0;
         // diagonal block
@@ -231,26 +239,21 @@ bool partial_cholesky(double* F, int f, int s, bool par) {
                 }
             }
         };
-        // trailing update (lower triangle): F[i][j] -= <row_i[k0:k1], row_j[k0:k1]>
-        auto trailing = [&](int i0, int i1) {
-            for (int i = i0; i < i1; i++) {
-                const double* ri = F + (size_t)i * f + k0;
-                double* out = F + (size_t)i * f;
-                for (int j = k1; j <= i; j++) {
-                    const double* rj = F + (size_t)j * f + k0;
-                    double acc = 0;
-                    for (int t = 0; t < nb; t++) acc += ri[t] * rj[t];
-                    out[j] -= acc;
-                }
-            }
-        };
+        // trailing update (lower triangle): F[i][j] -= <row_i[k0:k1], row_j[k0:k1]> as C -= A * Bt (host_blas.cpp)
         const int rows = f - k1;
+        if (rows <= 0) continue;
+        const int ldb = (rows + 7) & ~7;
+        auto trailing = [&](int i0, int i1) { host_syrk_rows(F, f, k0, nb, k1, i0, i1, Bt.data(), ldb); };
         if (par && rows > 256) {
             const int chunk = 16, nch = (rows + chunk - 1) / chunk;
             Pool::get().parallel_for(nch, [&](int c) { panel_rows(k1 + c * chunk, std::min(f, k1 + (c + 1) * chunk)); });
+            Bt.resize((size_t)nb * ldb);
+            host_transpose_panel(F, f, k0, nb, k1, Bt.data(), ldb);
             Pool::get().parallel_for(nch, [&](int c) { trailing(k1 + c * chunk, std::min(f, k1 + (c + 1) * chunk)); });
         } else {
             panel_rows(k1, f);
+            Bt.resize((size_t)nb * ldb);
+            host_transpose_panel(F, f, k0, nb, k1, Bt.data(), ldb);
             trailing(k1, f);
         }
     }
@@ -578,6 +581,8 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
     by_h.assign(max_h + 1, {});
     for (int t = 0; t < nT; t++) by_h[T[t].height].push_back(t);
     std::vector<std::vector<double>> U(nT);  // update matrices (b x b, lower used)
+    std::mutex prof_mu;
+    double prof_t[6] = {0, 0, 0, 0, 0, 0};
     const int nthreads = Pool::get().size();
     bool ok = true;
     for (int h = 0; h <= max_h && ok; h++) {
@@ -589,6 +594,7 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
             const int t = lv[li];
             TreeNode& n = T[t];
             const int s = n.s1 - n.s0, b = (int)n.B.size(), f = s + b;
+            const double tp0 = wall();
             std::vector<double> F((size_t)f * f, 0.0);
             auto loc = [&](int q) -> int {
                 if (q < n.s1) return q - n.s0;
@@ -615,10 +621,12 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
                     for (int j = 0; j <= i; j++) F[(size_t)map[i] * f + map[j]] += Uc[(size_t)i * cb + j];
                 std::vector<double>().swap(U[ch]);
             }
+            const double tp1 = wall();
             if (!partial_cholesky(F.data(), f, s, !outer)) {
                 ok = false;
                 return;
             }
+            const double tp2 = wall();
             // update matrix for the parent
             if (b > 0) {
                 U[t].resize((size_t)b * b);
@@ -646,13 +654,29 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
                     for (int c = 0; c <= k; c++) Gi[c] += l * Wk[c];
                 }
             };
-            if (!outer && s > 256) Pool::get().parallel_for(s, w_col);
-            else for (int c = 0; c < s; c++) w_col(c);
+            (void)w_col;
+            const double tp3 = wall();
+            if (!outer && s > 256) {
+                const int nblk = std::min(nthreads * 2, (s + 63) / 64);  // independent column ranges
+                Pool::get().parallel_for(nblk, [&](int q) {
+                    host_tri_inverse_rows(F.data(), f, s, FW, (int)((long long)s * q / nblk), (int)((long long)s * (q + 1) / nblk));
+                });
+            } else {
+                host_tri_inverse_rows(F.data(), f, s, FW, 0, s);
+            }
+            const double tp4 = wall();
             if (!outer && b > 256) Pool::get().parallel_for(b, g_row);
             else for (int i = 0; i < b; i++) g_row(i);
+            const double tp5 = wall();
             for (int r = 0; r < s; r++) {
                 for (int c = 0; c < s; c++) BW[(size_t)r * f + c] = FW[(size_t)c * s + r];
                 for (int c = 0; c < b; c++) BW[(size_t)r * f + s + c] = -FW[(size_t)(s + c) * s + r];
+            }
+            if (dbg) {
+                const double tp6 = wall();
+                std::lock_guard<std::mutex> lk(prof_mu);
+                prof_t[0] += tp1 - tp0; prof_t[1] += tp2 - tp1; prof_t[2] += tp3 - tp2; prof_t[3] += tp4 - tp3;
+                prof_t[4] += tp5 - tp4; prof_t[5] += tp6 - tp5;
             }
         };
         if (outer) Pool::get().parallel_for((int)lv.size(), do_node);
@@ -660,7 +684,11 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
         if (dbg) fprintf(stderr, "[shm3d]   height %d: %d nodes outer=%d %.4fs\n", h, (int)lv.size(), (int)outer, wall() - tl);
     }
     (void)0;
-    if (dbg) fprintf(stderr, "[shm3d] numeric factorisation %.3fs, %.1f MB\n", wall() - tdbg, out.mat_size * 8e-6);
+    if (dbg) {
+        fprintf(stderr, "[shm3d] numeric factorisation %.3fs, %.1f MB\n", wall() - tdbg, out.mat_size * 8e-6);
+        fprintf(stderr, "[shm3d]   thread-seconds: assemble %.3f  cholesky %.3f  update-matrix %.3f  W %.3f  G %.3f  transpose %.3f\n",
+                prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5]);
+    }
     if (!ok)
         throw Error(SHM3D_ERR_FACTORIZATION,
                     "constraint system A A^T is not positive definite (coincident / dependent source constraints)");
