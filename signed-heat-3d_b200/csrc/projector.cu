@@ -57,6 +57,8 @@ void build_constraint_rows(int nx, int ny, int nz, const double bmin[3], double 
 // ================================================================================================
 namespace {
 
+int g_ranks_on_node = 1;  // set through set_host_ranks_hint() before the pool is first used
+
 // Small blocking thread pool for the host factorisation.  (OpenMP's spin-waiting workers made the many short
 // parallel regions of the multifrontal sweep several times SLOWER on cgroup-limited and 128-thread hosts.)
 class Pool {
@@ -94,8 +96,10 @@ class Pool {
 
   private:
     Pool() {
+        // all hardware threads the ranks of this node can share without oversubscribing (a slab-parallel run has
+        // `world` processes factorising at the same time), at most 16
         unsigned hw = std::thread::hardware_concurrency();
-        int nt = (int)std::max(1u, std::min(16u, hw / 2));
+        int nt = (int)std::max(2u, std::min(16u, hw / (unsigned)std::max(1, g_ranks_on_node)));
         if (const char* e = getenv("SHM3D_HOST_THREADS")) nt = std::max(1, atoi(e));
         for (int i = 1; i < nt; i++) workers_.emplace_back([this] { loop(); });
     }
@@ -261,6 +265,8 @@ bool partial_cholesky(double* F, int f, int s, bool par) {
 }
 
 }  // namespace
+
+void set_host_ranks_hint(int ranks_on_node) { g_ranks_on_node = std::max(1, ranks_on_node); }
 
 // ================================================================================================
 // device kernels

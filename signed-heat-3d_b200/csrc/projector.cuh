@@ -53,6 +53,8 @@ struct HostFactor {
     std::vector<double> dinv;              // [m*8] 1/d of each corner node (1 when uniform)
     void solve_host(std::vector<double>& v) const;  // v (permuted order) <- (A D^-1 A^T)^-1 v, same algorithm as the GPU
 };
+// how many ranks share this node's host cores (sizes the factorisation thread pool; call before the first solve)
+void set_host_ranks_hint(int ranks_on_node);
 void factor_constraints(const ConstraintRows& rows, int nx, int ny, int nz, bool uniform, HostFactor& out);
 
 // per tree height: row maps of the forward (f rows per supernode) and backward (s rows) sweeps

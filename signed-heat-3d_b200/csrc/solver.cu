@@ -932,6 +932,7 @@ static int create_common(shm3d_ctx** out, int device, int rank, int world, const
     try {
         SHM3D_CUDA_CHECK(cudaSetDevice(device));
         SHM3D_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        set_host_ranks_hint(world);
         if (world > 1) c->dist.reset(new Dist(rank, world, nccl_id, c->stream));
     } catch (const shm3d::Error& ex) {
         g_create_error = ex.what();
