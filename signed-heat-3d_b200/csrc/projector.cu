@@ -643,14 +643,7 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
             double* FW = mat + n.fwd;
             double* BW = mat + n.bwd;
             std::fill(FW, FW + (size_t)f * s, 0.0);
-            auto w_col = [&](int c) {  // column c of W: solve L11 w = e_c
-                for (int i = c; i < s; i++) {
-                    double v = (i == c) ? 1.0 : 0.0;
-                    const double* Li = F.data() + (size_t)i * f;
-                    for (int k = c; k < i; k++) v -= Li[k] * FW[(size_t)k * s + c];
-                    FW[(size_t)i * s + c] = v / Li[i];
-                }
-            };
+            // W = L11^-1 (host_tri_inverse_rows, by rows in axpy form); G = L21 W
             auto g_row = [&](int i) {  // G[i, c] = sum_{k>=c} L21[i,k] W[k,c]
                 const double* Li = F.data() + (size_t)(s + i) * f;
                 double* Gi = FW + (size_t)(s + i) * s;
@@ -660,7 +653,6 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
                     for (int c = 0; c <= k; c++) Gi[c] += l * Wk[c];
                 }
             };
-            (void)w_col;
             const double tp3 = wall();
             if (!outer && s > 256) {
                 const int nblk = std::min(nthreads * 2, (s + 63) / 64);  // independent column ranges

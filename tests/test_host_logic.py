@@ -32,6 +32,35 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(shm3d.Stats) == 168
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/shm3d_grid.h must be consumable from C (the FFI boundary): compile a C99 program against it with gcc,
+    link it to the shared library, and compare the struct layouts with the ctypes mirror."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "shm3d_grid.h"
+int main(void) {
+    int k0 = -1, k1 = -1;
+    if (shm3d_slab_range(1, 4, 512, &k0, &k1) != SHM3D_OK) return 2;
+    printf("%zu %zu %zu %zu %zu %d %d %s\\n", sizeof(shm3d_params), sizeof(shm3d_stats), offsetof(shm3d_params, cell),
+           offsetof(shm3d_params, cull_tau), offsetof(shm3d_stats, kernel_launches), k0, k1, shm3d_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(shm3d.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-lshm3d_grid", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[0]) == ctypes.sizeof(shm3d.Params) and int(out[1]) == ctypes.sizeof(shm3d.Stats)
+    assert int(out[2]) == shm3d.Params.cell.offset and int(out[3]) == shm3d.Params.cull_tau.offset
+    assert int(out[4]) == shm3d.Stats.kernel_launches.offset
+    assert (int(out[5]), int(out[6])) == (128, 256)
+    assert "sm_100a" in " ".join(out[7:])
+
+
 @pytest.mark.parametrize("name,hc", [("bunny_small", 1), ("polygon-bear", 0), ("knot", 2)])
 def test_prepare_mesh_matches_oracle(name, hc):
     z, F = load_golden(name)
