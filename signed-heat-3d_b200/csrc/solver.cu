@@ -724,7 +724,7 @@ struct Solver {
         const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : (use_mg ? 3e-6 : 3e-7);
         const int maxit = p->cg_max_iters > 0 ? p->cg_max_iters : 2000;
         const bool verbose = (p->flags & SHM3D_FLAG_VERBOSE) != 0;
-        const int kCheck = (verbose || prof.on) ? 1 : 4;
+        const int kCheck = verbose ? 1 : 4;  // (the event profiler is asynchronous: it does not need per-iteration syncs)
         const bool fuse_dot = use_mg && !level_projected(0) && lv.size() > 1 && nu >= 1;
         if (!c->h_rho) SHM3D_CUDA_CHECK(cudaHostAlloc((void**)&c->h_rho, kRhoRing * sizeof(double), cudaHostAllocDefault));
         Timer t(s);
