@@ -5,10 +5,9 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The product path (signed-heat-3d_b200/) never does.
  *
- * Parity status: UNPINNED by the reference's own tests (the reference ships none for
- * this path and cannot be compiled here: Eigen is not vendored).  The restatement is
- * anchored on the reference source, cited per function below, and on the direct KKT
- * LU solve of the same linear system (oracle/shm_oracle.py).
+ * Parity status: checked against the reference's own translation units compiled against a
+ * shim (oracle/ref_shim, oracle/_ref/libshm_ref.so, tests/test_reference_build.py); the
+ * reference ships no tests or golden vectors for this path.  See oracle/shm_oracle.py.
  *
  * Each function cites the reference file:line it follows (paths relative to
  * /root/reference).

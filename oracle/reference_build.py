@@ -1,0 +1,149 @@
+"""
+oracle/reference_build.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes front-end of oracle/_ref/libshm_ref.so: the REFERENCE's own src/signed_heat_grid_solver.cpp and
+src/signed_heat_3d.cpp, compiled unmodified (recipe: oracle/Makefile) against oracle/ref_shim -- a stand-in for the
+slices of geometry-central / Eigen / polyscope those files use.  Everything first-party on the hot path (Step 1-2 loops,
+laplacian(), gradient(), constraint selection, trilinear weights, shift, integrateGreedily) therefore runs as written;
+the one thing the shim cannot provide is Eigen's SparseLU behind solveSquare, which is replaced by a callback that
+solves the assembled KKT system with scipy's SuperLU.
+
+Only tests/ (and bench.py's CPU-reference legs) may import this module.  The library exists only where it was built
+from /root/reference (this container); it travels to the GPU box as a prebuilt file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libshm_ref.so")
+REF_ROOT = "/root/reference"
+_LIB = None
+
+SOLVE_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                       C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+def build(force: bool = False) -> bool:
+    """(Re)build oracle/_ref/libshm_ref.so when the reference tree is present; returns whether the library exists."""
+    if os.path.isdir(os.path.join(REF_ROOT, "src")) and (force or not os.path.exists(LIB_PATH)):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return os.path.exists(LIB_PATH)
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(LIB_PATH)
+        dp, ip, fp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_float)
+        L.ref_compute_distance_mesh.argtypes = [dp, C.c_int64, ip, ip, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int,
+                                                SOLVE_FN, dp, C.c_int64, ip, fp]
+        L.ref_compute_distance_points.argtypes = [dp, dp, dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                  C.c_int, SOLVE_FN, dp, C.c_int64, ip, fp]
+        L.ref_mesh_scalars.argtypes = [dp, C.c_int64, ip, ip, C.c_int64, dp, dp, dp, dp, dp]
+        L.ref_yukawa.argtypes = [dp, dp, C.c_double]
+        L.ref_yukawa.restype = C.c_double
+        L.ref_last_error.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _flatten(faces):
+    off = np.zeros(len(faces) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(f) for f in faces])
+    return np.asarray([v for f in faces for v in f], dtype=np.int64), off
+
+
+class _Solver:
+    """The stand-in for Eigen::SparseLU: scipy SuperLU on the column-compressed matrix the reference assembled."""
+
+    def __init__(self):
+        self.calls = []
+        self.fn = SOLVE_FN(self._solve)
+
+    def _solve(self, n, nnz, colptr, rowidx, val, rhs, x):
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        cp = np.ctypeslib.as_array(colptr, shape=(n + 1,)).copy()
+        ri = np.ctypeslib.as_array(rowidx, shape=(nnz,)).copy()
+        v = np.ctypeslib.as_array(val, shape=(nnz,)).copy()
+        b = np.ctypeslib.as_array(rhs, shape=(n,)).copy()
+        A = sp.csc_matrix((v, ri, cp), shape=(n, n))
+        self.calls.append(dict(n=int(n), nnz=int(nnz), A=A, rhs=b))
+        np.ctypeslib.as_array(x, shape=(n,))[:] = spla.splu(A).solve(b)
+
+
+def compute_distance_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False, return_info=False):
+    """SignedHeatGridSolver::computeDistance(VertexPositionGeometry&, options) of the reference itself."""
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    fv, fo = _flatten(faces)
+    nx = int(2 * 2.0 ** (hCoef + 3))
+    phi = np.empty(nx ** 3)
+    dims = np.zeros(3, dtype=np.int64)
+    bbox = np.zeros(6, dtype=np.float32)
+    s = _Solver()
+    rc = lib().ref_compute_distance_mesh(_dp(V), len(V), _ip(fv), _ip(fo), len(fo) - 1, tCoef, hCoef, scale, int(fast), s.fn,
+                                         _dp(phi), phi.size, _ip(dims), bbox.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    if return_info:
+        return phi, dict(dims=dims, bbox=bbox, solves=s.calls)
+    return phi
+
+
+def compute_distance_points(P, normals, areas, h, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False, return_info=False):
+    """computeDistance(PointPositionNormalGeometry&, options) of the reference; the tufted-triangulation quantities it
+    reads (vertex dual areas, mean edge length) are the caller's."""
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    Nn = np.ascontiguousarray(normals, dtype=np.float64)
+    A = np.ascontiguousarray(areas, dtype=np.float64)
+    nx = int(2 * 2.0 ** (hCoef + 3))
+    phi = np.empty(nx ** 3)
+    dims = np.zeros(3, dtype=np.int64)
+    bbox = np.zeros(6, dtype=np.float32)
+    s = _Solver()
+    rc = lib().ref_compute_distance_points(_dp(P), _dp(Nn), _dp(A), len(P), float(h), tCoef, hCoef, scale, int(fast), s.fn,
+                                           _dp(phi), phi.size, _ip(dims), bbox.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    if return_info:
+        return phi, dict(dims=dims, bbox=bbox, solves=s.calls)
+    return phi
+
+
+def mesh_scalars(V, faces):
+    """centroid / radius / meanEdgeLength / setFaceVectorAreas of src/signed_heat_3d.cpp."""
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    fv, fo = _flatten(faces)
+    nF = len(fo) - 1
+    c = np.zeros(3)
+    r = C.c_double()
+    h = C.c_double()
+    area = np.zeros(nF)
+    nrm = np.zeros((nF, 3))
+    rc = lib().ref_mesh_scalars(_dp(V), len(V), _ip(fv), _ip(fo), nF, _dp(c), C.byref(r), C.byref(h), _dp(area), _dp(nrm))
+    if rc != 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+    return dict(centroid=c, radius=r.value, h=h.value, area=area, nrm=nrm)
+
+
+def yukawa(x, y, lam):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    return float(lib().ref_yukawa(_dp(x), _dp(y), float(lam)))

@@ -6,13 +6,15 @@ CPU fp64 restatement ("port") of the reference's grid-solver hot path
 bench.py's cpu_baseline / --impl reference legs may import this module.  The product
 path (signed-heat-3d_b200/) never does and fails loudly without its CUDA library.
 
-PARITY STATUS: UNPINNED by the reference's own tests -- the reference has no tests or
-golden vectors for this path and cannot be compiled here (Eigen 3.3.8 is fetched at
-configure time).  The restatement follows the reference source
-line by line (citations below, relative to /root/reference) and Step 3 is solved two
-ways -- a direct sparse LU of the reference's KKT matrix (scipy SuperLU, the lineage of
-Eigen::SparseLU that geometry-central's solveSquare uses) and an fp64 projected CG --
-which must agree (tests/test_oracle.py).
+PARITY STATUS: pinned against the reference's OWN SOURCE, not against reference-published vectors (the reference
+has no tests or golden vectors for this path).  oracle/_ref/libshm_ref.so is src/signed_heat_grid_solver.cpp +
+src/signed_heat_3d.cpp of the reference compiled unmodified against oracle/ref_shim (a stand-in for the slices of
+geometry-central / Eigen / polyscope they use: the real Eigen is fetched at configure time and absent here, SURVEY.md
+section 0 D7); tests/test_reference_build.py shows this restatement equal to it to ~1e-13 on phi (mesh, polygon,
+point-cloud and fastIntegration paths), with the identical KKT matrix and right-hand side.  NOT pinned: Eigen's
+SparseLU itself (the shim hands the assembled system to scipy SuperLU, the same solver used here) and
+geometry-central's own containers (restated in the shim).  Step 3 is also solved by an fp64 projected CG, which must
+agree with the LU (tests/test_oracle.py).
 
 Nothing here reads /root/reference at run time except the helper readers when a test
 explicitly passes such a path (CPU-only fixture generation, tests/golden/make_golden.py).

@@ -1,0 +1,92 @@
+"""The oracle against the REFERENCE'S OWN SOURCE: oracle/_ref/libshm_ref.so is src/signed_heat_grid_solver.cpp +
+src/signed_heat_3d.cpp of the reference, compiled unmodified against oracle/ref_shim (a stand-in for the slices of
+geometry-central / Eigen / polyscope they use; the sparse LU behind solveSquare is a scipy SuperLU callback).
+Built on demand where /root/reference exists (this container); skipped where neither the tree nor the prebuilt library is."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import icosphere, load_golden
+from oracle import reference_build as rb
+from oracle import shm_oracle as o
+
+pytestmark = pytest.mark.skipif(not rb.build(), reason="no reference tree and no prebuilt oracle/_ref/libshm_ref.so")
+
+
+@pytest.mark.parametrize("name,hc", [("bunny_small", 0), ("polygon-bear", 0), ("bunny_small", 1)])
+def test_oracle_equals_reference_source_mesh(name, hc):
+    z, F = load_golden(name)
+    phi, info = rb.compute_distance_mesh(z["V"], F, hCoef=hc, return_info=True)
+    ora = o.compute_distance_mesh(z["V"], F, hCoef=hc)
+    assert np.abs(phi - ora).max() < 1e-10 * np.abs(ora).max()
+    # ... and therefore the committed golden vectors are the reference's own numbers
+    assert np.abs(phi - z[f"h{hc}_phi"]).max() < 1e-10 * np.abs(ora).max()
+    # the side effect main.cpp relies on: registerVolumeGrid("domain", {nx,ny,nz}, bboxMin, bboxMax) (:35)
+    s = o.mesh_sources(z["V"], F)
+    g = o.make_grid(s["centroid"], s["radius"], hc)
+    assert list(info["dims"]) == [g.nx, g.ny, g.nz]
+    assert np.abs(info["bbox"][:3] - g.bmin.astype(np.float32)).max() < 1e-6
+    assert np.abs(info["bbox"][3:] - (g.bmin + g.cell * (g.nx - 1)).astype(np.float32)).max() < 1e-5
+
+
+def test_kkt_system_assembled_by_the_reference_matches_the_oracle():
+    """[[L, A^T],[A, 0]] and [D^T Y; 0] exactly as src/signed_heat_grid_solver.cpp:80-106 hands them to solveSquare."""
+    z, F = load_golden("bunny_small")
+    _, info = rb.compute_distance_mesh(z["V"], F, hCoef=0, return_info=True)
+    assert len(info["solves"]) == 1
+    K = info["solves"][0]
+    s = o.mesh_sources(z["V"], F)
+    g = o.make_grid(s["centroid"], s["radius"], 0)
+    L = o.laplacian_matrix(g)
+    src, idx, w = o.constraints(g, s["pos"])
+    A = o.constraint_matrix(g, idx, w)
+    m = A.shape[0]
+    assert K["n"] == g.N + m == 4096 + 79
+    LHS = sp.bmat([[L, A.T], [A, sp.csr_matrix((m, m))]], format="csc")
+    diff = (K["A"] - LHS).tocoo()
+    assert np.abs(diff.data).max() if diff.nnz else 0.0 < 1e-12 * np.abs(LHS.data).max()
+    assert (K["A"] != 0).nnz == (LHS != 0).nnz
+    lam = o.lambda_from_h(s["h"])
+    b = o.div_rhs(g, o.step12(g, lam, s["pos"], s["nrm"], s["area"]))
+    assert np.abs(K["rhs"][:g.N] - b).max() < 1e-9 * np.abs(b).max()
+    assert np.all(K["rhs"][g.N:] == 0)
+
+
+def test_helper_functions_match():
+    """centroid / radius / meanEdgeLength / setFaceVectorAreas / yukawaPotential (src/signed_heat_3d.cpp)."""
+    for name in ("bunny_small", "polygon-bear"):
+        z, F = load_golden(name)
+        r = rb.mesh_scalars(z["V"], F)
+        s = o.mesh_sources(z["V"], F)
+        assert abs(r["h"] - s["h"]) < 1e-13 and abs(r["radius"] - s["radius"]) < 1e-13
+        assert np.abs(r["centroid"] - s["centroid"]).max() < 1e-13
+        assert np.abs(r["area"] - s["area"]).max() < 1e-13 and np.abs(r["nrm"] - s["nrm"]).max() < 1e-12
+    x, y = np.array([0.3, -1.2, 2.0]), np.array([1.0, 0.5, -0.25])
+    rr = np.linalg.norm(x - y)
+    assert abs(rb.yukawa(x, y, 3.7) - np.exp(-3.7 * rr) / rr) < 1e-16
+
+
+def test_fast_integration_matches_reference_bfs():
+    z, F = load_golden("bunny_small")
+    ref = rb.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
+    assert np.abs(ref - o.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)).max() < 1e-12
+    # the closed form the GPU path uses
+    s = o.mesh_sources(z["V"], F)
+    g = o.make_grid(s["centroid"], s["radius"], 0)
+    Y = o.step12(g, o.lambda_from_h(s["h"]), s["pos"], s["nrm"], s["area"])
+    pre = o.integrate_greedily_prefix(g, Y)
+    pre = pre - o.source_average(g, pre, s["pos"], s["area"])
+    assert np.abs(ref - pre).max() < 1e-12
+
+
+def test_point_cloud_overload_matches():
+    V, F = icosphere(2)
+    s = o.mesh_sources(V, F)
+    P, Nn = s["pos"], s["nrm"]
+    areas = s["area"] * 1.3
+    h = 0.2
+    ref = rb.compute_distance_points(P, Nn, areas, h, hCoef=0)
+    c = P.sum(axis=0) / len(P)
+    r = np.sqrt(((P - c) ** 2).sum(axis=1)).max()
+    ora = o.compute_distance(P, Nn, areas, h, c, r, hCoef=0, scrub_nonfinite=False)
+    assert np.abs(ref - ora).max() < 1e-10 * np.abs(ora).max()
