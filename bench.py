@@ -13,7 +13,9 @@ One "step" = one complete computeDistance over the workload (BASELINE.json metri
            shm3d_solve) with HOST buffers: H2D of the sources and D2H of the double field inside the timed region;
   roofline     : the PCG fused p-update + stencil-apply + dot kernel (HBM-bound; 16 B/node/launch algorithmic)
   roofline_sum : the Step 1-2 summation kernel (SFU-bound: 2 MUFU per evaluated pair at 16/clk/SM)
-  cpu_baseline : the fp64 oracle port of the reference's Step 1-2 loop on the host cores, bounded sample.
+  cpu_baseline : the reference's own computeDistance (oracle/_ref: its sources compiled against a shim) on the
+                 workload's sources at 16^3, single-threaded; cpu_baseline_port_all_threads: the oracle's C port of the
+                 Step 1-2 loop with OpenMP on a bounded sample of the real grid.
 N > 1: the grid is z-slab partitioned over the ranks (NCCL halo exchange + all-reduces).  Default workloads keep
 ~512^3 nodes per GPU (512^3, 640^3, 768^3, 1024^3 at 1, 2, 4, 8 GPUs -> "scaling": "weak"); --workload sphereN fixes
 the grid for strong-scaling runs.
@@ -173,6 +175,28 @@ def cpu_baseline_obj(p, M, pos, nrm, area, seconds=12.0):
                        f"64^3) -> an UPPER bound on the CPU path's end-to-end nodes/s")}
 
 
+def reference_build_sample(name):
+    """One run of the REFERENCE'S OWN computeDistance (oracle/_ref/libshm_ref.so: its two translation units compiled
+    unmodified against oracle/ref_shim; sparse LU through a scipy SuperLU callback) on the workload's sources at the
+    reference's smallest grid, hCoef 0 = 16^3.  Returns (nodes, seconds, description) or None when the library is absent."""
+    from oracle import reference_build as rb
+    if not rb.available():
+        return None
+    V, F, n, desc = make_workload(name)
+    faces = F.tolist() if hasattr(F, "tolist") else F
+    t0 = time.perf_counter()
+    phi = rb.compute_distance_mesh(V, faces, hCoef=0)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(phi).all()
+    text = (f"the reference's own SignedHeatGridSolver::computeDistance (src/signed_heat_grid_solver.cpp + "
+            f"src/signed_heat_3d.cpp compiled unmodified against oracle/ref_shim; Eigen's SparseLU replaced by a scipy "
+            f"SuperLU callback), single-threaded like the reference, on the workload's {len(faces)} source faces at its "
+            f"smallest grid hCoef 0 = 16^3: {phi.size} nodes, whole path incl. Step 3, in {dt:.2f} s.  Step 1-2 cost per "
+            f"node does not depend on the grid and the KKT LU grows super-linearly, so nodes/s at 16^3 is an UPPER bound "
+            f"for the {n}^3 workload")
+    return phi.size, dt, text
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,8 +204,25 @@ def run_reference(args):
     import shm3d
     p, pos, nrm, area, desc = prepare(args.workload)  # host-only calls (no device code)
     from oracle import shm_oracle as o
-    threads = o.max_threads()
     M = len(area)
+    first = reference_build_sample(args.workload)  # also serves as warm-up
+    if first is not None:
+        t_tot, n_tot, text = 0.0, 0, first[2]
+        for _ in range(args.steps):
+            n, dt, text = reference_build_sample(args.workload)
+            n_tot += n
+            t_tot += dt
+        v = n_tot / t_tot
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
+                "scaling": "weak" if args.workload == DEFAULT_BY_GPUS.get(args.gpus, "sphere512") else "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "grid": [p.nx, p.ny, p.nz], "sources": M},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "per step: " + text},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    threads = o.max_threads()
     rows = cpu_sample_plan(p, M, threads, seconds=6.0)
     for _ in range(args.warmup):
         cpu_step12_sample(p, pos, nrm, area, max(1, rows // 8), threads)
@@ -373,7 +414,12 @@ def run_ours(args):
                     "(1.00 / 0.98 / 0.84 / 1.00 x 512^3 per GPU), same 1e5-triangle sphere" if default_wl else
                     "fixed grid given by --workload, z-slabs split over the ranks")
     if rank == 0:
-        cpu = cpu_baseline_obj(p, M, pos, nrm, area) if world == 1 and not args.no_cpu else None
+        cpu = cpu_port = None
+        if world == 1 and not args.no_cpu:
+            cpu_port = cpu_baseline_obj(p, M, pos, nrm, area)  # the oracle port, OpenMP over all host threads
+            rs = reference_build_sample(args.workload)          # the reference's own source, single-threaded
+            cpu = ({"value": rs[0] / rs[1], "unit": UNIT, "cores": 1, "kind": "reference", "sample": rs[2]}
+                   if rs is not None else cpu_port)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -385,6 +431,7 @@ def run_ours(args):
                            "cull_tau": 10.0, "timing": "CUDA events on the solver's stream, max over ranks"},
                 "wall_ms_per_step": wall_ms / args.steps, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "roofline_sum": roofline_sum, "cpu_baseline": cpu,
+                "cpu_baseline_port_all_threads": cpu_port,
                 "stages_ms": {"h2d+cluster": stats.ms_h2d, "sum(step1-2)": stats.ms_sum, "rhs": stats.ms_rhs,
                               "constraints+factor(host, overlapped with sum)": stats.ms_constraints,
                               "pcg": stats.ms_pcg, "shift": stats.ms_shift, "total": stats.ms_total},
