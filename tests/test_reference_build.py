@@ -90,3 +90,20 @@ def test_point_cloud_overload_matches():
     r = np.sqrt(((P - c) ** 2).sum(axis=1)).max()
     ora = o.compute_distance(P, Nn, areas, h, c, r, hCoef=0, scrub_nonfinite=False)
     assert np.abs(ref - ora).max() < 1e-10 * np.abs(ora).max()
+
+
+def test_product_host_half_equals_reference_source():
+    """The product's own host code (shm3d_prepare_mesh in libshm3d_grid.so: rows a4-a6) against the reference's
+    centroid / radius / meanEdgeLength / setFaceVectorAreas, and its grid against what the reference registered."""
+    import shm3d
+    for name, hc in (("bunny_small", 1), ("polygon-bear", 0)):
+        z, F = load_golden(name)
+        r = rb.mesh_scalars(z["V"], F)
+        p, pos, nrm, area, h = shm3d.prepare_mesh(z["V"], F, hCoef=hc)
+        assert abs(h - r["h"]) < 1e-13
+        assert np.abs(area - r["area"]).max() < 1e-13 and np.abs(nrm - r["nrm"]).max() < 1e-12
+        s = r["radius"] * 2.0
+        assert np.abs(np.array(p.bbox_min) - (r["centroid"] - s)).max() < 1e-13
+        assert abs(p.cell - 2.0 * s / (p.nx - 1)) < 1e-15
+        _, info = rb.compute_distance_mesh(z["V"], F, hCoef=hc, fast=True, return_info=True)
+        assert list(info["dims"]) == [p.nx, p.ny, p.nz]
