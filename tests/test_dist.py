@@ -74,6 +74,6 @@ def test_slab_partitioned_solve_matches_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29618", os.path.join(ROOT, "tools", "check_dist.py"), "bunny_small:0", "bunny_small:1", "knot:2"]
+           "--master-port", "29618", os.path.join(ROOT, "tools", "check_dist.py"), "bunny_small:0", "bunny_small:1", "knot:2", "bunny_small:1:fast"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -19,6 +19,9 @@ dctx = shm3d.Context(local, rank, world, ids[0])
 sctx = shm3d.Context(local)
 bad = 0
 for c in (sys.argv[1:] or ["sphere:3", "bunny_small:1", "bunny_small:0"]):
+    fast = c.endswith(":fast")
+    if fast:
+        c = c[:-5]
     name, hc = c.split(":"); hc = int(hc)
     if name == "sphere":
         V, F = fibonacci_sphere(100000)
@@ -26,6 +29,8 @@ for c in (sys.argv[1:] or ["sphere:3", "bunny_small:1", "bunny_small:0"]):
         z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz")); fo = z["face_offsets"]; fv = z["face_vertices"]
         V = z["V"]; F = [fv[fo[i]:fo[i + 1]].tolist() for i in range(len(fo) - 1)]
     p, pos, nrm, area, h = shm3d.prepare_mesh(V, F, hCoef=hc)
+    if fast:
+        p.flags |= shm3d.FLAG_FAST  # fastIntegration: the z prefix sums chain over the ranks
     phi1, st1 = sctx.solve(p, pos, nrm, area)
     dist.barrier()
     t = time.time(); phid, std = dctx.solve(p, pos, nrm, area); dt = time.time() - t
@@ -37,7 +42,7 @@ for c in (sys.argv[1:] or ["sphere:3", "bunny_small:1", "bunny_small:0"]):
     e = torch.tensor([err, dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(e, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"{name} {p.nx}^3 world={world}: max slab rel-L2 vs single GPU {float(e[0]):.3e}; its dist {std.cg_iters} / single {st1.cg_iters}; "
+        print(f"{name}{' fast' if fast else ''} {p.nx}^3 world={world}: max slab rel-L2 vs single GPU {float(e[0]):.3e}; its dist {std.cg_iters} / single {st1.cg_iters}; "
               f"wall dist {float(e[1])*1e3:.0f} ms (sum {std.ms_sum:.0f} constr {std.ms_constraints:.0f} pcg {std.ms_pcg:.0f}) / single {st1.ms_total:.0f} ms "
               f"(sum {st1.ms_sum:.0f} pcg {st1.ms_pcg:.0f})", flush=True)
     if float(e[0]) > 1e-4:
