@@ -8,12 +8,12 @@
 // Layout: x-fastest float arrays; every vector that is read through a stencil is allocated with one ghost
 // plane below and above the local z-slab, and kernels receive the pointer to the first interior plane.
 //
-// Kernel shape (B200): persistent grid (<= 8 CTAs of 256 threads per SM), grid-stride over "quads" of four
-// x-consecutive nodes moved as float4 (16 B per lane, coalesced 512 B per warp); y/z neighbours are float4 loads
-// of the adjacent rows/planes (L1/L2 hits: a 512^2 plane is 1 MB, the 126 MB L2 holds the working planes), the two
-// x-end neighbours are scalar loads of the adjacent quads.  Reductions are fp64 and deterministic: one partial
-// per CTA, the last CTA to finish (ticket) folds them in a fixed order -- with <= 1184 CTAs the single-address
-// ticket atomic is no longer the bottleneck it was with one CTA per 256 nodes.
+// Kernel shape (B200): persistent grid (<= 8 CTAs of 256 threads per SM).  Grids with nx % 4 == 0 -- every grid the
+// reference can produce -- use the row-oriented kernels of grid_rows.cuh (a warp owns a grid row: boundary predicates and
+// reciprocal diagonals once per row, float4 quads per lane, x-neighbours by shuffle).  The element-indexed templates
+// below (V = 1) remain as the general path for other sizes and for the pointwise kernels (V = 4: x/r update, dots).
+// Reductions are fp64 and deterministic: one partial per CTA, the last CTA to finish (ticket) folds them in a fixed
+// order.
 #include <algorithm>
 
 #include "kernels.cuh"
@@ -33,16 +33,14 @@ struct RedScratch {
     unsigned int* counter;
 };
 
-static double* g_partials = nullptr;
-static unsigned int* g_counter = nullptr;
+// The per-CTA partials and the ticket counter belong to the CONTEXT whose call is running on this host thread
+// (set_reduction_scratch at every API entry): two contexts -- other devices, or other streams of one device -- never
+// share them.
+thread_local RedScratch t_scratch{nullptr, nullptr};
 
 RedScratch red_scratch() {
-    if (!g_partials) {
-        SHM3D_CUDA_CHECK(cudaMalloc((void**)&g_partials, (size_t)kMaxBlocks * 4 * sizeof(double)));
-        SHM3D_CUDA_CHECK(cudaMalloc((void**)&g_counter, sizeof(unsigned int)));
-        SHM3D_CUDA_CHECK(cudaMemset(g_counter, 0, sizeof(unsigned int)));
-    }
-    return RedScratch{g_partials, g_counter};
+    if (!t_scratch.partials) throw Error(SHM3D_ERR_INVALID_ARG, "internal: reduction scratch not bound to a context");
+    return t_scratch;
 }
 
 template <int K>
@@ -652,6 +650,12 @@ inline unsigned int nblk(size_t groups) {
 inline bool vec4(const LevelDims& L) { return (L.nx % 4) == 0; }
 
 }  // namespace
+
+void set_reduction_scratch(double* partials, unsigned int* counter) {
+    t_scratch.partials = partials;
+    t_scratch.counter = counter;
+}
+size_t reduction_scratch_doubles() { return (size_t)kMaxBlocks * 4; }
 
 #define POST() \
     SHM3D_LAUNCHED(); \

@@ -63,6 +63,10 @@ void launch_fast_integrate_base(const LevelDims& L, float cell, const float* Y_p
 void launch_fast_integrate_z(const LevelDims& L, float cell, const float* Y_padded, size_t comp_stride, float* phi_padded,
                              cudaStream_t s);
 
+// deterministic-reduction scratch of the calling context (bound per host thread at every API entry)
+void set_reduction_scratch(double* partials, unsigned int* counter);
+size_t reduction_scratch_doubles();
+
 // generic helpers
 void launch_fill(float* p, size_t n, float v, cudaStream_t s);
 void launch_copy(float* dst, const float* src, size_t n, cudaStream_t s);

@@ -70,6 +70,8 @@ struct shm3d_ctx {
     DevBuf<float> d_pinv;
     DevBuf<double> d_phi64, shift_part;
     DevBuf<long long> d_coinc;
+    DevBuf<double> red_partials;       // deterministic reductions: one partial per CTA ...
+    DevBuf<unsigned int> red_counter;  // ... and the ticket counter (grid_ops.cu), owned by this context
     DevBuf<float4> d_qpts;
     DevBuf<float> d_qY;
     std::vector<MGLevel> levels;
@@ -892,7 +894,8 @@ struct Solver {
 #define SHM3D_API_BEGIN(ctx)                                   \
     if (!(ctx)) return SHM3D_ERR_INVALID_ARG;                  \
     try {                                                      \
-        SHM3D_CUDA_CHECK(cudaSetDevice((ctx)->device));
+        SHM3D_CUDA_CHECK(cudaSetDevice((ctx)->device));        \
+        set_reduction_scratch((ctx)->red_partials.p, (ctx)->red_counter.p);
 #define SHM3D_API_END(ctx)                                     \
     }                                                          \
     catch (const shm3d::Error& e) {                            \
@@ -933,6 +936,9 @@ static int create_common(shm3d_ctx** out, int device, int rank, int world, const
         SHM3D_CUDA_CHECK(cudaSetDevice(device));
         SHM3D_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         set_host_ranks_hint(world);
+        c->red_partials.alloc(reduction_scratch_doubles());
+        c->red_counter.alloc(1);
+        SHM3D_CUDA_CHECK(cudaMemset(c->red_counter.p, 0, sizeof(unsigned int)));
         if (world > 1) c->dist.reset(new Dist(rank, world, nccl_id, c->stream));
     } catch (const shm3d::Error& ex) {
         g_create_error = ex.what();
