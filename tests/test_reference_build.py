@@ -107,3 +107,11 @@ def test_product_host_half_equals_reference_source():
         assert abs(p.cell - 2.0 * s / (p.nx - 1)) < 1e-15
         _, info = rb.compute_distance_mesh(z["V"], F, hCoef=hc, fast=True, return_info=True)
         assert list(info["dims"]) == [p.nx, p.ny, p.nz]
+
+
+def test_knot_golden_is_the_reference_sources_output():
+    """data/knot.obj at hCoef 1 (30 504 faces x 32^3 nodes, ~1 min single-threaded: the reference recomputes every
+    barycentre per pair): the committed golden field the GPU tests compare against is the reference's own result."""
+    z, F = load_golden("knot")
+    phi = rb.compute_distance_mesh(z["V"], F, hCoef=1)
+    assert np.abs(phi - z["h1_phi"]).max() < 1e-9 * np.abs(phi).max()
