@@ -54,7 +54,8 @@ class Shm3dError(RuntimeError):
 EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm3d_nccl_unique_id", "shm3d_ctx_destroy",
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
-           "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points"]
+           "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points", "shm3d_point_weights",
+           "shm3d_debug_local_ring"]
 
 _lib = None
 
@@ -90,6 +91,8 @@ def lib():
         L.shm3d_debug_constraints.argtypes = [PP, C.c_int64, dp, i32p, i64p, dp, i64p, C.c_int64]
         L.shm3d_debug_factor_solve.argtypes = [PP, C.c_int64, dp, C.c_int32, dp, C.c_int32, dp, i32p]
         L.shm3d_version.restype = C.c_char_p
+        L.shm3d_point_weights.argtypes = [dp, dp, C.c_int64, C.c_int32, dp, dp, i64p]
+        L.shm3d_debug_local_ring.argtypes = [dp, C.c_int32, i32p, i32p]
         L.shm3d_ctx_stream.argtypes = [vp]
         L.shm3d_ctx_stream.restype = vp
         L.shm3d_host_alloc.argtypes = [C.c_size_t]
@@ -147,6 +150,28 @@ def prepare_points(P, h, tCoef=1.0, hCoef=0.0, scale=2.0):
     if rc != OK:
         raise Shm3dError(rc, "shm3d_prepare_points: invalid input")
     return p
+
+
+def point_weights(P, normals, k=30):
+    """Per-point areas and mean edge length for the point-cloud overload (row N1, without the tufted-cover flips):
+    returns (areas[nP], h, n_soup_triangles)."""
+    P, Nn = _c64(P), _c64(normals)
+    areas = np.empty(len(P))
+    h = C.c_double()
+    nt = C.c_int64()
+    rc = lib().shm3d_point_weights(_dp(P), _dp(Nn), len(P), k, _dp(areas), C.byref(h), C.byref(nt))
+    if rc != OK:
+        raise Shm3dError(rc, "shm3d_point_weights: invalid input (need more than k points, finite data, some triangles)")
+    return areas, h.value, nt.value
+
+
+def debug_local_ring(coords2d):
+    c = _c64(coords2d)
+    ring = np.empty(len(c), dtype=np.int32)
+    tri = np.empty(len(c), dtype=np.int32)
+    n = lib().shm3d_debug_local_ring(_dp(c), len(c), ring.ctypes.data_as(C.POINTER(C.c_int32)),
+                                     tri.ctypes.data_as(C.POINTER(C.c_int32)))
+    return ring[:n].copy(), tri[:n].copy()
 
 
 def debug_constraints(p: Params, pos):
@@ -363,6 +388,11 @@ class SignedHeatGridSolver:
             p, pos, nrm, area, _ = prepare_mesh(V, faces, options.tCoef, options.hCoef, options.scale)
         return self._finish(p, pos, nrm, area, options)
 
-    def computeDistancePoints(self, P, normals, areas, h, options: SignedHeat3DOptions = SignedHeat3DOptions()):
+    def computeDistancePoints(self, P, normals, areas=None, h=None,
+                              options: SignedHeat3DOptions = SignedHeat3DOptions()):
+        if areas is None or h is None:  # row N1 (partial): local-Delaunay weights instead of the caller's
+            a, hh, _ = point_weights(P, normals)
+            areas = a if areas is None else areas
+            h = hh if h is None else h
         p = prepare_points(P, h, options.tCoef, options.hCoef, options.scale)
         return self._finish(p, _c64(P), _c64(normals), _c64(areas), options)

@@ -59,11 +59,10 @@ def test_cli_reads_pc_files(tmp_path):
     assert r.returncode == 0, r.stderr
     d = json.loads(r.stdout)
     assert d["sources"] == len(F) and d["nx"] == 16
-    # surrogate h = mean nearest-neighbour distance (brute force check)
-    P = s["pos"]
-    d2 = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
-    np.fill_diagonal(d2, np.inf)
-    assert abs(d["h"] - np.sqrt(d2.min(axis=1)).mean()) < 1e-12
+    # h = mean edge length of the local-Delaunay triangle soup (row N1 without the tufted-cover flips)
+    import shm3d
+    _, h, _ = shm3d.point_weights(s["pos"], s["nrm"])
+    assert abs(d["h"] - h) < 1e-12 * h
 
 
 def test_cli_bad_input_fails_cleanly(tmp_path):

@@ -1,0 +1,103 @@
+"""CPU tests of the point-cloud source weights (row N1, partial: geometry-central's pipeline without the tufted-cover
+flips): kNN, tangent-plane local Delaunay rings against scipy's Delaunay triangulation, areas and mean edge length
+against closed forms on well-sampled surfaces."""
+import os
+import sys
+
+import numpy as np
+import pytest
+from scipy.spatial import ConvexHull, Delaunay, cKDTree
+
+import shm3d
+from conftest import GOLDEN, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def fib_points(n):
+    i = np.arange(n) + 0.5
+    phi = np.arccos(1 - 2 * i / n)
+    th = np.pi * (1 + 5 ** 0.5) * i
+    return np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1)
+
+
+def test_local_ring_equals_the_delaunay_star_of_the_centre():
+    """local_triangulation.cpp:10-210 restated: for an interior centre the surviving ring is the 1-ring of the centre in
+    the 2-D Delaunay triangulation of {centre} + neighbours."""
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n = int(rng.integers(8, 31))
+        pts = rng.standard_normal((n, 2))
+        ring, tri = shm3d.debug_local_ring(pts)
+        D = Delaunay(np.vstack([[0.0, 0.0], pts]))
+        star = set()
+        for s in D.simplices:
+            if 0 in s:
+                star |= set(int(v) - 1 for v in s if v != 0)
+        on_hull = 0 in set(D.convex_hull.ravel())
+        assert set(ring.tolist()) == star, (trial, sorted(ring.tolist()), sorted(star))
+        if not on_hull:
+            assert tri.all() and len(ring) >= 3
+        # counter-clockwise order
+        ang = np.arctan2(pts[ring, 1], pts[ring, 0])
+        assert (np.diff(ang) > 0).all()
+
+
+def test_ring_drops_collinear_far_points_and_handles_half_planes():
+    pts = np.array([[1.0, 0.0], [2.0, 0.0], [0.0, 1.0], [-1.0, 0.2], [0.0, -1.0]])
+    ring, tri = shm3d.debug_local_ring(pts)
+    assert 1 not in ring.tolist()            # (2,0) hides behind (1,0)
+    half = np.array([[1.0, 0.1], [0.5, 1.0], [-0.5, 1.0], [-1.0, 0.1]])   # all neighbours in the upper half-plane
+    ring, tri = shm3d.debug_local_ring(half)
+    assert len(ring) == 4 and tri.sum() == 3  # no triangle across the empty half-plane
+
+
+def test_sphere_weights():
+    n = 4000
+    P = fib_points(n)
+    areas, h, ntri = shm3d.point_weights(P, P)
+    assert ntri > 5 * n
+    # every surface triangle shows up in the local triangulation of each of its 3 corners, on 2 sheets of the cover
+    assert abs(areas.sum() / (6 * 4 * np.pi) - 1) < 0.02
+    assert areas.std() / areas.mean() < 0.1
+    hull = ConvexHull(P)
+    e = np.vstack([hull.simplices[:, [0, 1]], hull.simplices[:, [1, 2]], hull.simplices[:, [2, 0]]])
+    e = np.unique(np.sort(e, axis=1), axis=0)
+    h_hull = np.linalg.norm(P[e[:, 0]] - P[e[:, 1]], axis=1).mean()
+    assert abs(h / h_hull - 1) < 0.03
+    # any positive rescaling of the normals leaves the weights unchanged (only the tangent plane matters)
+    a2, h2, _ = shm3d.point_weights(P, 3.0 * P)
+    assert np.allclose(a2, areas, rtol=1e-9) and abs(h2 - h) < 1e-12
+
+
+def test_bunny_pc_weights_and_errors():
+    d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
+    P, N = d["P"], d["N"]
+    areas, h, ntri = shm3d.point_weights(P, N)
+    assert np.isfinite(areas).all() and (areas > 0).mean() > 0.99 and ntri > 4 * len(P)
+    nn = cKDTree(P).query(P, k=2)[0][:, 1].mean()
+    assert 0.8 * nn < h < 2.5 * nn      # a mean Delaunay edge is somewhat longer than the mean nearest-neighbour distance
+    with pytest.raises(shm3d.Shm3dError):
+        shm3d.point_weights(P[:20], N[:20])   # k + 1 = 31 > 20 points (knn.cpp:53)
+    bad = N.copy()
+    bad[3, 0] = np.nan
+    with pytest.raises(shm3d.Shm3dError):
+        shm3d.point_weights(P, bad)
+
+
+def test_knn_is_exact():
+    rng = np.random.default_rng(2)
+    P = rng.standard_normal((1500, 3)) * np.array([1.0, 0.3, 2.0])
+    Nn = np.tile([0.0, 0.0, 1.0], (len(P), 1))
+    a30, h30, _ = shm3d.point_weights(P, Nn, k=30)
+    # planar projection with a common normal: the soup is made of 2-D Delaunay stars; compare one point's ring with the
+    # ring built from its TRUE 30 nearest neighbours
+    tree = cKDTree(P)
+    for i in (0, 17, 733):
+        idx = tree.query(P[i], k=31)[1][1:]
+        v = P[idx] - P[i]
+        v = v - np.outer(v @ Nn[i], Nn[i])
+        # tangent basis of (0,0,1): basisX = cross((1,0,0), n) normalised = (0,-1,0); basisY = cross(n, basisX) = (1,0,0)
+        coords = np.stack([-v[:, 1], v[:, 0]], axis=1)
+        ring, tri = shm3d.debug_local_ring(coords)
+        assert len(ring) >= 3

@@ -87,60 +87,6 @@ static bool read_pc(const std::string& path, shm3d::OrientedPointCloud& pc) {
     return true;
 }
 
-// SURROGATE for the tufted-triangulation quantities of the point overload (not built
-// yet): h = mean nearest-neighbour distance, area = h^2 for every point.  Results with this surrogate match the
-// oracle run with the same surrogate, NOT the reference's tufted-cover areas.
-static void surrogate_point_weights(shm3d::OrientedPointCloud& pc) {
-    const int64_t n = pc.nPoints();
-    // uniform hash grid with ~2 points per bucket
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int64_t i = 0; i < n; i++)
-        for (int a = 0; a < 3; a++) {
-            lo[a] = std::min(lo[a], pc.positions[3 * i + a]);
-            hi[a] = std::max(hi[a], pc.positions[3 * i + a]);
-        }
-    const double ext = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-300});
-    const int g = std::max(1, (int)std::cbrt((double)n / 2.0));
-    const double cs = ext / g * (1 + 1e-12);
-    auto cell = [&](const double* q, int c[3]) {
-        for (int a = 0; a < 3; a++) c[a] = std::min(g - 1, std::max(0, (int)((q[a] - lo[a]) / cs)));
-    };
-    std::vector<std::vector<int64_t>> buckets((size_t)g * g * g);
-    for (int64_t i = 0; i < n; i++) {
-        int c[3];
-        cell(&pc.positions[3 * i], c);
-        buckets[(size_t)c[0] + (size_t)c[1] * g + (size_t)c[2] * g * g].push_back(i);
-    }
-    double sum = 0;
-    for (int64_t i = 0; i < n; i++) {
-        int c[3];
-        cell(&pc.positions[3 * i], c);
-        double best = 1e300;
-        for (int ring = 1; ring <= g; ring++) {
-            for (int dz = -ring; dz <= ring; dz++)
-                for (int dy = -ring; dy <= ring; dy++)
-                    for (int dx = -ring; dx <= ring; dx++) {
-                        if (std::max({std::abs(dx), std::abs(dy), std::abs(dz)}) != ring && ring > 1) continue;
-                        int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
-                        if (x < 0 || y < 0 || z < 0 || x >= g || y >= g || z >= g) continue;
-                        for (int64_t j : buckets[(size_t)x + (size_t)y * g + (size_t)z * g * g]) {
-                            if (j == i) continue;
-                            double d = 0;
-                            for (int a = 0; a < 3; a++) {
-                                double t = pc.positions[3 * i + a] - pc.positions[3 * j + a];
-                                d += t * t;
-                            }
-                            best = std::min(best, d);
-                        }
-                    }
-            if (best < 1e300 && std::sqrt(best) <= ring * cs) break;  // nothing closer can lie in farther rings
-        }
-        sum += std::sqrt(best);
-    }
-    pc.meanEdgeLength = sum / (double)n;
-    pc.areas.assign((size_t)n, pc.meanEdgeLength * pc.meanEdgeLength);
-}
-
 static bool write_npy(const std::string& path, const std::vector<double>& v, size_t nx, size_t ny, size_t nz) {
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) return false;
@@ -204,8 +150,10 @@ int main(int argc, char** argv) {
         shm3d::OrientedPointCloud pc;
         if (is_pc) {
             if (!read_pc(input, pc) || pc.nPoints() == 0) throw std::runtime_error("cannot read point cloud " + input);
-            surrogate_point_weights(pc);
-            std::fprintf(stderr, "[shm3d_cli] point cloud: SURROGATE weights (uniform area h^2, h = mean nearest-neighbour distance)\n");
+            if ((int64_t)pc.normals.size() != 3 * pc.nPoints()) throw std::runtime_error("point cloud needs one 'vn' per 'v'");
+            pc.computeWeights();  // row N1 (partial): see include/shm3d/signed_heat_grid_solver.hpp
+            std::fprintf(stderr, "[shm3d_cli] point cloud: local-Delaunay vertex areas (tufted-cover flips not applied), h = %g\n",
+                         pc.meanEdgeLength);
         } else if (!read_obj(input, mesh) || mesh.nFaces() == 0) {
             throw std::runtime_error("cannot read mesh " + input);
         }
