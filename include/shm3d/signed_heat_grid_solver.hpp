@@ -58,11 +58,12 @@ struct OrientedPointCloud {
     std::vector<double> areas;      // [nP]
     double meanEdgeLength = 0.0;
     int64_t nPoints() const { return (int64_t)positions.size() / 3; }
-    // Fill areas / meanEdgeLength from positions + normals with shm3d_point_weights: geometry-central's pipeline (kNN 30,
-    // local Delaunay stars, triangle soup, mollification, two cover sheets) WITHOUT the intrinsic flips on the cover.
+    // Fill areas / meanEdgeLength from positions + normals with shm3d_point_weights: geometry-central's pipeline restated
+    // (kNN 30, local Delaunay stars, triangle soup, mollification, tufted cover, intrinsic Delaunay flips).
     void computeWeights() {
         areas.assign((size_t)nPoints(), 0.0);
-        int rc = shm3d_point_weights(positions.data(), normals.data(), nPoints(), 30, areas.data(), &meanEdgeLength, nullptr);
+        int rc = shm3d_point_weights(positions.data(), normals.data(), nPoints(), 30, areas.data(), &meanEdgeLength, nullptr, nullptr,
+                                     nullptr, nullptr);
         if (rc != SHM3D_OK) throw std::invalid_argument("OrientedPointCloud::computeWeights: need > 30 finite points with usable normals");
     }
 };

@@ -158,15 +158,18 @@ int shm3d_prepare_mesh(const double* V, int64_t nV, const int64_t* face_vertices
 int shm3d_prepare_points(const double* P, int64_t nP, double h, double tCoef, double hCoef, double scale,
                          shm3d_params* out);
 
-/* Source weights for the point-cloud overload (PARTIAL): what the reference reads from
+/* Source weights for the point-cloud overload: what the reference reads from
  * geometry-central's tufted triangulation -- per-point vertex dual areas and the mean edge length h
- * (src/signed_heat_grid_solver.cpp:149-151,165) -- computed from positions + normals by kNN(k_neighbors <= 0: 30),
- * tangent-plane local Delaunay 1-rings (deps/geometry-central/src/pointcloud/local_triangulation.cpp:10-210), the triangle
- * soup of all local triangles, intrinsic mollification and the two sheets of the tufted cover.  The intrinsic edge
- * flips geometry-central then applies to the cover are NOT performed, so areas / h approximate its values (identical
- * total area).  Host only; no device work. */
+ * (src/signed_heat_grid_solver.cpp:149-151,165) -- computed from positions + normals by restating that pipeline:
+ * kNN(k_neighbors <= 0: 30), tangent-plane local Delaunay 1-rings (deps/geometry-central/src/pointcloud/
+ * local_triangulation.cpp:10-210), the triangle soup of all local triangles, intrinsic mollification, the tufted cover
+ * (src/surface/tufted_laplacian.cpp:39-121) and intrinsic Delaunay flips (src/surface/simple_idt.cpp).  geometry-central
+ * itself cannot be built here, so the restatement is checked by invariants only (tests/test_point_weights.py).
+ * Optional diagnostics: number of flips, smallest edge cotan weight after the flips (>= -1e-6 = intrinsically
+ * Delaunay), total cover area before the flips (= sum of areas_out).  Host only; no device work. */
 int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_neighbors, double* areas_out,
-                        double* h_out, int64_t* n_triangles_out);
+                        double* h_out, int64_t* n_triangles_out, int64_t* n_flips_out, double* min_cotan_out,
+                        double* area_before_out);
 /* probe for the tests: the local Delaunay 1-ring of the origin among n tangent-plane points (returns the ring size) */
 int shm3d_debug_local_ring(const double* coords2d, int32_t n, int32_t* ring_out, int32_t* tri_after_out);
 

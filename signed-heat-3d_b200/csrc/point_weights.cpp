@@ -6,11 +6,13 @@
 //   kNN(30) -> tangent-plane coordinates -> local Delaunay 1-ring of every point (local_triangulation.cpp:10-210)
 //   -> the union of all local triangles as a triangle soup -> intrinsic mollification (1e-5) -> tufted cover
 //   -> intrinsic edge flips to Delaunay -> vertexDualAreas = sum of incident face areas / 3, mean intrinsic edge length.
-// Restated here: everything up to and including the mollification, and the two sheets of the cover (a factor 2).
-// NOT restated: the intrinsic flips on the cover -- they preserve the total area and move little of it between
-// neighbouring points when the local triangulations agree with each other (well-sampled surfaces); the result is
-// therefore an approximation of geometry-central's weights, stated as such in DESIGN.md / INTEGRATION.md.
-// Any positive rescaling of all areas cancels in Steps 1-2 (normalisation) and in the shift (a weighted mean).
+// All of it is restated here from the cited sources: the soup mesh's edge / sibling order (surface_mesh.cpp:60-205), the
+// mollification (intrinsic_mollification.cpp:7-38), the gluing rule of the cover (tufted_laplacian.cpp:39-121, the
+// position-free "natural ordering" branch the point-cloud path takes), the Euclidean intrinsic flips (simple_idt.cpp:11-188,
+// SurfaceMesh::flip :848-928).  It CANNOT be checked against geometry-central here (that library needs Eigen, absent
+// from this image): the tests check what can be checked without it -- every local star against scipy's Delaunay
+// triangulation, total area preserved by the flips, the final cover intrinsically Delaunay, closed forms on sampled
+// spheres.  Any positive rescaling of all areas cancels in Steps 1-2 (normalisation) and in the shift (a weighted mean).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -176,6 +178,184 @@ void knn_all(const double* P, int64_t n, int k, std::vector<int64_t>& nbr) {
     }
 }
 
+// ---------------------------------------------------------------- tufted cover + intrinsic Delaunay flips
+struct CoverStats {
+    int64_t flips = 0;
+    double min_cotan = 0;    // smallest edge cotan weight after the flips (>= -1e-6 when intrinsically Delaunay)
+    double area_before = 0;  // total cover area before the flips (the flips must preserve it)
+};
+
+inline double tri_area(double a, double b, double c) {  // utilities/elementary_geometry.ipp:7-12
+    const double s = (a + b + c) / 2.0;
+    return std::sqrt(std::max(0., s * (s - a) * (s - b) * (s - c)));
+}
+// third vertex of a triangle laid out in the plane (elementary_geometry.ipp:18-33)
+inline V2 layout_vertex(const V2& pA, const V2& pB, double lBC, double lCA) {
+    const double lAB = std::sqrt((pB.x - pA.x) * (pB.x - pA.x) + (pB.y - pA.y) * (pB.y - pA.y));
+    const double h = 2. * tri_area(lAB, lBC, lCA) / lAB;
+    const double w = (lAB * lAB - lBC * lBC + lCA * lCA) / (2. * lAB);
+    const V2 n{(pB.x - pA.x) / lAB, (pB.y - pA.y) / lAB};
+    return V2{pA.x + w * n.x - h * n.y, pA.y + w * n.y + h * n.x};
+}
+
+void tufted_cover_weights(const double* P, int64_t nP, const std::vector<int64_t>& tris, double* areas_out, double* h_out,
+                          CoverStats& st) {
+    const int64_t T = (int64_t)tris.size() / 3;
+    // ---- soup mesh: unique edges in creation order, their front halfedges in creation order (surface_mesh.cpp:145-185)
+    struct SoupEdge {
+        int64_t v0;                 // tail of the first halfedge created on the edge (defines orientation = true)
+        double len;
+        std::vector<int64_t> hes;   // front halfedges 3f + s in creation order h_1 .. h_n
+    };
+    std::vector<SoupEdge> edges;
+    std::vector<int64_t> he_edge((size_t)3 * T);
+    {
+        std::vector<std::pair<std::pair<int64_t, int64_t>, int64_t>> keyed((size_t)3 * T);
+        for (int64_t h = 0; h < 3 * T; h++) {
+            const int64_t f = h / 3, sl = h % 3, a = tris[3 * f + sl], b = tris[3 * f + (sl + 1) % 3];
+            keyed[h] = {{std::min(a, b), std::max(a, b)}, h};
+        }
+        std::vector<std::pair<std::pair<int64_t, int64_t>, int64_t>> sorted = keyed;
+        std::sort(sorted.begin(), sorted.end());  // group by key; within a key ascending halfedge index = creation order
+        std::vector<int64_t> first_of_group;      // creation order of edges = order of their first halfedge
+        for (size_t i = 0; i < sorted.size();) {
+            size_t j = i;
+            while (j < sorted.size() && sorted[j].first == sorted[i].first) j++;
+            first_of_group.push_back((int64_t)i);
+            i = j;
+        }
+        std::sort(first_of_group.begin(), first_of_group.end(),
+                  [&](int64_t x, int64_t y) { return sorted[x].second < sorted[y].second; });
+        for (int64_t gi : first_of_group) {
+            SoupEdge e;
+            const int64_t h1 = sorted[gi].second;
+            e.v0 = tris[3 * (h1 / 3) + h1 % 3];
+            const double* a = P + 3 * sorted[gi].first.first;
+            const double* b = P + 3 * sorted[gi].first.second;
+            e.len = std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+            for (size_t i = (size_t)gi; i < sorted.size() && sorted[i].first == sorted[gi].first; i++) {
+                e.hes.push_back(sorted[i].second);
+                he_edge[sorted[i].second] = (int64_t)edges.size();
+            }
+            edges.push_back(std::move(e));
+        }
+    }
+    // ---- intrinsic mollification (intrinsic_mollification.cpp:7-38)
+    {
+        double sum = 0;
+        for (const SoupEdge& e : edges) sum += e.len;
+        const double delta = (sum / (double)edges.size()) * 1e-5;
+        double eps = 0;
+        for (int64_t f = 0; f < T; f++)
+            for (int sl = 0; sl < 3; sl++) {
+                const double lA = edges[he_edge[3 * f + sl]].len, lB = edges[he_edge[3 * f + (sl + 1) % 3]].len,
+                             lC = edges[he_edge[3 * f + (sl + 2) % 3]].len;
+                eps = std::fmax(eps, lC - lA - lB + delta);
+            }
+        for (SoupEdge& e : edges) e.len += eps;
+    }
+    // ---- the cover: front face f -> halfedges 6f + s (v_s -> v_{s+1}), back face (orientation inverted) -> halfedges
+    // 6f + 3 + s running v_{s+1} -> v_s; otherSheet pairs 6f + s with 6f + 3 + s
+    const int64_t H = 6 * T;
+    std::vector<int64_t> next(H), twin(H, -1), vert(H), hedge(H, -1);
+    std::vector<double> elen;  // per cover edge
+    for (int64_t f = 0; f < T; f++)
+        for (int sl = 0; sl < 3; sl++) {
+            next[6 * f + sl] = 6 * f + (sl + 1) % 3;
+            vert[6 * f + sl] = tris[3 * f + sl];
+            next[6 * f + 3 + sl] = 6 * f + 3 + (sl + 2) % 3;
+            vert[6 * f + 3 + sl] = tris[3 * f + (sl + 1) % 3];
+        }
+    auto front_of = [&](int64_t soup_he) { return 6 * (soup_he / 3) + soup_he % 3; };
+    auto other = [&](int64_t h) { return (h % 6) < 3 ? h + 3 : h - 3; };
+    for (const SoupEdge& e : edges) {
+        // e.adjacentHalfedges(): h_1, then the sibling chain h_n, h_{n-1}, ..., h_2 (surface_mesh.cpp:187-203)
+        const size_t n = e.hes.size();
+        std::vector<int64_t> F(n);
+        F[0] = front_of(e.hes[0]);
+        for (size_t i = 1; i < n; i++) F[i] = front_of(e.hes[n - i]);
+        // orientation(): front halfedge = (tail == tail of h_1); the inverted back copy has the opposite flag
+        auto orient = [&](int64_t h) { return vert[h] == e.v0; };
+        // tufted_laplacian.cpp:103-113
+        int64_t curr = F[0];
+        if (orient(curr)) curr = other(curr);
+        for (size_t i = 0; i < n; i++) {
+            int64_t nxt = F[(i + 1) % n];
+            if (orient(curr) == orient(nxt)) nxt = other(nxt);
+            twin[curr] = nxt;
+            twin[nxt] = curr;
+            hedge[curr] = hedge[nxt] = (int64_t)elen.size();
+            elen.push_back(e.len);
+            curr = other(nxt);
+        }
+    }
+    const int64_t E = (int64_t)elen.size();
+    std::vector<int64_t> edge_he(E, -1);
+    for (int64_t h = 0; h < H; h++)
+        if (hedge[h] >= 0 && edge_he[hedge[h]] < 0) edge_he[hedge[h]] = h;
+    auto face_area = [&](int64_t h) { return tri_area(elen[hedge[h]], elen[hedge[next[h]]], elen[hedge[next[next[h]]]]); };
+    for (int64_t f = 0; f < 2 * T; f++) st.area_before += face_area(3 * f);
+    // ---- intrinsic flips to Delaunay (simple_idt.cpp:11-188, Euclidean, eps 1e-6)
+    auto he_cotan = [&](int64_t h) {
+        const double lij = elen[hedge[h]], ljk = elen[hedge[next[h]]], lki = elen[hedge[next[next[h]]]];
+        return (-lij * lij + ljk * ljk + lki * lki) / (4. * tri_area(lij, ljk, lki)) / 2;
+    };
+    auto edge_cotan = [&](int64_t e) { return he_cotan(edge_he[e]) + he_cotan(twin[edge_he[e]]); };
+    std::vector<int64_t> queue(E);
+    std::iota(queue.begin(), queue.end(), 0);
+    std::vector<char> in_queue(E, 1);
+    size_t head = 0;
+    while (head < queue.size()) {
+        const int64_t e = queue[head++];
+        in_queue[e] = 0;
+        if (!(edge_cotan(e) < -1e-6)) continue;
+        const int64_t ha1 = edge_he[e], ha2 = next[ha1], ha3 = next[ha2];
+        const int64_t hb1 = twin[ha1], hb2 = next[hb1], hb3 = next[hb2];
+        if (hb1 < 0 || ha2 == hb1 || hb2 == ha1) continue;  // SurfaceMesh::flip: incident on a degree-1 vertex
+        // new length by laying out the two triangles (simple_idt.cpp:15-52)
+        const double l01 = elen[hedge[ha2]], l12 = elen[hedge[ha3]], l23 = elen[hedge[hb2]], l30 = elen[hedge[hb3]],
+                     l02 = elen[e];
+        const V2 p3{0., 0.}, p0{l30, 0.};
+        const V2 p2 = layout_vertex(p3, p0, l02, l23);
+        const V2 p1 = layout_vertex(p2, p0, l01, l12);
+        const double nl = std::sqrt((p1.x - p3.x) * (p1.x - p3.x) + (p1.y - p3.y) * (p1.y - p3.y));
+        if (!std::isfinite(nl)) continue;
+        // combinatorial flip (surface_mesh.cpp:895-919)
+        const int64_t vc = vert[ha3], vd = vert[hb3];
+        next[ha1] = hb3; next[hb3] = ha2; next[ha2] = ha1;
+        next[hb1] = ha3; next[ha3] = hb2; next[hb2] = hb1;
+        vert[ha1] = vc;
+        vert[hb1] = vd;
+        elen[e] = nl;
+        st.flips++;
+        const int64_t nb[4] = {hedge[next[ha1]], hedge[next[next[ha1]]], hedge[next[hb1]], hedge[next[next[hb1]]]};
+        for (int64_t ne : nb)
+            if (!in_queue[ne]) {
+                queue.push_back(ne);
+                in_queue[ne] = 1;
+            }
+    }
+    // ---- vertex dual areas (intrinsic_geometry_interface.cpp:90-101) and mean edge length (src/signed_heat_3d.cpp:51-60)
+    for (int64_t i = 0; i < nP; i++) areas_out[i] = 0;
+    std::vector<char> seen(H, 0);
+    st.min_cotan = 1e300;
+    for (int64_t h = 0; h < H; h++) {
+        if (seen[h]) continue;
+        const int64_t h1 = next[h], h2 = next[h1];
+        seen[h] = seen[h1] = seen[h2] = 1;
+        const double A = face_area(h);
+        areas_out[vert[h]] += A / 3.0;
+        areas_out[vert[h1]] += A / 3.0;
+        areas_out[vert[h2]] += A / 3.0;
+    }
+    double hs = 0;
+    for (int64_t e = 0; e < E; e++) {
+        hs += elen[e];
+        st.min_cotan = std::min(st.min_cotan, edge_cotan(e));
+    }
+    *h_out = hs / (double)E;
+}
+
 }  // namespace
 
 extern "C" {
@@ -195,7 +375,8 @@ int shm3d_debug_local_ring(const double* coords2d, int32_t n, int32_t* ring_out,
 }
 
 int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_neighbors, double* areas_out,
-                        double* h_out, int64_t* n_triangles_out) {
+                        double* h_out, int64_t* n_triangles_out, int64_t* n_flips_out, double* min_cotan_out,
+                        double* area_before_out) {
     if (!P || !N || !areas_out || !h_out || nP <= 0) return SHM3D_ERR_INVALID_ARG;
     const int k = k_neighbors > 0 ? k_neighbors : 30;  // PointPositionGeometry::kNeighborSize
     if ((int64_t)k + 1 > nP) return SHM3D_ERR_INVALID_ARG;  // "k+1 is greater than number of points" (knn.cpp:53)
@@ -245,32 +426,11 @@ int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_
         *h_out = 0;
         return SHM3D_ERR_INVALID_ARG;
     }
-    // 3-D edge lengths per soup triangle, intrinsic mollification (intrinsic_mollification.cpp:7-38): every length
-    // grows by eps = max(0, max over corners of lC - lA - lB + delta), delta = 1e-5 * mean edge length
-    std::vector<double> len((size_t)3 * T);
-    double perim = 0;
-    for (int64_t f = 0; f < T; f++)
-        for (int e = 0; e < 3; e++) {
-            const double* a = P + 3 * tris[3 * f + e];
-            const double* b = P + 3 * tris[3 * f + (e + 1) % 3];
-            const double d = std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
-            len[3 * f + e] = d;
-            perim += d;
-        }
-    const double delta = (perim / (3.0 * T)) * 1e-5;
-    double eps = 0;
-    for (int64_t f = 0; f < T; f++)
-        for (int e = 0; e < 3; e++)
-            eps = std::fmax(eps, len[3 * f + (e + 2) % 3] - len[3 * f + e] - len[3 * f + (e + 1) % 3] + delta);
-    double hsum = 0;
-    for (int64_t f = 0; f < T; f++) {
-        const double a = len[3 * f] + eps, b = len[3 * f + 1] + eps, c = len[3 * f + 2] + eps;
-        const double s = 0.5 * (a + b + c);
-        const double area = std::sqrt(std::max(0.0, s * (s - a) * (s - b) * (s - c)));  // Heron on the intrinsic lengths
-        for (int e = 0; e < 3; e++) areas_out[tris[3 * f + e]] += 2.0 * area / 3.0;     // two sheets of the tufted cover
-        hsum += a + b + c;
-    }
-    *h_out = hsum / (3.0 * T);  // cover edges: 3T, each carrying the length of the triangle side it came from
+    CoverStats cs;
+    tufted_cover_weights(P, nP, tris, areas_out, h_out, cs);
+    if (n_flips_out) *n_flips_out = cs.flips;
+    if (min_cotan_out) *min_cotan_out = cs.min_cotan;
+    if (area_before_out) *area_before_out = cs.area_before;
     return SHM3D_OK;
 }
 

@@ -91,7 +91,7 @@ def lib():
         L.shm3d_debug_constraints.argtypes = [PP, C.c_int64, dp, i32p, i64p, dp, i64p, C.c_int64]
         L.shm3d_debug_factor_solve.argtypes = [PP, C.c_int64, dp, C.c_int32, dp, C.c_int32, dp, i32p]
         L.shm3d_version.restype = C.c_char_p
-        L.shm3d_point_weights.argtypes = [dp, dp, C.c_int64, C.c_int32, dp, dp, i64p]
+        L.shm3d_point_weights.argtypes = [dp, dp, C.c_int64, C.c_int32, dp, dp, i64p, i64p, dp, dp]
         L.shm3d_debug_local_ring.argtypes = [dp, C.c_int32, i32p, i32p]
         L.shm3d_ctx_stream.argtypes = [vp]
         L.shm3d_ctx_stream.restype = vp
@@ -152,16 +152,20 @@ def prepare_points(P, h, tCoef=1.0, hCoef=0.0, scale=2.0):
     return p
 
 
-def point_weights(P, normals, k=30):
-    """Per-point areas and mean edge length for the point-cloud overload (row N1, without the tufted-cover flips):
-    returns (areas[nP], h, n_soup_triangles)."""
+def point_weights(P, normals, k=30, diagnostics=False):
+    """Per-point areas and mean edge length for the point-cloud overload (row N1: geometry-central's tufted-cover
+    pipeline restated).  Returns (areas[nP], h, n_soup_triangles) [+ dict(flips, min_cotan, area_before)]."""
     P, Nn = _c64(P), _c64(normals)
     areas = np.empty(len(P))
     h = C.c_double()
-    nt = C.c_int64()
-    rc = lib().shm3d_point_weights(_dp(P), _dp(Nn), len(P), k, _dp(areas), C.byref(h), C.byref(nt))
+    nt, nf = C.c_int64(), C.c_int64()
+    mc, ab = C.c_double(), C.c_double()
+    rc = lib().shm3d_point_weights(_dp(P), _dp(Nn), len(P), k, _dp(areas), C.byref(h), C.byref(nt), C.byref(nf),
+                                   C.byref(mc), C.byref(ab))
     if rc != OK:
         raise Shm3dError(rc, "shm3d_point_weights: invalid input (need more than k points, finite data, some triangles)")
+    if diagnostics:
+        return areas, h.value, nt.value, dict(flips=nf.value, min_cotan=mc.value, area_before=ab.value)
     return areas, h.value, nt.value
 
 

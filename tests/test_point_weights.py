@@ -1,6 +1,8 @@
-"""CPU tests of the point-cloud source weights (row N1, partial: geometry-central's pipeline without the tufted-cover
-flips): kNN, tangent-plane local Delaunay rings against scipy's Delaunay triangulation, areas and mean edge length
-against closed forms on well-sampled surfaces."""
+"""CPU tests of the point-cloud source weights (row N1: geometry-central's tufted-cover pipeline restated in
+csrc/point_weights.cpp).  geometry-central cannot be built here, so the checks are: tangent-plane local Delaunay rings
+against scipy's Delaunay triangulation, invariants of the cover (closed manifold, area preserved by the intrinsic
+flips, intrinsically Delaunay at the end), closed forms on sampled spheres, and the bunny point cloud (= the vertices
+of data/bunny_small.obj) against that mesh's own mean edge length."""
 import os
 import sys
 
@@ -101,3 +103,31 @@ def test_knn_is_exact():
         coords = np.stack([-v[:, 1], v[:, 0]], axis=1)
         ring, tri = shm3d.debug_local_ring(coords)
         assert len(ring) >= 3
+
+
+def test_tufted_cover_invariants():
+    """The intrinsic flips preserve the total area of the cover and end with every edge Delaunay (cotan weight >= -1e-6,
+    simple_idt.cpp); the weights are exactly the thirds of the final face areas."""
+    rng = np.random.default_rng(4)
+    P = fib_points(3000) + 0.004 * rng.standard_normal((3000, 3))      # noisy sphere: the local stars disagree
+    Nn = P / np.linalg.norm(P, axis=1, keepdims=True)
+    areas, h, ntri, d = shm3d.point_weights(P, Nn, diagnostics=True)
+    assert d["flips"] > 0
+    assert abs(areas.sum() / d["area_before"] - 1) < 1e-10
+    assert d["min_cotan"] >= -1e-6
+    assert (areas > 0).all()
+
+
+def test_bunny_cloud_mean_edge_length_matches_its_mesh():
+    """bunny.pc holds the vertices of bunny_small.obj: the tufted triangulation's mean intrinsic edge length must be
+    close to the mesh's mean edge length (0.0950) -- it sets lambda for the point overload."""
+    from conftest import load_golden
+    from oracle import shm_oracle as o
+    d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
+    z, F = load_golden("bunny_small")
+    assert np.abs(d["P"] - z["V"]).max() < 1e-5
+    areas, h, ntri, diag = shm3d.point_weights(d["P"], d["N"], diagnostics=True)
+    assert abs(h / o.mesh_sources(z["V"], F)["h"] - 1) < 0.02
+    assert diag["min_cotan"] >= -1e-6 and abs(areas.sum() / diag["area_before"] - 1) < 1e-10
+    # six copies of the surface (3 local stars x 2 sheets), give or take the disagreement between neighbouring stars
+    assert 0.9 < areas.sum() / (6 * o.mesh_sources(z["V"], F)["area"].sum()) < 1.25

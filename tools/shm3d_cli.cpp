@@ -151,8 +151,8 @@ int main(int argc, char** argv) {
         if (is_pc) {
             if (!read_pc(input, pc) || pc.nPoints() == 0) throw std::runtime_error("cannot read point cloud " + input);
             if ((int64_t)pc.normals.size() != 3 * pc.nPoints()) throw std::runtime_error("point cloud needs one 'vn' per 'v'");
-            pc.computeWeights();  // row N1 (partial): see include/shm3d/signed_heat_grid_solver.hpp
-            std::fprintf(stderr, "[shm3d_cli] point cloud: local-Delaunay vertex areas (tufted-cover flips not applied), h = %g\n",
+            pc.computeWeights();  // row N1: see include/shm3d/signed_heat_grid_solver.hpp
+            std::fprintf(stderr, "[shm3d_cli] point cloud: tufted-cover vertex dual areas, mean intrinsic edge length h = %g\n",
                          pc.meanEdgeLength);
         } else if (!read_obj(input, mesh) || mesh.nFaces() == 0) {
             throw std::runtime_error("cannot read mesh " + input);
