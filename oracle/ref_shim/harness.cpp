@@ -5,19 +5,6 @@
 
 #include "signed_heat_grid_solver.h"
 
-namespace geometrycentral {
-shim_solve_fn& shim_solver() {
-    static shim_solve_fn f = nullptr;
-    return f;
-}
-}  // namespace geometrycentral
-namespace polyscope {
-VolumeGrid& shim_last_grid() {
-    static VolumeGrid g;
-    return g;
-}
-}  // namespace polyscope
-
 namespace {
 std::string g_err;
 SignedHeat3DOptions make_opts(double tCoef, double hCoef, double scale, int fast) {

@@ -115,3 +115,27 @@ def test_knot_golden_is_the_reference_sources_output():
     z, F = load_golden("knot")
     phi = rb.compute_distance_mesh(z["V"], F, hCoef=1)
     assert np.abs(phi - z["h1_phi"]).max() < 1e-9 * np.abs(phi).max()
+
+
+def test_adapter_compiles_against_the_reference_headers(tmp_path):
+    """adapter/signed_heat_grid_solver_b200.cpp -- the drop-in replacement of src/signed_heat_grid_solver.cpp -- must
+    compile against the reference's own unchanged headers (the shim stands in for geometry-central / Eigen / polyscope)
+    and link against libshm3d_grid.so together with the reference's src/signed_heat_3d.cpp."""
+    import os
+    import subprocess
+    import shm3d
+    from conftest import ROOT
+    if not os.path.isdir(os.path.join(rb.REF_ROOT, "include")):
+        pytest.skip("needs the reference tree")
+    libdir = os.path.dirname(shm3d.LIB_PATH)
+    out = str(tmp_path / "libadapter.so")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-shared", "-w",
+                           "-I" + os.path.join(ROOT, "oracle", "ref_shim", "include"),
+                           "-I" + os.path.join(rb.REF_ROOT, "include"), "-I" + os.path.join(ROOT, "include"),
+                           "-o", out, os.path.join(ROOT, "adapter", "signed_heat_grid_solver_b200.cpp"),
+                           os.path.join(rb.REF_ROOT, "src", "signed_heat_3d.cpp"),
+                           os.path.join(ROOT, "oracle", "ref_shim", "shim_defs.cpp"),
+                           "-L" + libdir, "-lshm3d_grid", "-Wl,-rpath," + libdir, "-Wl,--no-undefined"])
+    import ctypes
+    L = ctypes.CDLL(out)   # resolves every symbol: the class is fully defined by the adapter + signed_heat_3d.cpp
+    assert L is not None
