@@ -21,6 +21,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libshm_ref.so")
+# the same C entry points around the PRODUCT's drop-in translation unit (adapter/signed_heat_grid_solver_b200.cpp compiled
+# against the reference's unchanged headers and linked to libshm3d_grid.so): needs a GPU at run time
+ADAPTER_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_adapter.so")
 REF_ROOT = "/root/reference"
 _LIB = None
 
@@ -30,7 +33,8 @@ SOLVE_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINT
 
 def build(force: bool = False) -> bool:
     """(Re)build oracle/_ref/libshm_ref.so when the reference tree is present; returns whether the library exists."""
-    if os.path.isdir(os.path.join(REF_ROOT, "src")) and (force or not os.path.exists(LIB_PATH)):
+    if os.path.isdir(os.path.join(REF_ROOT, "src")) and (force or not os.path.exists(LIB_PATH)
+                                                         or not os.path.exists(ADAPTER_LIB_PATH)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return os.path.exists(LIB_PATH)
 
@@ -39,10 +43,20 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+_ADAPTER = None
+
+
+def use_adapter(flag: bool):
+    """Route the compute_distance_* calls below to the product's drop-in TU (GPU) instead of the reference's source."""
+    global _LIB, _ADAPTER
+    _ADAPTER = bool(flag)
+    _LIB = None
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(ADAPTER_LIB_PATH if _ADAPTER else LIB_PATH)
         dp, ip, fp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_float)
         L.ref_compute_distance_mesh.argtypes = [dp, C.c_int64, ip, ip, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int,
                                                 SOLVE_FN, dp, C.c_int64, ip, fp]
