@@ -377,6 +377,9 @@ struct Solver {
         G.cell = prm->cell;
         L0 = LevelDims{G.nx, G.ny, G.nz, G.k0, G.k1};
         if (L0.nzl() < 1) throw Error(SHM3D_ERR_INVALID_ARG, "more ranks than grid planes");
+        // the grid kernels index a rank's nodes (plus two ghost planes) with 32-bit integers
+        if ((double)L0.n() + 2.0 * (double)L0.plane() >= 4294967296.0)
+            throw Error(SHM3D_ERR_INVALID_ARG, "this rank's slab has 2^32 or more nodes: split the grid over more GPUs");
         nu = prm->mg_smooth > 0 ? prm->mg_smooth : 2;
         use_mg = !(prm->flags & SHM3D_FLAG_NO_MG);
         prof.on = (prm->flags & SHM3D_FLAG_PROFILE) != 0;
