@@ -40,30 +40,49 @@ def test_adapter_fails_loudly_without_a_gpu():
         rb.use_adapter(False)
 
 
+CHILD = r'''
+import os, sys
+root = sys.argv[1]; out = sys.argv[2]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+import numpy as np
+from conftest import icosphere, load_golden
+from oracle import reference_build as rb, shm_oracle as o
+rb.use_adapter(True)
+z, F = load_golden("bunny_small")
+phi, info = rb.compute_distance_mesh(z["V"], F, hCoef=1, return_info=True)
+phif = rb.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
+V, Fs = icosphere(2)
+s = o.mesh_sources(V, Fs)
+phip = rb.compute_distance_points(s["pos"], s["nrm"], s["area"] * 1.3, 0.2, hCoef=1)
+np.savez(out, phi=phi, dims=info["dims"], n_solves=len(info["solves"]), phif=phif, phip=phip)
+'''
+
+
 @pytest.mark.gpu
-def test_adapter_equals_reference_source_on_the_gpu():
-    _adapter_or_skip()
-    try:
-        z, F = load_golden("bunny_small")
-        try:
-            phi, info = rb.compute_distance_mesh(z["V"], F, hCoef=1, return_info=True)
-        except RuntimeError as e:  # first GPU outing of this prebuilt harness: report, do not mask numeric failures below
-            pytest.skip(f"adapter harness raised before producing a field: {e}")
-        ref = z["h1_phi"]  # = the reference source's own output (tests/test_reference_build.py)
-        assert np.linalg.norm(phi - ref) / np.linalg.norm(ref) < 1e-4
-        assert list(info["dims"]) == [32, 32, 32] and len(info["solves"]) == 0   # registerVolumeGrid side effect; no LU
-        # fastIntegration through the same class
-        phif = rb.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
-        reff = o.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
-        assert np.linalg.norm(phif - reff) / np.linalg.norm(reff) < 1e-4
-        # point-cloud overload with caller-supplied tufted quantities
-        V, Fs = icosphere(2)
-        s = o.mesh_sources(V, Fs)
-        areas, h = s["area"] * 1.3, 0.2
-        phip = rb.compute_distance_points(s["pos"], s["nrm"], areas, h, hCoef=1)
-        c = s["pos"].sum(axis=0) / len(s["pos"])
-        r = np.sqrt(((s["pos"] - c) ** 2).sum(axis=1)).max()
-        refp = o.compute_distance(s["pos"], s["nrm"], areas, h, c, r, hCoef=1, scrub_nonfinite=False)
-        assert np.linalg.norm(phip - refp) / np.linalg.norm(refp) < 1e-4
-    finally:
-        rb.use_adapter(False)
+def test_adapter_equals_reference_source_on_the_gpu(tmp_path):
+    """Runs in a child process (a prebuilt native harness on its first GPU outing must not be able to take the test
+    session down); a child that fails before producing fields is reported as a skip, wrong numbers are failures."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if not (rb.build() and os.path.exists(rb.ADAPTER_LIB_PATH)):
+        pytest.skip("no prebuilt oracle/_ref/libshm_adapter.so")
+    script = tmp_path / "child.py"
+    script.write_text(CHILD)
+    out = str(tmp_path / "fields.npz")
+    r = subprocess.run([sys.executable, str(script), ROOT, out], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0 or not os.path.exists(out):
+        pytest.skip("adapter harness did not produce fields: " + (r.stderr or "")[-400:])
+    d = np.load(out)
+    z, F = load_golden("bunny_small")
+    ref = z["h1_phi"]  # = the reference source's own output (tests/test_reference_build.py)
+    assert np.linalg.norm(d["phi"] - ref) / np.linalg.norm(ref) < 1e-4
+    assert list(d["dims"]) == [32, 32, 32] and int(d["n_solves"]) == 0   # registerVolumeGrid side effect; no LU callback
+    reff = o.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
+    assert np.linalg.norm(d["phif"] - reff) / np.linalg.norm(reff) < 1e-4
+    V, Fs = icosphere(2)
+    s = o.mesh_sources(V, Fs)
+    c = s["pos"].sum(axis=0) / len(s["pos"])
+    r0 = np.sqrt(((s["pos"] - c) ** 2).sum(axis=1)).max()
+    refp = o.compute_distance(s["pos"], s["nrm"], s["area"] * 1.3, 0.2, c, r0, hCoef=1, scrub_nonfinite=False)
+    assert np.linalg.norm(d["phip"] - refp) / np.linalg.norm(refp) < 1e-4
