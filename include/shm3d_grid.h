@@ -170,6 +170,9 @@ int shm3d_prepare_points(const double* P, int64_t nP, double h, double tCoef, do
 int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_neighbors, double* areas_out,
                         double* h_out, int64_t* n_triangles_out, int64_t* n_flips_out, double* min_cotan_out,
                         double* area_before_out);
+/* probe for the tests: tufted cover + intrinsic Delaunay flips of a given triangle soup (tris: int64[T][3]) */
+int shm3d_debug_tufted_weights(const double* P, int64_t nP, const int64_t* tris, int64_t T, double* areas_out, double* h_out,
+                               int64_t* n_flips_out, double* min_cotan_out, double* area_before_out);
 /* probe for the tests: the local Delaunay 1-ring of the origin among n tangent-plane points (returns the ring size) */
 int shm3d_debug_local_ring(const double* coords2d, int32_t n, int32_t* ring_out, int32_t* tri_after_out);
 

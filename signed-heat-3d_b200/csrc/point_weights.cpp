@@ -374,6 +374,21 @@ int shm3d_debug_local_ring(const double* coords2d, int32_t n, int32_t* ring_out,
     return (int)ring.size();
 }
 
+// probe for the tests: tufted cover + intrinsic Delaunay flips of a GIVEN triangle soup (tris[T][3], vertex indices)
+int shm3d_debug_tufted_weights(const double* P, int64_t nP, const int64_t* tris, int64_t T, double* areas_out, double* h_out,
+                               int64_t* n_flips_out, double* min_cotan_out, double* area_before_out) {
+    if (!P || !tris || !areas_out || !h_out || nP <= 0 || T <= 0) return SHM3D_ERR_INVALID_ARG;
+    for (int64_t i = 0; i < 3 * T; i++)
+        if (tris[i] < 0 || tris[i] >= nP) return SHM3D_ERR_INVALID_ARG;
+    std::vector<int64_t> t(tris, tris + 3 * T);
+    CoverStats cs;
+    tufted_cover_weights(P, nP, t, areas_out, h_out, cs);
+    if (n_flips_out) *n_flips_out = cs.flips;
+    if (min_cotan_out) *min_cotan_out = cs.min_cotan;
+    if (area_before_out) *area_before_out = cs.area_before;
+    return SHM3D_OK;
+}
+
 int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_neighbors, double* areas_out,
                         double* h_out, int64_t* n_triangles_out, int64_t* n_flips_out, double* min_cotan_out,
                         double* area_before_out) {

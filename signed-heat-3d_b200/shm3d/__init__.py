@@ -55,7 +55,7 @@ EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
            "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points", "shm3d_point_weights",
-           "shm3d_debug_local_ring"]
+           "shm3d_debug_local_ring", "shm3d_debug_tufted_weights"]
 
 _lib = None
 
@@ -93,6 +93,7 @@ def lib():
         L.shm3d_version.restype = C.c_char_p
         L.shm3d_point_weights.argtypes = [dp, dp, C.c_int64, C.c_int32, dp, dp, i64p, i64p, dp, dp]
         L.shm3d_debug_local_ring.argtypes = [dp, C.c_int32, i32p, i32p]
+        L.shm3d_debug_tufted_weights.argtypes = [dp, C.c_int64, i64p, C.c_int64, dp, dp, i64p, dp, dp]
         L.shm3d_ctx_stream.argtypes = [vp]
         L.shm3d_ctx_stream.restype = vp
         L.shm3d_host_alloc.argtypes = [C.c_size_t]
@@ -167,6 +168,20 @@ def point_weights(P, normals, k=30, diagnostics=False):
     if diagnostics:
         return areas, h.value, nt.value, dict(flips=nf.value, min_cotan=mc.value, area_before=ab.value)
     return areas, h.value, nt.value
+
+
+def debug_tufted_weights(P, tris):
+    """Tufted cover + intrinsic Delaunay flips of a given triangle soup -> (areas[nP], h, dict(flips, min_cotan, area_before))."""
+    P = _c64(P)
+    t = np.ascontiguousarray(tris, dtype=np.int64)
+    areas = np.empty(len(P))
+    h, mc, ab = C.c_double(), C.c_double(), C.c_double()
+    nf = C.c_int64()
+    rc = lib().shm3d_debug_tufted_weights(_dp(P), len(P), t.ctypes.data_as(C.POINTER(C.c_int64)), len(t), _dp(areas),
+                                          C.byref(h), C.byref(nf), C.byref(mc), C.byref(ab))
+    if rc != OK:
+        raise Shm3dError(rc, "shm3d_debug_tufted_weights: invalid input")
+    return areas, h.value, dict(flips=nf.value, min_cotan=mc.value, area_before=ab.value)
 
 
 def debug_local_ring(coords2d):

@@ -131,3 +131,76 @@ def test_bunny_cloud_mean_edge_length_matches_its_mesh():
     assert diag["min_cotan"] >= -1e-6 and abs(areas.sum() / diag["area_before"] - 1) < 1e-10
     # six copies of the surface (3 local stars x 2 sheets), give or take the disagreement between neighbouring stars
     assert 0.9 < areas.sum() / (6 * o.mesh_sources(z["V"], F)["area"].sum()) < 1.25
+
+
+def _dual_areas(P, tris):
+    a = np.zeros(len(P))
+    for t in tris:
+        p0, p1, p2 = P[t[0]], P[t[1]], P[t[2]]
+        A = 0.5 * np.linalg.norm(np.cross(p1 - p0, p2 - p0))
+        a[list(t)] += A / 3
+    return a
+
+
+def test_cover_of_a_delaunay_manifold_mesh_needs_no_flips():
+    """A closed manifold Delaunay mesh (convex hull of sphere points): the cover is two glued copies, nothing to flip,
+    vertex areas = 2 x the mesh's barycentric dual areas, mean edge length unchanged."""
+    P = fib_points(800)
+    hull = ConvexHull(P)
+    tris = hull.simplices.astype(np.int64)
+    a, b, c = P[tris[:, 0]], P[tris[:, 1]], P[tris[:, 2]]
+    flip = np.einsum("ij,ij->i", np.cross(b - a, c - a), a + b + c) < 0
+    tris[flip] = tris[flip][:, [0, 2, 1]]
+    areas, h, d = shm3d.debug_tufted_weights(P, tris)
+    assert d["flips"] == 0
+    assert np.abs(areas - 2 * _dual_areas(P, tris)).max() < 1e-9       # (mollification adds ~1e-7 relative)
+    e = np.unique(np.sort(np.vstack([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]]), axis=1), axis=0)
+    assert abs(h - np.linalg.norm(P[e[:, 0]] - P[e[:, 1]], axis=1).mean()) < 1e-6
+
+
+def test_intrinsic_flips_recover_the_planar_delaunay_triangulation():
+    """A planar triangulation spoiled by random edge flips has the same intrinsic (flat) metric as the Delaunay
+    triangulation of its vertices, which is unique in general position: after the intrinsic flips on the cover the vertex
+    areas must equal 2 x the Delaunay dual areas, whatever the starting triangulation, boundary included."""
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(0, 1, size=(300, 2))
+    D = Delaunay(pts)
+    tris = D.simplices.astype(np.int64).copy()
+    # spoil it: flip interior edges whose quadrilateral is strictly convex, a few hundred times
+    def orient(t):
+        p = pts[t]
+        return (p[1, 0] - p[0, 0]) * (p[2, 1] - p[0, 1]) - (p[1, 1] - p[0, 1]) * (p[2, 0] - p[0, 0])
+    for _ in range(400):
+        edge_faces = {}
+        for fi, t in enumerate(tris):
+            for k in range(3):
+                edge_faces.setdefault(tuple(sorted((t[k], t[(k + 1) % 3]))), []).append(fi)
+        inner = [(e, f) for e, f in edge_faces.items() if len(f) == 2]
+        e, (f0, f1) = inner[rng.integers(len(inner))]
+        o0 = [v for v in tris[f0] if v not in e][0]
+        o1 = [v for v in tris[f1] if v not in e][0]
+        t0, t1 = np.array([o0, e[0], o1]), np.array([o0, o1, e[1]])
+        if orient(t0) * orient(t1) <= 1e-12:      # not strictly convex: skip
+            continue
+        if orient(t0) < 0:
+            t0, t1 = t0[[0, 2, 1]], t1[[0, 2, 1]]
+        tris[f0], tris[f1] = t0, t1
+    P3 = np.column_stack([pts, np.zeros(len(pts))])
+    assert abs(_dual_areas(P3, tris).sum() - _dual_areas(P3, D.simplices).sum()) < 1e-12   # still a triangulation of the hull
+    areas, h, d = shm3d.debug_tufted_weights(P3, tris)
+    assert d["flips"] > 50 and d["min_cotan"] >= -1e-6
+    assert abs(areas.sum() / d["area_before"] - 1) < 1e-10
+    ref = 2 * _dual_areas(P3, D.simplices.astype(np.int64))
+    rel = np.abs(areas - ref) / ref.max()
+    db = np.minimum(pts, 1 - pts).min(axis=1)          # distance to the boundary of the square
+    # Away from the boundary the planar Delaunay areas come back (to the ~1e-4 the mollification of the skinny spoiled
+    # triangles perturbs the metric by).  Along the boundary the cover folds front onto back -- the double of the convex
+    # hull, with cone points at the hull vertices -- and the intrinsic Delaunay triangulation of THAT surface legitimately
+    # flips obtuse boundary triangles across the fold: only vertices close to the boundary may differ.
+    assert (db > 0.15).sum() > 100
+    assert rel[db > 0.15].max() < 5e-4
+    assert (db[rel > 5e-4] < 0.12).all()
+    # uniqueness: starting from the unspoiled Delaunay triangulation gives the same final cover, vertex by vertex
+    areas0, _, d0 = shm3d.debug_tufted_weights(P3, D.simplices.astype(np.int64))
+    assert d0["flips"] > 0                               # the flips across the boundary fold
+    assert (np.abs(areas - areas0) / ref.max()).max() < 2e-3
