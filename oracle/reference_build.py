@@ -24,6 +24,8 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libshm_ref.so")
 # the same C entry points around the PRODUCT's drop-in translation unit (adapter/signed_heat_grid_solver_b200.cpp compiled
 # against the reference's unchanged headers and linked to libshm3d_grid.so): needs a GPU at run time
 ADAPTER_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_adapter.so")
+# the marching-cubes routine of the reference's downstream consumer (row N3): polyscope's vendored MarchingCube/MC.h + glm
+MC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_mc_ref.so")
 REF_ROOT = "/root/reference"
 _LIB = None
 
@@ -34,7 +36,8 @@ SOLVE_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINT
 def build(force: bool = False) -> bool:
     """(Re)build oracle/_ref/libshm_ref.so when the reference tree is present; returns whether the library exists."""
     if os.path.isdir(os.path.join(REF_ROOT, "src")) and (force or not os.path.exists(LIB_PATH)
-                                                         or not os.path.exists(ADAPTER_LIB_PATH)):
+                                                         or not os.path.exists(ADAPTER_LIB_PATH)
+                                                         or not os.path.exists(MC_LIB_PATH)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return os.path.exists(LIB_PATH)
 
@@ -161,3 +164,50 @@ def yukawa(x, y, lam):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
     return float(lib().ref_yukawa(_dp(x), _dp(y), float(lam)))
+
+
+# ------------------------------------------------------------------------------------------------ row N3: isosurface
+_MC = None
+
+
+def mc_available() -> bool:
+    return os.path.exists(MC_LIB_PATH)
+
+
+def mc_lib():
+    global _MC
+    if _MC is None:
+        L = C.CDLL(MC_LIB_PATH)
+        fp, up, ip = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)
+        L.ref_isosurface.argtypes = [fp, C.c_float, up, fp, fp, C.c_int, fp, C.c_int64, up, C.c_int64, ip, ip]
+        L.ref_mc_table.restype = C.POINTER(C.c_uint64)
+        _MC = L
+    return _MC
+
+
+def mc_table():
+    """The 256-entry packed case table of MarchingCube/MC.h (low nibble = triangle count, then one nibble per corner)."""
+    return np.ctypeslib.as_array(mc_lib().ref_mc_table(), shape=(256,)).copy()
+
+
+def isosurface(values, isoval, dims, bound_min, bound_max, world=True):
+    """registerIsosurfaceAsMesh of the reference's consumer (deps/polyscope/src/volume_grid_scalar_quantity.cpp:209-228):
+    values = the node scalars (any float type; narrowed to float32 as polyscope stores them), index i + j*nx + k*nx*ny.
+    Returns (vertices float32[nV,3], triangles uint32[nT,3]) in the order MC::marching_cube produced them."""
+    v = np.ascontiguousarray(np.asarray(values).ravel(), dtype=np.float32)
+    d = np.asarray(dims, dtype=np.uint32)
+    assert v.size == int(d[0]) * int(d[1]) * int(d[2])
+    bmin = np.ascontiguousarray(bound_min, dtype=np.float32)
+    bmax = np.ascontiguousarray(bound_max, dtype=np.float32)
+    fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    nv, ni = C.c_int64(), C.c_int64()
+    L = mc_lib()
+    args = (v.ctypes.data_as(fp), np.float32(isoval), d.ctypes.data_as(up), bmin.ctypes.data_as(fp), bmax.ctypes.data_as(fp),
+            int(bool(world)))
+    L.ref_isosurface(*args, None, 0, None, 0, C.byref(nv), C.byref(ni))
+    verts = np.empty((nv.value, 3), dtype=np.float32)
+    idx = np.empty(ni.value, dtype=np.uint32)
+    rc = L.ref_isosurface(*args, verts.ctypes.data_as(fp), nv.value, idx.ctypes.data_as(up), ni.value, C.byref(nv), C.byref(ni))
+    if rc != 0:
+        raise RuntimeError("reference marching cubes: capacity")
+    return verts, idx.reshape(-1, 3)

@@ -514,3 +514,102 @@ def compute_distance(pos, nrm, area, h, centroid, radius, tCoef=1.0, hCoef=0.0, 
 def compute_distance_mesh(V, faces, **kw):
     s = mesh_sources(V, faces)
     return compute_distance(s["pos"], s["nrm"], s["area"], s["h"], s["centroid"], s["radius"], **kw)
+
+
+# ------------------------------------------------------------------------------------------------ row N3: isosurface
+# The reference's downstream consumer (src/main.cpp:116-128 -> polyscope registerIsosurfaceAsMesh,
+# deps/polyscope/src/volume_grid_scalar_quantity.cpp:209-228) narrows phi to float32 (volume_grid.ipp:103-106) and runs
+# MC::marching_cube (deps/polyscope/deps/MarchingCubeCpp/include/MarchingCube/MC.h:242-315) on it.  Restated below in
+# float32 arithmetic, cell by cell in the same traversal order, so that vertex numbering and triangle order coincide.
+
+_MC_CASES = None
+
+
+def mc_case_table():
+    """case -> list of edge triples (oracle/mc_case_table.txt; provenance: tools/make_mc_table.py)."""
+    global _MC_CASES
+    if _MC_CASES is None:
+        import os
+        tab = [[] for _ in range(256)]
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "mc_case_table.txt")) as f:
+            for line in f:
+                if line.startswith("#"):
+                    continue
+                c, rest = line.split(":")
+                tab[int(c)] = [tuple(int(e) for e in t.split()) for t in rest.split(";") if t.strip()]
+        _MC_CASES = tab
+    return _MC_CASES
+
+
+def marching_cubes(values, isoval, dims, bound_min=None, bound_max=None):
+    """MC::marching_cube as polyscope calls it (MC.h:242-315), plus registerIsosurfaceAsMesh's swizzle/scale/translate
+    when bounds are given.  values: index i + j*nx + k*nx*ny.  The library reads its field as (X*ny + Y)*nz + Z, i.e. its
+    X is the grid's k, its Z the grid's i (volume_grid_scalar_quantity.cpp:222 swizzles back); traversal is Z outermost,
+    X innermost.  Returns (vertices float32[nV,3], triangles uint32[nT,3])."""
+    f32 = np.float32
+    nx, ny, nz = (int(d) for d in dims)
+    SX, SY, SZ = nz, ny, nx          # extents of the library's X, Y, Z (the reference always has nx = ny = nz)
+    fld = np.ascontiguousarray(np.asarray(values).ravel(), dtype=f32).reshape(SX, SY, SZ)   # fld[X, Y, Z]
+    vs = f32(-f32(isoval)) + fld                                                            # MC.h:258-265
+    neg = vs < 0
+    cfg = np.zeros((SX - 1, SY - 1, SZ - 1), dtype=np.int32)
+    for b in range(8):               # corner b: X + (b & 1), Y + (b >> 1 & 1), Z + (b >> 2 & 1)   (MC.h:267-275)
+        dx, dy, dz = b & 1, (b >> 1) & 1, (b >> 2) & 1
+        cfg |= neg[dx:SX - 1 + dx, dy:SY - 1 + dy, dz:SZ - 1 + dz].astype(np.int32) << b
+    act = np.argwhere((cfg != 0) & (cfg != 255))
+    act = act[np.lexsort((act[:, 0], act[:, 1], act[:, 2]))]     # Z outermost, then Y, X innermost (MC.h:252-256)
+    cases = mc_case_table()
+    verts, tris, edge_vertex = [], [], {}
+
+    def compute_edge(va, vb, axis, x, y, z):                      # MC.h:183-193
+        if (va < 0) == (vb < 0):
+            return
+        v = [f32(x), f32(y), f32(z)]
+        v[axis] = f32(v[axis] + f32(va / f32(va - vb)))
+        edge_vertex[(x, y, z, axis)] = len(verts)
+        verts.append(v)
+
+    for x, y, z in act.tolist():
+        c = [vs[x + (b & 1), y + ((b >> 1) & 1), z + ((b >> 2) & 1)] for b in range(8)]
+        if y == 0 and z == 0:                                     # MC.h:279-304
+            compute_edge(c[0], c[1], 0, x, y, z)
+        if z == 0:
+            compute_edge(c[2], c[3], 0, x, y + 1, z)
+        if y == 0:
+            compute_edge(c[4], c[5], 0, x, y, z + 1)
+        compute_edge(c[6], c[7], 0, x, y + 1, z + 1)
+        if x == 0 and z == 0:
+            compute_edge(c[0], c[2], 1, x, y, z)
+        if z == 0:
+            compute_edge(c[1], c[3], 1, x + 1, y, z)
+        if x == 0:
+            compute_edge(c[4], c[6], 1, x, y, z + 1)
+        compute_edge(c[5], c[7], 1, x + 1, y, z + 1)
+        if x == 0 and y == 0:
+            compute_edge(c[0], c[4], 2, x, y, z)
+        if y == 0:
+            compute_edge(c[1], c[5], 2, x + 1, y, z)
+        if x == 0:
+            compute_edge(c[2], c[6], 2, x, y + 1, z)
+        compute_edge(c[3], c[7], 2, x + 1, y + 1, z)
+        edge_key = [(x, y, z, 0), (x, y + 1, z, 0), (x, y, z + 1, 0), (x, y + 1, z + 1, 0),       # MC.h:306-317
+                    (x, y, z, 1), (x + 1, y, z, 1), (x, y, z + 1, 1), (x + 1, y, z + 1, 1),
+                    (x, y, z, 2), (x + 1, y, z, 2), (x, y + 1, z, 2), (x + 1, y + 1, z, 2)]
+        for t in cases[int(cfg[x, y, z])]:
+            tris.append([edge_vertex[edge_key[e]] for e in t])
+    V = np.asarray(verts, dtype=f32).reshape(-1, 3)
+    T = np.asarray(tris, dtype=np.uint32).reshape(-1, 3)
+    if bound_min is not None:        # volume_grid.ipp:72-76 and volume_grid_scalar_quantity.cpp:220-224, float32
+        bmin = np.asarray(bound_min, dtype=f32)
+        bmax = np.asarray(bound_max, dtype=f32)
+        scale = (bmax - bmin) / np.array([nx - 1, ny - 1, nz - 1], dtype=f32)
+        V = (V[:, ::-1] * scale + bmin).astype(f32)
+    return V, T
+
+
+def grid_bounds_f32(g: "Grid"):
+    """The glm::vec3 bounds the reference registers its volume grid with (src/signed_heat_grid_solver.cpp:20-24,35):
+    bboxMin / bboxMax narrowed to float."""
+    bmin = np.asarray(g.bbox_min, dtype=np.float64)
+    bmax = bmin + g.cell * (np.array([g.nx, g.ny, g.nz]) - 1)
+    return bmin.astype(np.float32), bmax.astype(np.float32)
