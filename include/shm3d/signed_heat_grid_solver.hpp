@@ -7,6 +7,8 @@
 //     bool VERBOSE                        <- :22
 //     computeDistance(mesh, options)      <- :16-17, src/signed_heat_grid_solver.cpp:5-114
 //     computeDistance(points, options)    <- :19-20, src/signed_heat_grid_solver.cpp:116-222
+//     isosurface(phi, isoval)             <- what src/main.cpp:116-128 asks polyscope for (registerIsosurfaceAsMesh,
+//                                            deps/polyscope/src/volume_grid_scalar_quantity.cpp:209-228), on the GPU
 // What differs, and why: the reference's overloads take geometry-central objects (VertexPositionGeometry&,
 // PointPositionNormalGeometry&) and return Eigen::VectorXd; neither library can be a dependency of this repository
 // (Eigen is not vendored anywhere on this image), so the inputs here are flat arrays carrying exactly what the
@@ -123,6 +125,32 @@ class SignedHeatGridSolver {
         }
     }
     const shm3d_stats& lastStats() const { return stats_; }
+
+    // The level set {phi = isoval} of a field on the grid of the last solve, as the indexed mesh polyscope's
+    // registerIsosurfaceAsMesh would produce from the float32-narrowed values: same vertex coordinates (world), same
+    // vertex numbering, same triangle order.
+    struct IsoMesh {
+        std::vector<float> vertices;      // [nV][3]
+        std::vector<uint32_t> triangles;  // [nT][3]
+        shm3d_iso_stats stats{};
+    };
+    IsoMesh isosurface(const std::vector<double>& phi, float isoval = 0.f) {
+        if (!haveGrid_) throw std::invalid_argument("isosurface: no grid yet (call computeDistance first)");
+        if (phi.size() != (size_t)grid_.nx * grid_.ny * grid_.nz) throw std::invalid_argument("isosurface: field size does not match the grid");
+        IsoMesh m;
+        int rc = shm3d_isosurface(ctx_, &grid_, phi.data(), SHM3D_FIELD_HOST_F64, isoval, nullptr, nullptr, 0u, &m.stats);
+        if (rc == SHM3D_OK) {
+            m.vertices.resize((size_t)m.stats.n_vertices * 3);
+            m.triangles.resize((size_t)m.stats.n_triangles * 3);
+            rc = shm3d_isosurface_fetch(ctx_, m.vertices.data(), m.triangles.data());
+        }
+        if (rc != SHM3D_OK) {
+            const std::string msg = shm3d_last_error(ctx_);
+            if (rc == SHM3D_ERR_INVALID_ARG) throw std::invalid_argument(msg);
+            throw std::runtime_error(msg);
+        }
+        return m;
+    }
     shm3d_params solverParams{};  // optional overrides: cull_tau, cg_rel_tol, cg_max_iters, mg_smooth (0 = defaults)
 
   private:

@@ -176,6 +176,38 @@ int shm3d_debug_tufted_weights(const double* P, int64_t nP, const int64_t* tris,
 /* probe for the tests: the local Delaunay 1-ring of the origin among n tangent-plane points (returns the ring size) */
 int shm3d_debug_local_ring(const double* coords2d, int32_t n, int32_t* ring_out, int32_t* tri_after_out);
 
+/* ---- Row N3: the consumer of phi, on the device -------------------------------------------------
+ * The reference hands N doubles to polyscope, which narrows them to float32
+ * (deps/polyscope/include/polyscope/volume_grid.ipp:103-106) and, when the user contours (src/main.cpp:116-128), runs
+ * registerIsosurfaceAsMesh (deps/polyscope/src/volume_grid_scalar_quantity.cpp:209-228) = MC::marching_cube of
+ * deps/polyscope/deps/MarchingCubeCpp/include/MarchingCube/MC.h:242-315 + a swizzle/scale/translate of the vertices.
+ * shm3d_isosurface produces the same indexed mesh on the GPU -- same float32 coordinates, same vertex numbering, same
+ * triangle order -- from a field that can stay where shm3d_solve_device left it.  Single-GPU contexts only. */
+#define SHM3D_FIELD_DEVICE_F32 0 /* float[nx*ny*nz] in device memory (phi_dev of shm3d_solve_device) */
+#define SHM3D_FIELD_HOST_F64 1   /* double[nx*ny*nz] on the host (phi_out of shm3d_solve); narrowed to float32 on the device */
+#define SHM3D_FIELD_HOST_F32 2   /* float[nx*ny*nz] on the host */
+#define SHM3D_ISO_LATTICE 1u     /* flag: vertices in the marching-cubes library's own lattice coordinates (k, j, i) */
+typedef struct shm3d_iso_stats {
+    int64_t n_vertices, n_triangles;
+    double ms_device;     /* CUDA-event time of the extraction kernels */
+    int64_t gpu_launches; /* kernels launched by the call (incl. the narrowing of a host field) */
+} shm3d_iso_stats;
+/* Uses p->nx,ny,nz (and bbox_min, cell when the bounds are NULL).  bound_min / bound_max: the float[3] bounds the volume
+ * grid was registered with (src/signed_heat_grid_solver.cpp:20-24,35); NULL = (float)bbox_min and
+ * (float)(bbox_min + cell*(n-1)).  The mesh stays in buffers owned by the context until the next call. */
+int shm3d_isosurface(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t field_kind, float isoval,
+                     const float* bound_min, const float* bound_max, uint32_t iso_flags, shm3d_iso_stats* out);
+/* Copies the last mesh to the host: vertices_out float[n_vertices][3], triangles_out uint32[n_triangles][3]
+ * (either may be NULL). */
+int shm3d_isosurface_fetch(shm3d_ctx* ctx, float* vertices_out, uint32_t* triangles_out);
+/* Device pointers of the last mesh (valid until the next shm3d_isosurface on this context). */
+int shm3d_isosurface_device(shm3d_ctx* ctx, const float** d_vertices, const uint32_t** d_triangles);
+/* Plane slice through the field (what the reference's slice plane displays, src/main.cpp:101-103): out[a + b*nu] =
+ * trilinear interpolant of the node values (src/signed_heat_grid_solver.cpp:405-431) at origin + a*du + b*dv,
+ * a < nu, b < nv; NaN where the point is outside the grid.  out: float[nu*nv] on the host. */
+int shm3d_slice(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t field_kind, const double* origin,
+                const double* du, const double* dv, int32_t nu, int32_t nv, float* out);
+
 /* Host-logic probes for the CPU test-suite (no device code runs; not part of the product path):
  * constraint rows (src/signed_heat_grid_solver.cpp:80-100, :433-464) and the nested-dissection factor of
  * A D^-1 A^T applied on the host with the same block layout the GPU kernels consume. */

@@ -610,6 +610,6 @@ def marching_cubes(values, isoval, dims, bound_min=None, bound_max=None):
 def grid_bounds_f32(g: "Grid"):
     """The glm::vec3 bounds the reference registers its volume grid with (src/signed_heat_grid_solver.cpp:20-24,35):
     bboxMin / bboxMax narrowed to float."""
-    bmin = np.asarray(g.bbox_min, dtype=np.float64)
+    bmin = np.asarray(g.bmin, dtype=np.float64)
     bmax = bmin + g.cell * (np.array([g.nx, g.ny, g.nz]) - 1)
     return bmin.astype(np.float32), bmax.astype(np.float32)

@@ -8,7 +8,7 @@ mkdir -p ../lib
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
      -Xcompiler -fPIC,-pthread,-mavx2,-mfma,-Wall \
      -I"$NCCL_INC" -shared -o $OUT \
-     k_sum.cu grid_ops.cu projector.cu sources.cu dist.cu solver.cu host_api.cu host_blas.cpp point_weights.cpp \
+     k_sum.cu grid_ops.cu projector.cu sources.cu dist.cu isosurface.cu solver.cu host_api.cu host_blas.cpp point_weights.cpp \
      -ldl -lpthread "$@"
 echo "built $OUT"
 # headless driver on top of the C++ mirror (include/shm3d/signed_heat_grid_solver.hpp)

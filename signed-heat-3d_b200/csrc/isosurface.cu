@@ -1,0 +1,262 @@
+// isosurface.cu -- row N3: the downstream consumer of phi on the device.
+//
+// Reference flow being replaced: computeDistance returns N doubles to the host (8.6 GB at 1024^3), polyscope narrows
+// them to float32 (deps/polyscope/include/polyscope/volume_grid.ipp:103-106) and registerIsosurfaceAsMesh
+// (deps/polyscope/src/volume_grid_scalar_quantity.cpp:209-228; called from src/main.cpp:116-128) runs the sequential
+// MC::marching_cube (deps/polyscope/deps/MarchingCubeCpp/include/MarchingCube/MC.h:242-315) over them.
+// Here shm3d_solve_device leaves phi in HBM as float32 and four launches produce the same indexed mesh -- identical
+// vertex coordinates, vertex numbering and triangle order (logic and its derivation: isosurface_core.h):
+//
+//   k_mc_count      one thread per lattice column (fixed j,i; marching along k), lanes along i so that every step reads
+//                   contiguous rows of the k-plane; per column: vertices created, triangles emitted      [reads phi once]
+//   k_mc_scan       exclusive scan of the (nx-1)(ny-1) column counts (one CTA)
+//   k_mc_vertices   columns that create vertices march again and write positions + per-column search keys
+//   k_mc_triangles  columns that emit triangles march again and resolve each corner to a vertex id by locating the
+//                   creating cell's column and bisecting its short key list
+//
+// All four are HBM-bound integer / compare work: 4 B per node for the count pass (algorithmic), and the two emit passes
+// only touch columns the surface crosses.  No tensor cores, no atomics, deterministic output.
+#include "isosurface.cuh"
+
+#include <math.h>
+
+#include "isosurface_core.h"
+
+namespace shm3d {
+
+using mc::Lattice;
+
+__device__ const unsigned long long d_mc_table[256] = {
+#include "mc_table.inc"
+};
+
+constexpr int kLanesZ = 32;  // lattice Z (grid i, contiguous in memory) across the lanes of a warp
+constexpr int kRowsY = 8;    // warps per CTA: consecutive lattice Y (grid j)
+
+__device__ __forceinline__ void load_table(unsigned long long* s_tab) {
+    for (int i = threadIdx.y * kLanesZ + threadIdx.x; i < 256; i += kLanesZ * kRowsY) s_tab[i] = d_mc_table[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kLanesZ* kRowsY)
+    k_mc_count(const Lattice L, const float* __restrict__ field, unsigned int* __restrict__ col_v,
+               unsigned int* __restrict__ col_t) {
+    __shared__ unsigned long long s_tab[256];
+    load_table(s_tab);
+    const int z = blockIdx.x * kLanesZ + threadIdx.x, y = blockIdx.y * kRowsY + threadIdx.y;
+    if (z >= L.SZ - 1 || y >= L.SY - 1) return;
+    mc::CountVisitor cv{s_tab, y, z, 0u, 0u};
+    mc::march_column(L, field, y, z, cv);
+    const int c = mc::column_id(L, y, z);
+    col_v[c] = cv.nv;
+    col_t[c] = cv.nt;
+}
+
+// one CTA: thread t owns the contiguous chunk [t*chunk, (t+1)*chunk) of the n column counts
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+    k_mc_scan(const unsigned int* __restrict__ col_v, const unsigned int* __restrict__ col_t, int n,
+              unsigned long long* __restrict__ voff, unsigned long long* __restrict__ toff) {
+    __shared__ unsigned long long sv[kScanThreads], st[kScanThreads];
+    const int t = threadIdx.x;
+    const int chunk = (n + kScanThreads - 1) / kScanThreads;
+    const long long b0 = (long long)t * chunk;
+    const int b = (int)(b0 < n ? b0 : n), e = (int)(b0 + chunk < n ? b0 + chunk : n);
+    unsigned long long a = 0, c = 0;
+    for (int i = b; i < e; i++) {
+        a += col_v[i];
+        c += col_t[i];
+    }
+    sv[t] = a;
+    st[t] = c;
+    __syncthreads();
+    for (int off = 1; off < kScanThreads; off <<= 1) {  // inclusive scan of the chunk sums
+        unsigned long long x = t >= off ? sv[t - off] : 0ull, y = t >= off ? st[t - off] : 0ull;
+        __syncthreads();
+        sv[t] += x;
+        st[t] += y;
+        __syncthreads();
+    }
+    unsigned long long pv = sv[t] - a, pt = st[t] - c;
+    for (int i = b; i < e; i++) {
+        voff[i] = pv;
+        toff[i] = pt;
+        pv += col_v[i];
+        pt += col_t[i];
+    }
+    if (t == kScanThreads - 1) {
+        voff[n] = sv[t];
+        toff[n] = st[t];
+    }
+}
+
+__global__ void __launch_bounds__(kLanesZ* kRowsY)
+    k_mc_vertices(const Lattice L, const float* __restrict__ field, const unsigned long long* __restrict__ voff,
+                  float* __restrict__ vertices, uint32_t* __restrict__ vkey) {
+    const int z = blockIdx.x * kLanesZ + threadIdx.x, y = blockIdx.y * kRowsY + threadIdx.y;
+    if (z >= L.SZ - 1 || y >= L.SY - 1) return;
+    const int c = mc::column_id(L, y, z);
+    const unsigned long long v0 = voff[c];
+    if (voff[c + 1] == v0) return;  // this column creates nothing: no need to read it again
+    mc::VertexVisitor vv{&L, y, z, v0, vertices, vkey};
+    mc::march_column(L, field, y, z, vv);
+}
+
+__global__ void __launch_bounds__(kLanesZ* kRowsY)
+    k_mc_triangles(const Lattice L, const float* __restrict__ field, const unsigned long long* __restrict__ voff,
+                   const unsigned long long* __restrict__ toff, const uint32_t* __restrict__ vkey,
+                   uint32_t* __restrict__ triangles) {
+    __shared__ unsigned long long s_tab[256];
+    load_table(s_tab);
+    const int z = blockIdx.x * kLanesZ + threadIdx.x, y = blockIdx.y * kRowsY + threadIdx.y;
+    if (z >= L.SZ - 1 || y >= L.SY - 1) return;
+    const int c = mc::column_id(L, y, z);
+    const unsigned long long t0 = toff[c];
+    if (toff[c + 1] == t0) return;
+    mc::TriangleVisitor tv{&L, s_tab, voff, vkey, y, z, t0, triangles};
+    mc::march_column(L, field, y, z, tv);
+}
+
+__global__ void k_narrow_f64(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i];  // round to nearest, like the consumer's static_cast (volume_grid.ipp:103-106)
+}
+
+// trilinear interpolant of the node values at origin + a*du + b*dv (src/signed_heat_grid_solver.cpp:405-431), fp64
+// arithmetic on the float32 field; NaN where the point's cell is not inside the grid
+__global__ void k_slice(int nx, int ny, int nz, const float* __restrict__ field, double bx, double by, double bz, double cell,
+                        double ox, double oy, double oz, double ux, double uy, double uz, double vx, double vy, double vz,
+                        int nu, int nv, float* __restrict__ out) {
+    const size_t total = (size_t)nu * nv;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const double a = (double)(q % nu), b = (double)(q / nu);
+        const double qx = ox + a * ux + b * vx, qy = oy + a * uy + b * vy, qz = oz + a * uz + b * vz;
+        const double fi = floor((qx - bx) / cell), fj = floor((qy - by) / cell), fk = floor((qz - bz) / cell);
+        float r = nanf("");
+        if (fi >= 0 && fj >= 0 && fk >= 0 && fi < nx - 1 && fj < ny - 1 && fk < nz - 1) {
+            const int i = (int)fi, j = (int)fj, k = (int)fk;
+            const double tx = (qx - (bx + i * cell)) / cell, ty = (qy - (by + j * cell)) / cell,
+                         tz = (qz - (bz + k * cell)) / cell;
+            const float* p = field + (size_t)i + (size_t)j * nx + (size_t)k * nx * ny;
+            const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
+            const double v00 = p[0] * (1. - tx) + p[1] * tx, v01 = p[sz] * (1. - tx) + p[sz + 1] * tx;
+            const double v10 = p[sy] * (1. - tx) + p[sy + 1] * tx, v11 = p[sy + sz] * (1. - tx) + p[sy + sz + 1] * tx;
+            const double v0 = v00 * (1. - ty) + v10 * ty, v1 = v01 * (1. - ty) + v11 * ty;
+            r = (float)(v0 * (1. - tz) + v1 * tz);
+        }
+        out[q] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+IsoSurface::IsoSurface() {
+    SHM3D_CUDA_CHECK(cudaHostAlloc((void**)&h_totals_, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    SHM3D_CUDA_CHECK(cudaEventCreate(&ev0_));
+    SHM3D_CUDA_CHECK(cudaEventCreate(&ev1_));
+}
+
+IsoSurface::~IsoSurface() {
+    if (h_totals_) cudaFreeHost(h_totals_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+}
+
+const float* IsoSurface::stage_field(cudaStream_t s, size_t n, const void* field, int kind) {
+    if (kind == SHM3D_FIELD_DEVICE_F32) return (const float*)field;
+    field32_.alloc(n);
+    if (kind == SHM3D_FIELD_HOST_F32) {
+        SHM3D_CUDA_CHECK(cudaMemcpyAsync(field32_.p, field, n * sizeof(float), cudaMemcpyHostToDevice, s));
+        return field32_.p;
+    }
+    if (kind != SHM3D_FIELD_HOST_F64) throw Error(SHM3D_ERR_INVALID_ARG, "unknown field kind");
+    const size_t chunk = (size_t)1 << 26;  // 512 MB of doubles per hop
+    stage64_.alloc(n < chunk ? n : chunk);
+    const double* h = (const double*)field;
+    for (size_t b = 0; b < n; b += chunk) {
+        const size_t cnt = n - b < chunk ? n - b : chunk;
+        SHM3D_CUDA_CHECK(cudaMemcpyAsync(stage64_.p, h + b, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+        k_narrow_f64<<<148 * 8, 256, 0, s>>>(stage64_.p, field32_.p + b, cnt);
+        SHM3D_LAUNCHED();
+        SHM3D_CUDA_CHECK(cudaGetLastError());
+    }
+    return field32_.p;
+}
+
+IsoResult IsoSurface::extract(cudaStream_t s, int nx, int ny, int nz, const float* d_field, float isoval,
+                              const float* bound_min, const float* bound_max) {
+    if (nx < 2 || ny < 2 || nz < 2) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: the grid needs at least 2 nodes per axis");
+    if ((bound_min == nullptr) != (bound_max == nullptr))
+        throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: give both bounds or neither");
+    if ((long long)(nx - 1) * (ny - 1) > 0x7fffffffLL) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: too many columns");
+    const Lattice L = mc::make_lattice(nx, ny, nz, isoval, bound_min, bound_max);
+    const int nc = L.ncols();
+    col_v_.alloc((size_t)nc);
+    col_t_.alloc((size_t)nc);
+    voff_.alloc((size_t)nc + 1);
+    toff_.alloc((size_t)nc + 1);
+    const dim3 block(kLanesZ, kRowsY), grid((unsigned)((L.SZ - 1 + kLanesZ - 1) / kLanesZ), (unsigned)((L.SY - 1 + kRowsY - 1) / kRowsY));
+    if (grid.y > 65535u) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: ny too large");
+    IsoResult res;
+    SHM3D_CUDA_CHECK(cudaEventRecord(ev0_, s));
+    k_mc_count<<<grid, block, 0, s>>>(L, d_field, col_v_.p, col_t_.p);
+    SHM3D_LAUNCHED();
+    k_mc_scan<<<1, kScanThreads, 0, s>>>(col_v_.p, col_t_.p, nc, voff_.p, toff_.p);
+    SHM3D_LAUNCHED();
+    SHM3D_CUDA_CHECK(cudaGetLastError());
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(&h_totals_[0], voff_.p + nc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(&h_totals_[1], toff_.p + nc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+    const unsigned long long nV = h_totals_[0], nT = h_totals_[1];
+    if (nV >= 0xffffffffULL) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: more than 2^32 vertices");
+    res.launches = 2;
+    if (nV > 0) {
+        verts_.alloc((size_t)(3 * nV));
+        vkey_.alloc((size_t)nV);
+        k_mc_vertices<<<grid, block, 0, s>>>(L, d_field, voff_.p, verts_.p, vkey_.p);
+        SHM3D_LAUNCHED();
+        res.launches++;
+    }
+    if (nT > 0) {  // a triangle only references edges that cross, i.e. vertices that exist
+        tris_.alloc((size_t)(3 * nT));
+        k_mc_triangles<<<grid, block, 0, s>>>(L, d_field, voff_.p, toff_.p, vkey_.p, tris_.p);
+        SHM3D_LAUNCHED();
+        res.launches++;
+    }
+    SHM3D_CUDA_CHECK(cudaGetLastError());
+    SHM3D_CUDA_CHECK(cudaEventRecord(ev1_, s));
+    SHM3D_CUDA_CHECK(cudaEventSynchronize(ev1_));
+    float ms = 0;
+    SHM3D_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    res.ms_device = ms;
+    res.n_vertices = (int64_t)nV;
+    res.n_triangles = (int64_t)nT;
+    last_ = res;
+    return res;
+}
+
+void IsoSurface::fetch(cudaStream_t s, float* vertices_out, uint32_t* triangles_out) const {
+    if (vertices_out && last_.n_vertices)
+        SHM3D_CUDA_CHECK(cudaMemcpyAsync(vertices_out, verts_.p, (size_t)last_.n_vertices * 3 * sizeof(float),
+                                         cudaMemcpyDeviceToHost, s));
+    if (triangles_out && last_.n_triangles)
+        SHM3D_CUDA_CHECK(cudaMemcpyAsync(triangles_out, tris_.p, (size_t)last_.n_triangles * 3 * sizeof(uint32_t),
+                                         cudaMemcpyDeviceToHost, s));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+int64_t IsoSurface::slice(cudaStream_t s, int nx, int ny, int nz, const float* d_field, const double bbox_min[3], double cell,
+                          const double origin[3], const double du[3], const double dv[3], int nu, int nv, float* out_host) {
+    if (nu < 1 || nv < 1 || !out_host || !(cell > 0)) throw Error(SHM3D_ERR_INVALID_ARG, "slice: bad arguments");
+    const size_t total = (size_t)nu * nv;
+    slice_.alloc(total);
+    const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_slice<<<blocks, 256, 0, s>>>(nx, ny, nz, d_field, bbox_min[0], bbox_min[1], bbox_min[2], cell, origin[0], origin[1],
+                                   origin[2], du[0], du[1], du[2], dv[0], dv[1], dv[2], nu, nv, slice_.p);
+    SHM3D_LAUNCHED();
+    SHM3D_CUDA_CHECK(cudaGetLastError());
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(out_host, slice_.p, total * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+    return 1;
+}
+
+}  // namespace shm3d

@@ -13,6 +13,7 @@
 #include <memory>
 
 #include "dist.cuh"
+#include "isosurface.cuh"
 #include "projector.cuh"
 
 using namespace shm3d;
@@ -75,6 +76,7 @@ struct shm3d_ctx {
     DevBuf<float4> d_qpts;
     DevBuf<float> d_qY;
     std::vector<MGLevel> levels;
+    std::unique_ptr<IsoSurface> iso;  // row N3, created on first use
 };
 
 namespace shm3d {
@@ -1183,6 +1185,63 @@ int shm3d_debug_factor_solve(const shm3d_params* p, int64_t M, const double* pos
         return e.code;
     }
     return SHM3D_OK;
+}
+
+// ---- row N3: consumer of phi on the device (isosurface.cu) -------------------------------------------------------
+static const float* n3_field(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t kind, const char* who) {
+    if (!p || !phi) throw Error(SHM3D_ERR_INVALID_ARG, std::string(who) + ": null argument");
+    if (ctx->world != 1)
+        throw Error(SHM3D_ERR_INVALID_ARG, std::string(who) + ": single-GPU contexts only (a z-slab rank holds part of the field)");
+    if (p->nx < 2 || p->ny < 2 || p->nz < 2) throw Error(SHM3D_ERR_INVALID_ARG, std::string(who) + ": grid too small");
+    if (!ctx->iso) ctx->iso.reset(new IsoSurface());
+    return ctx->iso->stage_field(ctx->stream, (size_t)p->nx * p->ny * p->nz, phi, kind);
+}
+
+int shm3d_isosurface(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t field_kind, float isoval,
+                     const float* bound_min, const float* bound_max, uint32_t iso_flags, shm3d_iso_stats* out) {
+    SHM3D_API_BEGIN(ctx)
+    const int64_t launches0 = g_kernel_launches;
+    const float* d_field = n3_field(ctx, p, phi, field_kind, "shm3d_isosurface");
+    float bmin[3], bmax[3];
+    const int n[3] = {p->nx, p->ny, p->nz};
+    for (int a = 0; a < 3; a++) {  // the narrowing of bboxMin / bboxMax to glm::vec3 (src/signed_heat_grid_solver.cpp:20-24)
+        bmin[a] = bound_min ? bound_min[a] : (float)p->bbox_min[a];
+        bmax[a] = bound_max ? bound_max[a] : (float)(p->bbox_min[a] + p->cell * (double)(n[a] - 1));
+    }
+    const bool lattice = (iso_flags & SHM3D_ISO_LATTICE) != 0;
+    IsoResult r = ctx->iso->extract(ctx->stream, p->nx, p->ny, p->nz, d_field, isoval, lattice ? nullptr : bmin,
+                                    lattice ? nullptr : bmax);
+    if (out) {
+        out->n_vertices = r.n_vertices;
+        out->n_triangles = r.n_triangles;
+        out->ms_device = r.ms_device;
+        out->gpu_launches = g_kernel_launches - launches0;
+    }
+    SHM3D_API_END(ctx)
+}
+
+int shm3d_isosurface_fetch(shm3d_ctx* ctx, float* vertices_out, uint32_t* triangles_out) {
+    SHM3D_API_BEGIN(ctx)
+    if (!ctx->iso) throw Error(SHM3D_ERR_INVALID_ARG, "shm3d_isosurface_fetch: no isosurface has been extracted on this context");
+    ctx->iso->fetch(ctx->stream, vertices_out, triangles_out);
+    SHM3D_API_END(ctx)
+}
+
+int shm3d_isosurface_device(shm3d_ctx* ctx, const float** d_vertices, const uint32_t** d_triangles) {
+    SHM3D_API_BEGIN(ctx)
+    if (!ctx->iso) throw Error(SHM3D_ERR_INVALID_ARG, "shm3d_isosurface_device: no isosurface has been extracted on this context");
+    if (d_vertices) *d_vertices = ctx->iso->d_vertices();
+    if (d_triangles) *d_triangles = ctx->iso->d_triangles();
+    SHM3D_API_END(ctx)
+}
+
+int shm3d_slice(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t field_kind, const double* origin,
+                const double* du, const double* dv, int32_t nu, int32_t nv, float* out) {
+    SHM3D_API_BEGIN(ctx)
+    if (!origin || !du || !dv || !out) throw Error(SHM3D_ERR_INVALID_ARG, "shm3d_slice: null argument");
+    const float* d_field = n3_field(ctx, p, phi, field_kind, "shm3d_slice");
+    ctx->iso->slice(ctx->stream, p->nx, p->ny, p->nz, d_field, p->bbox_min, p->cell, origin, du, dv, nu, nv, out);
+    SHM3D_API_END(ctx)
 }
 
 }  // extern "C"

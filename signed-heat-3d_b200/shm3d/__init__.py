@@ -45,6 +45,15 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class IsoStats(C.Structure):
+    _fields_ = [("n_vertices", C.c_int64), ("n_triangles", C.c_int64), ("ms_device", C.c_double),
+                ("gpu_launches", C.c_int64)]
+
+
+FIELD_DEVICE_F32, FIELD_HOST_F64, FIELD_HOST_F32 = 0, 1, 2
+ISO_LATTICE = 1
+
+
 class Shm3dError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"shm3d error {code}: {msg}")
@@ -55,7 +64,8 @@ EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
            "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points", "shm3d_point_weights",
-           "shm3d_debug_local_ring", "shm3d_debug_tufted_weights"]
+           "shm3d_debug_local_ring", "shm3d_debug_tufted_weights", "shm3d_isosurface", "shm3d_isosurface_fetch",
+           "shm3d_isosurface_device", "shm3d_slice"]
 
 _lib = None
 
@@ -94,6 +104,10 @@ def lib():
         L.shm3d_point_weights.argtypes = [dp, dp, C.c_int64, C.c_int32, dp, dp, i64p, i64p, dp, dp]
         L.shm3d_debug_local_ring.argtypes = [dp, C.c_int32, i32p, i32p]
         L.shm3d_debug_tufted_weights.argtypes = [dp, C.c_int64, i64p, C.c_int64, dp, dp, i64p, dp, dp]
+        L.shm3d_isosurface.argtypes = [vp, PP, vp, C.c_int32, C.c_float, fp, fp, C.c_uint32, C.POINTER(IsoStats)]
+        L.shm3d_isosurface_fetch.argtypes = [vp, fp, C.POINTER(C.c_uint32)]
+        L.shm3d_isosurface_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+        L.shm3d_slice.argtypes = [vp, PP, vp, C.c_int32, dp, dp, dp, C.c_int32, C.c_int32, fp]
         L.shm3d_ctx_stream.argtypes = [vp]
         L.shm3d_ctx_stream.restype = vp
         L.shm3d_host_alloc.argtypes = [C.c_size_t]
@@ -334,6 +348,56 @@ class Context:
                                       C.byref(st)))
         return phi, st
 
+    # ---- row N3: the consumer of phi on the device
+    @staticmethod
+    def _field(p: Params, phi):
+        """numpy float64 / float32 array (host) or an int device pointer to float32[N] -> (pointer, kind, keep-alive)"""
+        if isinstance(phi, (int, np.integer)):
+            return C.c_void_p(int(phi)), FIELD_DEVICE_F32, None
+        a = np.asarray(phi)
+        if a.dtype == np.float32:
+            a = np.ascontiguousarray(a).ravel()
+            kind = FIELD_HOST_F32
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+            kind = FIELD_HOST_F64
+        if a.size != p.N:
+            raise ValueError("field size does not match the grid")
+        return C.c_void_p(a.ctypes.data), kind, a
+
+    def isosurface(self, p: Params, phi, isoval=0.0, bound_min=None, bound_max=None, lattice=False, fetch=True):
+        """registerIsosurfaceAsMesh on the GPU: (vertices float32[nV,3], triangles uint32[nT,3], IsoStats), numbered and
+        ordered like MC::marching_cube's output.  phi: host array (float64 as computeDistance returns it, or float32)
+        or a device pointer (int) to float32[N].  fetch=False leaves the mesh on the device (returns the stats only)."""
+        ptr, kind, keep = self._field(p, phi)
+        st = IsoStats()
+        bm = None if bound_min is None else np.ascontiguousarray(bound_min, dtype=np.float32)
+        bM = None if bound_max is None else np.ascontiguousarray(bound_max, dtype=np.float32)
+        self._check(lib().shm3d_isosurface(self._h, C.byref(p), ptr, kind, float(isoval), None if bm is None else _fp(bm),
+                                           None if bM is None else _fp(bM), ISO_LATTICE if lattice else 0, C.byref(st)))
+        del keep
+        if not fetch:
+            return st
+        V = np.empty((st.n_vertices, 3), dtype=np.float32)
+        T = np.empty((st.n_triangles, 3), dtype=np.uint32)
+        self._check(lib().shm3d_isosurface_fetch(self._h, _fp(V), T.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return V, T, st
+
+    def isosurface_device(self):
+        """device pointers (ints) of the last mesh: (vertices float32[nV,3], triangles uint32[nT,3])"""
+        dv, dt = C.c_void_p(), C.c_void_p()
+        self._check(lib().shm3d_isosurface_device(self._h, C.byref(dv), C.byref(dt)))
+        return dv.value, dt.value
+
+    def slice(self, p: Params, phi, origin, du, dv, nu, nv):
+        """float32[nv, nu]: trilinear interpolant of phi at origin + a*du + b*dv (NaN outside the grid)"""
+        ptr, kind, keep = self._field(p, phi)
+        o, u, v = _c64(origin), _c64(du), _c64(dv)
+        out = np.empty((nv, nu), dtype=np.float32)
+        self._check(lib().shm3d_slice(self._h, C.byref(p), ptr, kind, _dp(o), _dp(u), _dp(v), nu, nv, _fp(out)))
+        del keep
+        return out
+
 
 def slab_range(rank, world, nz):
     k0, k1 = C.c_int32(), C.c_int32()
@@ -406,6 +470,15 @@ class SignedHeatGridSolver:
         else:
             p, pos, nrm, area, _ = prepare_mesh(V, faces, options.tCoef, options.hCoef, options.scale)
         return self._finish(p, pos, nrm, area, options)
+
+    def isosurface(self, phi, isoval=0.0):
+        """What the reference's contour() does with PHI (src/main.cpp:116-128): the level set as an indexed mesh in world
+        coordinates, identical to polyscope's registerIsosurfaceAsMesh on the float32-narrowed field."""
+        if self.params is None:
+            raise Shm3dError(ERR_INVALID_ARG, "isosurface: no grid yet (call computeDistance first)")
+        V, T, st = self.ctx.isosurface(self.params, phi, isoval)
+        self.iso_stats = st
+        return V, T
 
     def computeDistancePoints(self, P, normals, areas=None, h=None,
                               options: SignedHeat3DOptions = SignedHeat3DOptions()):

@@ -2,13 +2,15 @@
 // way to run a solve unattended: SURVEY.md section 0 D3/D4).
 //
 //   shm3d_cli INPUT.{obj,pc} [--grid|-g] [--h K] [--t TCOEF] [--fast|-f] [--verbose|-V] [--device D]
-//             [-o OUT.{npy,raw}] [--dry-run]
+//             [-o OUT.{npy,raw}] [--isoval C --iso-out SURFACE.obj] [--dry-run]
 //
 // Flags follow the reference's (src/main.cpp:230-238: positional mesh, -g/--grid, -f/--fast, -V/--verbose, --help)
 // plus the --h the README documents (README.md:70) but main.cpp never defined.  Input readers restate
 // geometry-central's OBJ loader (deps/geometry-central/src/surface/simple_polygon_mesh.cpp:167-232 + meshio.cpp:22-29:
 // v / f records, index before the first '/', unused vertices stripped, no vertex merging) and main.cpp's .pc reader
 // (src/main.cpp:196-225: 'v x y z' and 'vn x y z' records).
+// --isoval / --iso-out: what the GUI's "Contour" + "Export isosurface" buttons do (src/main.cpp:116-128, :160-190): the
+// level set phi = C extracted on the GPU (row N3) and written as an OBJ (same vertices / faces polyscope would hold).
 // --dry-run prints the grid / source scalars and exits without touching the GPU (used by the CPU tests).
 #include <algorithm>
 #include <cmath>
@@ -108,13 +110,14 @@ static bool write_npy(const std::string& path, const std::vector<double>& v, siz
 static void usage() {
     std::fprintf(stderr,
                  "usage: shm3d_cli INPUT.{obj,pc} [-g|--grid] [--h K] [--t TCOEF] [-f|--fast] [-V|--verbose] [--device D]\n"
-                 "                 [-o OUT.{npy,raw}] [--dry-run]\n"
+                 "                 [-o OUT.{npy,raw}] [--isoval C --iso-out SURFACE.obj] [--dry-run]\n"
                  "  Generalized signed distance to INPUT on an nx^3 grid, nx = 16*2^K (B200 grid solver; %s)\n",
                  shm3d_version());
 }
 
 int main(int argc, char** argv) {
-    std::string input, output;
+    std::string input, output, iso_output;
+    float isoval = 0.f;
     shm3d::SignedHeat3DOptions opts;
     bool verbose = false, dry = false;
     int device = 0;
@@ -135,6 +138,8 @@ int main(int argc, char** argv) {
         else if (a == "--t") opts.tCoef = std::atof(need("--t"));
         else if (a == "--device") device = std::atoi(need("--device"));
         else if (a == "-o") output = need("-o");
+        else if (a == "--isoval") isoval = (float)std::atof(need("--isoval"));
+        else if (a == "--iso-out") iso_output = need("--iso-out");
         else if (a == "--dry-run") dry = true;
         else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
         else input = a;
@@ -201,6 +206,19 @@ int main(int argc, char** argv) {
                 if (f) std::fclose(f);
             }
             if (!ok) throw std::runtime_error("cannot write " + output);
+        }
+        if (!iso_output.empty()) {
+            shm3d::SignedHeatGridSolver::IsoMesh m = solver.isosurface(phi, isoval);
+            FILE* f = std::fopen(iso_output.c_str(), "w");
+            if (!f) throw std::runtime_error("cannot write " + iso_output);
+            for (size_t v = 0; v < m.vertices.size() / 3; v++)
+                std::fprintf(f, "v %.9g %.9g %.9g\n", m.vertices[3 * v], m.vertices[3 * v + 1], m.vertices[3 * v + 2]);
+            for (size_t t = 0; t < m.triangles.size() / 3; t++)
+                std::fprintf(f, "f %u %u %u\n", m.triangles[3 * t] + 1, m.triangles[3 * t + 1] + 1, m.triangles[3 * t + 2] + 1);
+            std::fclose(f);
+            std::fprintf(stderr, "[shm3d_cli] isosurface phi = %g: %lld vertices, %lld triangles, %.3f ms on the device -> %s\n",
+                         (double)isoval, (long long)m.stats.n_vertices, (long long)m.stats.n_triangles, m.stats.ms_device,
+                         iso_output.c_str());
         }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "shm3d_cli: %s\n", e.what());
