@@ -441,10 +441,26 @@ def run_ours(args):
                                                  "projector": prof.ms_pcg_projector / args.steps,
                                                  "update": prof.ms_pcg_update / args.steps}},
                 "checksum": checksum}
+        if world == 1 and not args.no_cpu:
+            line["consumer_n3"] = consumer_leg(min(p.nx, 512))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+def consumer_leg(n):
+    """Row N3 (isosurface of the device-resident field) measured in a child process after the solver's own numbers are
+    in: a separate context, and nothing it does can take the main line down.  Not part of `value` / `e2e`."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_consumer.py"), "--n", str(n)],
+                           capture_output=True, text=True, timeout=600)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout or "no output")[-400:]}
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def main():

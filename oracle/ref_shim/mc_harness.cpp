@@ -21,27 +21,32 @@ const unsigned long long* ref_mc_table(void) { return MC::mc_internalMarching_cu
 // values: float[nx*ny*nz], index i + j*nx + k*nx*ny (what addNodeScalarQuantity stored after narrowing).
 // node_dim = {nx,ny,nz} as registered; bound_min/max = the glm::vec3 the grid was registered with.
 // world != 0 applies registerIsosurfaceAsMesh's transform; world == 0 returns MC's own lattice coordinates.
-// Call with vertices_out == NULL to get the counts only.
+// The mesh is kept until the next call; ref_isosurface_copy hands it out.
+static MC::mcMesh g_mesh;
+
 int ref_isosurface(const float* values, float isoval, const uint32_t* node_dim, const float* bound_min,
-                   const float* bound_max, int world, float* vertices_out, int64_t vertex_capacity, uint32_t* indices_out,
-                   int64_t index_capacity, int64_t* n_vertices, int64_t* n_indices) {
-    MC::mcMesh mesh;
-    MC::marching_cube(const_cast<float*>(values), isoval, node_dim[0], node_dim[1], node_dim[2], mesh);
-    *n_vertices = (int64_t)mesh.vertices.size();
-    *n_indices = (int64_t)mesh.indices.size();
-    if (!vertices_out) return 0;
-    if (*n_vertices > vertex_capacity || *n_indices > index_capacity) return 2;
+                   const float* bound_max, int world, int64_t* n_vertices, int64_t* n_indices) {
+    g_mesh = MC::mcMesh();
+    MC::marching_cube(const_cast<float*>(values), isoval, node_dim[0], node_dim[1], node_dim[2], g_mesh);
     if (world) {
         glm::vec3 boundMin{bound_min[0], bound_min[1], bound_min[2]}, boundMax{bound_max[0], bound_max[1], bound_max[2]};
         glm::uvec3 gridNodeDim{node_dim[0], node_dim[1], node_dim[2]};
         glm::uvec3 gridCellDim = gridNodeDim - 1u;
         glm::vec3 width = boundMax - boundMin;
         glm::vec3 scale = width / (glm::vec3(gridCellDim));
-        for (auto& p : mesh.vertices) p = glm::vec3{p.z, p.y, p.x} * scale + boundMin;
+        for (auto& p : g_mesh.vertices) p = glm::vec3{p.z, p.y, p.x} * scale + boundMin;
     }
-    for (size_t i = 0; i < mesh.vertices.size(); i++)
-        for (int a = 0; a < 3; a++) vertices_out[3 * i + a] = mesh.vertices[i][a];
-    if (!mesh.indices.empty()) std::memcpy(indices_out, mesh.indices.data(), mesh.indices.size() * sizeof(uint32_t));
+    *n_vertices = (int64_t)g_mesh.vertices.size();
+    *n_indices = (int64_t)g_mesh.indices.size();
+    return 0;
+}
+
+int ref_isosurface_copy(float* vertices_out, int64_t vertex_capacity, uint32_t* indices_out, int64_t index_capacity) {
+    if ((int64_t)g_mesh.vertices.size() > vertex_capacity || (int64_t)g_mesh.indices.size() > index_capacity) return 2;
+    for (size_t i = 0; i < g_mesh.vertices.size(); i++)
+        for (int a = 0; a < 3; a++) vertices_out[3 * i + a] = g_mesh.vertices[i][a];
+    if (!g_mesh.indices.empty()) std::memcpy(indices_out, g_mesh.indices.data(), g_mesh.indices.size() * sizeof(uint32_t));
+    g_mesh = MC::mcMesh();
     return 0;
 }
 }

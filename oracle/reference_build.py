@@ -179,7 +179,8 @@ def mc_lib():
     if _MC is None:
         L = C.CDLL(MC_LIB_PATH)
         fp, up, ip = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)
-        L.ref_isosurface.argtypes = [fp, C.c_float, up, fp, fp, C.c_int, fp, C.c_int64, up, C.c_int64, ip, ip]
+        L.ref_isosurface.argtypes = [fp, C.c_float, up, fp, fp, C.c_int, ip, ip]
+        L.ref_isosurface_copy.argtypes = [fp, C.c_int64, up, C.c_int64]
         L.ref_mc_table.restype = C.POINTER(C.c_uint64)
         _MC = L
     return _MC
@@ -202,12 +203,10 @@ def isosurface(values, isoval, dims, bound_min, bound_max, world=True):
     fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
     nv, ni = C.c_int64(), C.c_int64()
     L = mc_lib()
-    args = (v.ctypes.data_as(fp), np.float32(isoval), d.ctypes.data_as(up), bmin.ctypes.data_as(fp), bmax.ctypes.data_as(fp),
-            int(bool(world)))
-    L.ref_isosurface(*args, None, 0, None, 0, C.byref(nv), C.byref(ni))
+    L.ref_isosurface(v.ctypes.data_as(fp), np.float32(isoval), d.ctypes.data_as(up), bmin.ctypes.data_as(fp),
+                     bmax.ctypes.data_as(fp), int(bool(world)), C.byref(nv), C.byref(ni))
     verts = np.empty((nv.value, 3), dtype=np.float32)
     idx = np.empty(ni.value, dtype=np.uint32)
-    rc = L.ref_isosurface(*args, verts.ctypes.data_as(fp), nv.value, idx.ctypes.data_as(up), ni.value, C.byref(nv), C.byref(ni))
-    if rc != 0:
+    if L.ref_isosurface_copy(verts.ctypes.data_as(fp), nv.value, idx.ctypes.data_as(up), ni.value) != 0:
         raise RuntimeError("reference marching cubes: capacity")
     return verts, idx.reshape(-1, 3)
