@@ -30,8 +30,9 @@ __device__ const unsigned long long d_mc_table[256] = {
 #include "mc_table.inc"
 };
 
-constexpr int kLanesZ = 32;  // lattice Z (grid i, contiguous in memory) across the lanes of a warp
-constexpr int kRowsY = 8;    // warps per CTA: consecutive lattice Y (grid j)
+using mc::kLanesZ;
+using mc::kRowsY;
+using mc::kScanThreads;
 
 __device__ __forceinline__ void load_table(unsigned long long* s_tab) {
     for (int i = threadIdx.y * kLanesZ + threadIdx.x; i < 256; i += kLanesZ * kRowsY) s_tab[i] = d_mc_table[i];
@@ -43,8 +44,8 @@ __global__ void __launch_bounds__(kLanesZ* kRowsY)
                unsigned int* __restrict__ col_t) {
     __shared__ unsigned long long s_tab[256];
     load_table(s_tab);
-    const int z = blockIdx.x * kLanesZ + threadIdx.x, y = blockIdx.y * kRowsY + threadIdx.y;
-    if (z >= L.SZ - 1 || y >= L.SY - 1) return;
+    int y, z;
+    if (!mc::thread_column(L, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, y, z)) return;
     mc::CountVisitor cv{s_tab, y, z, 0u, 0u};
     mc::march_column(L, field, y, z, cv);
     const int c = mc::column_id(L, y, z);
@@ -52,21 +53,16 @@ __global__ void __launch_bounds__(kLanesZ* kRowsY)
     col_t[c] = cv.nt;
 }
 
-// one CTA: thread t owns the contiguous chunk [t*chunk, (t+1)*chunk) of the n column counts
-constexpr int kScanThreads = 1024;
+// one CTA: thread t owns a contiguous chunk of the n column counts (mc::scan_chunk)
 __global__ void __launch_bounds__(kScanThreads)
     k_mc_scan(const unsigned int* __restrict__ col_v, const unsigned int* __restrict__ col_t, int n,
               unsigned long long* __restrict__ voff, unsigned long long* __restrict__ toff) {
     __shared__ unsigned long long sv[kScanThreads], st[kScanThreads];
     const int t = threadIdx.x;
-    const int chunk = (n + kScanThreads - 1) / kScanThreads;
-    const long long b0 = (long long)t * chunk;
-    const int b = (int)(b0 < n ? b0 : n), e = (int)(b0 + chunk < n ? b0 + chunk : n);
-    unsigned long long a = 0, c = 0;
-    for (int i = b; i < e; i++) {
-        a += col_v[i];
-        c += col_t[i];
-    }
+    int b, e;
+    mc::scan_chunk(n, t, b, e);
+    unsigned long long a, c;
+    mc::scan_chunk_sum(col_v, col_t, b, e, a, c);
     sv[t] = a;
     st[t] = c;
     __syncthreads();
@@ -77,13 +73,7 @@ __global__ void __launch_bounds__(kScanThreads)
         st[t] += y;
         __syncthreads();
     }
-    unsigned long long pv = sv[t] - a, pt = st[t] - c;
-    for (int i = b; i < e; i++) {
-        voff[i] = pv;
-        toff[i] = pt;
-        pv += col_v[i];
-        pt += col_t[i];
-    }
+    mc::scan_chunk_write(col_v, col_t, b, e, sv[t] - a, st[t] - c, voff, toff);
     if (t == kScanThreads - 1) {
         voff[n] = sv[t];
         toff[n] = st[t];
@@ -93,8 +83,8 @@ __global__ void __launch_bounds__(kScanThreads)
 __global__ void __launch_bounds__(kLanesZ* kRowsY)
     k_mc_vertices(const Lattice L, const float* __restrict__ field, const unsigned long long* __restrict__ voff,
                   float* __restrict__ vertices, uint32_t* __restrict__ vkey) {
-    const int z = blockIdx.x * kLanesZ + threadIdx.x, y = blockIdx.y * kRowsY + threadIdx.y;
-    if (z >= L.SZ - 1 || y >= L.SY - 1) return;
+    int y, z;
+    if (!mc::thread_column(L, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, y, z)) return;
     const int c = mc::column_id(L, y, z);
     const unsigned long long v0 = voff[c];
     if (voff[c + 1] == v0) return;  // this column creates nothing: no need to read it again
@@ -108,8 +98,8 @@ __global__ void __launch_bounds__(kLanesZ* kRowsY)
                    uint32_t* __restrict__ triangles) {
     __shared__ unsigned long long s_tab[256];
     load_table(s_tab);
-    const int z = blockIdx.x * kLanesZ + threadIdx.x, y = blockIdx.y * kRowsY + threadIdx.y;
-    if (z >= L.SZ - 1 || y >= L.SY - 1) return;
+    int y, z;
+    if (!mc::thread_column(L, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, y, z)) return;
     const int c = mc::column_id(L, y, z);
     const unsigned long long t0 = toff[c];
     if (toff[c + 1] == t0) return;
@@ -194,7 +184,9 @@ IsoResult IsoSurface::extract(cudaStream_t s, int nx, int ny, int nz, const floa
     col_t_.alloc((size_t)nc);
     voff_.alloc((size_t)nc + 1);
     toff_.alloc((size_t)nc + 1);
-    const dim3 block(kLanesZ, kRowsY), grid((unsigned)((L.SZ - 1 + kLanesZ - 1) / kLanesZ), (unsigned)((L.SY - 1 + kRowsY - 1) / kRowsY));
+    unsigned gx, gy;
+    mc::launch_grid(L, gx, gy);
+    const dim3 block(kLanesZ, kRowsY), grid(gx, gy);
     if (grid.y > 65535u) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: ny too large");
     IsoResult res;
     SHM3D_CUDA_CHECK(cudaEventRecord(ev0_, s));

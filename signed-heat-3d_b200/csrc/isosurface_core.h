@@ -192,6 +192,48 @@ MC_HD void march_column(const Lattice& L, const float* __restrict__ field, int y
     }
 }
 
+// ---- launch geometry and the chunked scan, shared with the host emulation ------------------------------------------
+constexpr int kLanesZ = 32;        // lattice Z (grid i, contiguous in memory) across the lanes of a warp
+constexpr int kRowsY = 8;          // warps per CTA: consecutive lattice Y (grid j)
+constexpr int kScanThreads = 1024; // the one CTA of the scan kernel
+
+MC_HD void launch_grid(const Lattice& L, unsigned& gx, unsigned& gy) {
+    gx = (unsigned)((L.SZ - 1 + kLanesZ - 1) / kLanesZ);
+    gy = (unsigned)((L.SY - 1 + kRowsY - 1) / kRowsY);
+}
+// the column thread (tx,ty) of CTA (bx,by) works on; false = idle thread
+MC_HD bool thread_column(const Lattice& L, unsigned bx, unsigned by, unsigned tx, unsigned ty, int& y, int& z) {
+    z = (int)(bx * kLanesZ + tx);
+    y = (int)(by * kRowsY + ty);
+    return z < L.SZ - 1 && y < L.SY - 1;
+}
+// scan thread t owns the contiguous chunk [b,e) of the n column counts
+MC_HD void scan_chunk(int n, int t, int& b, int& e) {
+    const int chunk = (n + kScanThreads - 1) / kScanThreads;
+    const long long b0 = (long long)t * chunk;
+    b = (int)(b0 < n ? b0 : n);
+    e = (int)(b0 + chunk < n ? b0 + chunk : n);
+}
+MC_HD void scan_chunk_sum(const unsigned* col_v, const unsigned* col_t, int b, int e, unsigned long long& sv,
+                          unsigned long long& st) {
+    sv = 0;
+    st = 0;
+    for (int i = b; i < e; i++) {
+        sv += col_v[i];
+        st += col_t[i];
+    }
+}
+// pv / pt: sum of all chunks before this one
+MC_HD void scan_chunk_write(const unsigned* col_v, const unsigned* col_t, int b, int e, unsigned long long pv,
+                            unsigned long long pt, unsigned long long* voff, unsigned long long* toff) {
+    for (int i = b; i < e; i++) {
+        voff[i] = pv;
+        toff[i] = pt;
+        pv += col_v[i];
+        pt += col_t[i];
+    }
+}
+
 // ---- the three visitors ------------------------------------------------------------------------------------------
 struct CountVisitor {  // pass 1: how many vertices this column creates, how many triangles it emits
     const unsigned long long* table;

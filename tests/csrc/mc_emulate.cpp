@@ -1,9 +1,10 @@
 // mc_emulate.cpp -- TEST INFRASTRUCTURE.  Runs the device logic of row N3 (signed-heat-3d_b200/csrc/isosurface_core.h
 // and the product's case table, the very files the CUDA kernels are built from) on the host, one "thread" after the
-// other: count per column -> exclusive scan -> vertices -> triangles, exactly the structure of isosurface.cu.  Lets
+// other, over the kernels' own launch geometry: count -> chunked scan -> vertices -> triangles, as in isosurface.cu.  Lets
 // the CPU test-suite compare the kernels' arithmetic and index logic with the reference's marching-cubes library
-// bit for bit; the launch geometry and the device scan are what only the GPU tests cover.
-// Built by tests/test_isosurface.py with g++ -ffp-contract=off.  Never loaded by the product.
+// bit for bit, including the thread -> column mapping and the chunking of the scan; what remains for the GPU tests is
+// the execution itself (barriers, memory staging, launches).
+// Built by tests/test_row_n3_isosurface.py with g++ -ffp-contract=off.  Never loaded by the product.
 #include <cstdint>
 #include <vector>
 
@@ -20,38 +21,83 @@ extern "C" int mc_emulate(const float* field, int nx, int ny, int nz, float isov
                           int64_t triangle_capacity, int64_t* n_vertices, int64_t* n_triangles) {
     Lattice L = make_lattice(nx, ny, nz, isoval, bound_min, bound_max);
     const int nc = L.ncols();
-    std::vector<unsigned long long> voff(nc + 1, 0), toff(nc + 1, 0);
-    for (int z = 0; z < L.SZ - 1; z++)
-        for (int y = 0; y < L.SY - 1; y++) {
-            CountVisitor cv{kTable, y, z, 0u, 0u};
-            march_column(L, field, y, z, cv);
-            voff[column_id(L, y, z) + 1] = cv.nv;
-            toff[column_id(L, y, z) + 1] = cv.nt;
+    unsigned gx, gy;
+    launch_grid(L, gx, gy);
+    // every (CTA, thread) of the kernels' launch geometry, CTAs in a scrambled order: nothing may depend on the order
+    // in which CTAs run
+    auto for_each_thread = [&](auto&& body) {
+        const unsigned nb = gx * gy;
+        for (unsigned i = 0; i < nb; i++) {
+            const unsigned blk = (unsigned)(((unsigned long long)i * 7919ull + 13ull) % nb);
+            const unsigned b = (nb % 7919u == 0) ? i : blk, bx = b % gx, by = b / gx;
+            for (unsigned ty = 0; ty < (unsigned)kRowsY; ty++)
+                for (unsigned tx = 0; tx < (unsigned)kLanesZ; tx++) {
+                    int y, z;
+                    if (thread_column(L, bx, by, tx, ty, y, z)) body(y, z);
+                }
         }
-    for (int c = 0; c < nc; c++) {
-        voff[c + 1] += voff[c];
-        toff[c + 1] += toff[c];
+    };
+    // k_mc_count
+    std::vector<unsigned> col_v(nc, 0xdeadbeefu), col_t(nc, 0xdeadbeefu);
+    for_each_thread([&](int y, int z) {
+        CountVisitor cv{kTable, y, z, 0u, 0u};
+        march_column(L, field, y, z, cv);
+        col_v[column_id(L, y, z)] = cv.nv;
+        col_t[column_id(L, y, z)] = cv.nt;
+    });
+    // k_mc_scan: phase 1 (chunk sums), the CTA-wide inclusive scan, phase 2 (chunk writes)
+    std::vector<unsigned long long> voff(nc + 1, ~0ull), toff(nc + 1, ~0ull), sv(kScanThreads), st(kScanThreads), a(kScanThreads),
+        c(kScanThreads);
+    for (int t = 0; t < kScanThreads; t++) {
+        int b, e;
+        scan_chunk(nc, t, b, e);
+        scan_chunk_sum(col_v.data(), col_t.data(), b, e, a[t], c[t]);
+        sv[t] = a[t];
+        st[t] = c[t];
     }
+    for (int off = 1; off < kScanThreads; off <<= 1) {
+        std::vector<unsigned long long> x(kScanThreads), y(kScanThreads);
+        for (int t = 0; t < kScanThreads; t++) {
+            x[t] = t >= off ? sv[t - off] : 0ull;
+            y[t] = t >= off ? st[t - off] : 0ull;
+        }
+        for (int t = 0; t < kScanThreads; t++) {
+            sv[t] += x[t];
+            st[t] += y[t];
+        }
+    }
+    for (int t = kScanThreads - 1; t >= 0; t--) {
+        int b, e;
+        scan_chunk(nc, t, b, e);
+        scan_chunk_write(col_v.data(), col_t.data(), b, e, sv[t] - a[t], st[t] - c[t], voff.data(), toff.data());
+    }
+    voff[nc] = sv[kScanThreads - 1];
+    toff[nc] = st[kScanThreads - 1];
+    for (int i = 0; i < nc; i++)  // the scan the kernels rely on: exclusive, complete, monotone
+        if (voff[i + 1] != voff[i] + col_v[i] || toff[i + 1] != toff[i] + col_t[i]) return 5;
+    if (voff[0] != 0 || toff[0] != 0) return 5;
     *n_vertices = (int64_t)voff[nc];
     *n_triangles = (int64_t)toff[nc];
     if (!vertices) return 0;
     if (*n_vertices > vertex_capacity || *n_triangles > triangle_capacity) return 2;
     std::vector<uint32_t> vkey(voff[nc] + 1);
-    // columns in a scrambled order: nothing may depend on the order in which the "threads" run
-    for (int pass = 0; pass < 2; pass++)
-        for (int i = 0; i < nc; i++) {
-            int c = (int)(((long long)i * 7919 + 13) % nc);
-            if (nc % 7919 == 0) c = i;
-            int z = c / (L.SY - 1), y = c % (L.SY - 1);
-            if (pass == 0) {
-                VertexVisitor vv{&L, y, z, voff[c], vertices, vkey.data()};
-                march_column(L, field, y, z, vv);
-                if (vv.v != voff[c + 1]) return 3;
-            } else {
-                TriangleVisitor tv{&L, kTable, voff.data(), vkey.data(), y, z, toff[c], triangles};
-                march_column(L, field, y, z, tv);
-                if (tv.t != toff[c + 1]) return 4;
-            }
-        }
+    int bad = 0;
+    // k_mc_vertices
+    for_each_thread([&](int y, int z) {
+        const int col = column_id(L, y, z);
+        if (voff[col + 1] == voff[col]) return;
+        VertexVisitor vv{&L, y, z, voff[col], vertices, vkey.data()};
+        march_column(L, field, y, z, vv);
+        if (vv.v != voff[col + 1]) bad = 3;
+    });
+    // k_mc_triangles
+    for_each_thread([&](int y, int z) {
+        const int col = column_id(L, y, z);
+        if (toff[col + 1] == toff[col]) return;
+        TriangleVisitor tv{&L, kTable, voff.data(), vkey.data(), y, z, toff[col], triangles};
+        march_column(L, field, y, z, tv);
+        if (tv.t != toff[col + 1]) bad = 4;
+    });
+    if (bad) return bad;
     return 0;
 }

@@ -4,7 +4,7 @@
 CPU: the numpy restatement against the reference's own library (oracle/_ref/libshm_mc_ref.so, compiled from the
 vendored header) and the golden fixture; the product's case table against the header and against its intrinsic
 properties; the DEVICE LOGIC (isosurface_core.h, the file the kernels are built from) run thread-by-thread on the host
-(tests/csrc/mc_emulate.cpp) against the oracle -- everything but launch geometry and the device scan.
+(tests/csrc/mc_emulate.cpp) over the kernels' own launch geometry and scan chunking, against the oracle.
 GPU: the kernels through the C ABI against the oracle -- bit-identical vertices, numbering and triangle order."""
 import ctypes as C
 import os
@@ -146,7 +146,7 @@ def test_device_logic_on_the_host_equals_oracle(emulator, name, n, iso):
 
 def test_device_logic_non_cubic_and_degenerate(emulator):
     rng = np.random.default_rng(11)
-    for dims in ((9, 14, 6), (2, 2, 2), (2, 17, 3), (31, 2, 5)):          # (nx, ny, nz)
+    for dims in ((9, 14, 6), (2, 2, 2), (2, 17, 3), (31, 2, 5), (70, 33, 41), (34, 35, 3)):          # (nx, ny, nz)
         phi = rng.standard_normal(dims[0] * dims[1] * dims[2])
         Vo, To = o.marching_cubes(phi, 0.0, dims, BMIN, BMAX)
         Ve, Te = emulator(phi, 0.0, dims, BMIN, BMAX)
