@@ -204,3 +204,31 @@ def test_intrinsic_flips_recover_the_planar_delaunay_triangulation():
     areas0, _, d0 = shm3d.debug_tufted_weights(P3, D.simplices.astype(np.int64))
     assert d0["flips"] > 0                               # the flips across the boundary fold
     assert (np.abs(areas - areas0) / ref.max()).max() < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------- GPU: config[2]
+@pytest.mark.gpu
+def test_gpu_point_overload_with_tufted_weights_matches_oracle(gpu_ctx):
+    """BASELINE config[2] (data/bunny.pc, point overload) with the row-N1 weights instead of the surrogate: at 32^3 against
+    the fp64 oracle fed the same weights (tolerance of the north star: 1e-4 relative L2), then the 256^3 configuration
+    through the class mirror with its automatic weights."""
+    from oracle import shm_oracle as o
+    d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
+    P, N = d["P"], d["N"]
+    areas, h, _ = shm3d.point_weights(P, N)
+    c = P.mean(axis=0)
+    r = np.sqrt(((P - c) ** 2).sum(axis=1)).max()
+    ref = o.compute_distance(P, N, areas, h, c, r, hCoef=1, scrub_nonfinite=False)
+    solver = shm3d.SignedHeatGridSolver(context=gpu_ctx)
+    phi = np.array(solver.computeDistancePoints(P, N, options=shm3d.SignedHeat3DOptions(hCoef=1)))   # weights: N1
+    assert np.linalg.norm(phi - ref) / np.linalg.norm(ref) < 1e-4
+    phi = solver.computeDistancePoints(P, N, options=shm3d.SignedHeat3DOptions(hCoef=4))
+    p, st = solver.params, solver.stats
+    assert p.nx == 256 and np.isfinite(phi).all() and abs(p.lambda_ - 1.0 / h) < 1e-9 / h
+    g = o.Grid(p.nx, p.ny, p.nz, np.array(p.bbox_min), p.cell)
+    v = o.evaluate_function(g, np.asarray(phi), P)
+    assert abs((areas * v).sum() / areas.sum()) < 1e-5                  # the shift (:216-217), area-weighted with the N1 areas
+    src, _, _ = shm3d.debug_constraints(p, P)
+    assert len(src) == st.m_constraints
+    assert np.abs(v[src] + st.shift).max() < 2e-4 * np.abs(phi).max()   # pinned cells interpolate to the common level
+    assert phi[0] > 0 and phi[-1] > 0 and o.evaluate_function(g, np.asarray(phi), c[None, :])[0] < 0
