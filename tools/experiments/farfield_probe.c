@@ -1,7 +1,8 @@
 // farfield_probe.c -- EXPERIMENT (round-2 preparation, CPU only): how accurate are Steps 1-2 if source clusters that are
 // far from a node in units of the kernel's footprint are replaced by a few equivalent sources?
 // X(x) = sum_s w_s exp(-lam r)/r.  Clusters: contiguous ranges of <= 32 Morton-sorted sources with centre c, radius rho.
-// Per node: d0 = min over clusters of max(R - rho, 0); clusters with (R - rho) - d0 > tau/lam are culled (as in k_sum);
+// Per node: d0 = min over clusters of (R + rho) >= the nearest-source distance; clusters with (R - rho) - d0 > tau/lam are
+// culled (k_sum's safe rule without its brick slack: dropped terms are < e^-tau of the leading one);
 // a kept cluster is "admissible" if lam*rho^2 / max(R - rho, 1e-30) < eps, and is then evaluated through its
 // n_eq equivalent sources instead of its members.  With cl_gadm != NULL the rule is g >= cl_gadm[c] instead (a per-cluster
 // admissible distance tabulated beforehand from the cluster's own equivalent-source error).
@@ -24,8 +25,7 @@ void farfield_eval(int64_t n_nodes, const double* nodes, int64_t n_cl, const int
         double d0 = 1e300;
         for (int64_t c = 0; c < n_cl; c++) {
             double dx = x - cl_centre[3 * c], dy = y - cl_centre[3 * c + 1], dz = z - cl_centre[3 * c + 2];
-            double g = sqrt(dx * dx + dy * dy + dz * dz) - cl_rho[c];
-            if (g < 0) g = 0;
+            double g = sqrt(dx * dx + dy * dy + dz * dz) + cl_rho[c];  // upper bound of the nearest-source distance
             if (g < d0) d0 = g;
         }
         double ax = 0, ay = 0, az = 0, S = 0;
