@@ -16,7 +16,8 @@ def pytest_configure(config):
 
 # GPU tests written after round 1's GPU minutes were spent run last (first outing = the round-end run), so that under
 # `-x` a surprise there cannot hide the results of the tests already validated on the B200.
-RUN_LAST = ("test_row_n3_isosurface.py", "test_gpu_point_overload_with_tufted_weights_matches_oracle")
+RUN_LAST = ("test_row_n3_isosurface.py", "test_cli_contour_and_export",
+            "test_gpu_point_overload_with_tufted_weights_matches_oracle")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -96,3 +96,24 @@ def test_cli_fast_flag(tmp_path):
     ref = o.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
     phi = np.load(out).ravel()
     assert np.linalg.norm(phi - ref) / np.linalg.norm(ref) < 1e-4
+
+
+@pytest.mark.gpu
+def test_cli_contour_and_export(tmp_path):
+    """The GUI's Contour + "Export isosurface" buttons (src/main.cpp:116-128, :160-190) as flags: the OBJ holds the mesh
+    the reference's consumer would extract from the phi the same run wrote."""
+    z, F = load_golden("bunny_small")
+    path = str(tmp_path / "bunny_small.obj")
+    out, iso = str(tmp_path / "phi.npy"), str(tmp_path / "iso.obj")
+    write_obj(path, z["V"], F)
+    r = subprocess.run([CLI, path, "--grid", "--h", "1", "-o", out, "--isoval", "0.25", "--iso-out", iso],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "isosurface phi = 0.25" in r.stderr
+    phi = np.load(out)
+    g = o.Grid(32, 32, 32, z["h1_bmin"], float(z["h1_cell"]))
+    Vo, To = o.marching_cubes(phi.ravel(), 0.25, (32, 32, 32), *o.grid_bounds_f32(g))
+    V = np.array([[float(t) for t in ln.split()[1:]] for ln in open(iso) if ln.startswith("v ")], dtype=np.float32)
+    T = np.array([[int(t) - 1 for t in ln.split()[1:]] for ln in open(iso) if ln.startswith("f ")], dtype=np.uint32)
+    # %.9g round-trips float32; the grid origin comes from the CLI's own host set-up (equal to the fixture's to ~1 ulp of double)
+    assert np.array_equal(T, To) and V.shape == Vo.shape and np.abs(V - Vo).max() < 1e-5
