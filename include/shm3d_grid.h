@@ -163,8 +163,9 @@ int shm3d_prepare_points(const double* P, int64_t nP, double h, double tCoef, do
  * (src/signed_heat_grid_solver.cpp:149-151,165) -- computed from positions + normals by restating that pipeline:
  * kNN(k_neighbors <= 0: 30), tangent-plane local Delaunay 1-rings (deps/geometry-central/src/pointcloud/
  * local_triangulation.cpp:10-210), the triangle soup of all local triangles, intrinsic mollification, the tufted cover
- * (src/surface/tufted_laplacian.cpp:39-121) and intrinsic Delaunay flips (src/surface/simple_idt.cpp).  geometry-central
- * itself cannot be built here, so the restatement is checked by invariants only (tests/test_point_weights.py).
+ * (src/surface/tufted_laplacian.cpp:39-121) and intrinsic Delaunay flips (src/surface/simple_idt.cpp).  Equal to
+ * geometry-central's own code (its sources compiled for the tests, oracle/_ref/libshm_gc_ref.so) to <= 1e-12 relative on
+ * areas and h (tests/test_point_weights.py).
  * Optional diagnostics: number of flips, smallest edge cotan weight after the flips (>= -1e-6 = intrinsically
  * Delaunay), total cover area before the flips (= sum of areas_out).  Host only; no device work. */
 int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_neighbors, double* areas_out,

@@ -1,0 +1,45 @@
+// gc_harness.cpp -- TEST INFRASTRUCTURE.  C entry point around geometry-central's OWN point-cloud pipeline, compiled from
+// where its sources lie under /root/reference/deps/geometry-central (recipe: oracle/Makefile -> oracle/_ref/libshm_gc_ref.so)
+// against oracle/ref_shim/eigen_stub, a stand-in for Eigen's *interface* only (Eigen itself is fetched by
+// geometry-central's configure step and is absent from this image).  The calls below are the ones the reference makes
+// for the point-cloud overload (src/main.cpp:277-285, src/signed_heat_grid_solver.cpp:149-151,165): none of the code
+// they execute touches a matrix, so every geometry-central line on the path -- kNN (nanoflann), tangent coordinates,
+// buildLocalTriangulations, the triangle-soup SurfaceMesh, mollifyIntrinsic, buildIntrinsicTuftedCover, flipToDelaunay,
+// vertexDualAreas -- and the reference's own meanEdgeLength (src/signed_heat_3d.cpp:51-60) run as written.
+// Pins row N1 (shm3d_point_weights).
+#include <cstdint>
+#include <string>
+
+#include "signed_heat_3d.h"
+
+namespace {
+std::string g_err;
+}
+
+extern "C" {
+
+const char* gcref_last_error(void) { return g_err.c_str(); }
+
+int gcref_point_weights(const double* P, const double* N, int64_t nP, double* areas_out, double* h_out,
+                        int64_t* n_faces_out, int64_t* n_edges_out) {
+    try {
+        pointcloud::PointCloud cloud((size_t)nP);                       // main.cpp:277
+        pointcloud::PointData<Vector3> pointPositions(cloud), pointNormals(cloud);
+        for (int64_t i = 0; i < nP; i++) {
+            pointPositions[(size_t)i] = Vector3{P[3 * i], P[3 * i + 1], P[3 * i + 2]};
+            pointNormals[(size_t)i] = Vector3{N[3 * i], N[3 * i + 1], N[3 * i + 2]};
+        }
+        pointcloud::PointPositionNormalGeometry pointGeom(cloud, pointPositions, pointNormals);  // main.cpp:284-285
+        pointGeom.requireTuftedTriangulation();                          // src/signed_heat_grid_solver.cpp:149
+        pointGeom.tuftedGeom->requireVertexDualAreas();                  // :150
+        *h_out = meanEdgeLength(*(pointGeom.tuftedGeom));                // :151
+        for (int64_t i = 0; i < nP; i++) areas_out[i] = pointGeom.tuftedGeom->vertexDualAreas[(size_t)i];  // :165
+        if (n_faces_out) *n_faces_out = (int64_t)pointGeom.tuftedMesh->nFaces();
+        if (n_edges_out) *n_edges_out = (int64_t)pointGeom.tuftedMesh->nEdges();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+}

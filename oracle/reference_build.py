@@ -26,6 +26,9 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libshm_ref.so")
 ADAPTER_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_adapter.so")
 # the marching-cubes routine of the reference's downstream consumer (row N3): polyscope's vendored MarchingCube/MC.h + glm
 MC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_mc_ref.so")
+# geometry-central's own point-cloud pipeline (row N1), compiled from the reference's vendored sources against an Eigen
+# interface stub (oracle/ref_shim/eigen_stub)
+GC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_gc_ref.so")
 REF_ROOT = "/root/reference"
 _LIB = None
 
@@ -37,7 +40,8 @@ def build(force: bool = False) -> bool:
     """(Re)build oracle/_ref/libshm_ref.so when the reference tree is present; returns whether the library exists."""
     if os.path.isdir(os.path.join(REF_ROOT, "src")) and (force or not os.path.exists(LIB_PATH)
                                                          or not os.path.exists(ADAPTER_LIB_PATH)
-                                                         or not os.path.exists(MC_LIB_PATH)):
+                                                         or not os.path.exists(MC_LIB_PATH)
+                                                         or not os.path.exists(GC_LIB_PATH)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return os.path.exists(LIB_PATH)
 
@@ -210,3 +214,33 @@ def isosurface(values, isoval, dims, bound_min, bound_max, world=True):
     if L.ref_isosurface_copy(verts.ctypes.data_as(fp), nv.value, idx.ctypes.data_as(up), ni.value) != 0:
         raise RuntimeError("reference marching cubes: capacity")
     return verts, idx.reshape(-1, 3)
+
+
+# ------------------------------------------------------------------------------------------------ row N1: point weights
+_GC = None
+
+
+def gc_available() -> bool:
+    return os.path.exists(GC_LIB_PATH)
+
+
+def gc_point_weights(P, normals):
+    """What the reference reads from geometry-central for the point-cloud overload (src/main.cpp:277-285,
+    src/signed_heat_grid_solver.cpp:149-151,165), run through geometry-central's own sources: returns
+    (vertexDualAreas[nP], meanEdgeLength(tuftedGeom), n_faces, n_edges of the tufted mesh)."""
+    global _GC
+    if _GC is None:
+        L = C.CDLL(GC_LIB_PATH)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+        L.gcref_point_weights.argtypes = [dp, dp, C.c_int64, dp, dp, ip, ip]
+        L.gcref_last_error.restype = C.c_char_p
+        _GC = L
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    Nn = np.ascontiguousarray(normals, dtype=np.float64)
+    areas = np.empty(len(P))
+    h = C.c_double()
+    nf, ne = C.c_int64(), C.c_int64()
+    rc = _GC.gcref_point_weights(_dp(P), _dp(Nn), len(P), _dp(areas), C.byref(h), C.byref(nf), C.byref(ne))
+    if rc != 0:
+        raise RuntimeError("geometry-central: " + _GC.gcref_last_error().decode())
+    return areas, h.value, nf.value, ne.value

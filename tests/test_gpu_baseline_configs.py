@@ -1,8 +1,9 @@
 """GPU tests at the BASELINE.json configuration sizes.
 
 config[1] knot.obj 128^3     : against the fp64 oracle (C loop + projected CG, tests/golden/make_golden_large.py)
-config[2] bunny.pc 256^3     : point overload; size-independent properties (the tufted-cover weights are row N1 -- the
-                               test uses the CLI's stated surrogate: uniform area h^2, h = mean nearest-neighbour distance)
+config[2] bunny.pc 256^3     : point overload; size-independent properties, here with caller-supplied weights (uniform area
+                               h^2, h = mean nearest-neighbour distance); with the row-N1 tufted-cover weights:
+                               tests/test_point_weights.py::test_gpu_point_overload_with_tufted_weights_matches_oracle
 config[3] SprayBottle 512^3  : lambda*r up to 580 (fp32 range stress); properties
 config[4] 1e5-triangle sphere 512^3 : the bench workload; analytic distance in a band, constraint / shift identities
 """
@@ -50,7 +51,7 @@ def test_config1_knot_128_matches_oracle(gpu_ctx):
 def test_config2_bunny_point_cloud_256(gpu_ctx):
     d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
     P, N = d["P"], d["N"]
-    # surrogate weights (same rule as tools/shm3d_cli.cpp): h = mean nearest-neighbour distance, area = h^2
+    # caller-supplied weights: h = mean nearest-neighbour distance, area = h^2
     d2 = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
     np.fill_diagonal(d2, np.inf)
     h = float(np.sqrt(d2.min(axis=1)).mean())

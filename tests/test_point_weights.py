@@ -1,8 +1,11 @@
 """CPU tests of the point-cloud source weights (row N1: geometry-central's tufted-cover pipeline restated in
-csrc/point_weights.cpp).  geometry-central cannot be built here, so the checks are: tangent-plane local Delaunay rings
-against scipy's Delaunay triangulation, invariants of the cover (closed manifold, area preserved by the intrinsic
-flips, intrinsically Delaunay at the end), closed forms on sampled spheres, and the bunny point cloud (= the vertices
-of data/bunny_small.obj) against that mesh's own mean edge length."""
+csrc/point_weights.cpp).  Pinned to geometry-central's OWN sources: oracle/_ref/libshm_gc_ref.so is its point-cloud /
+tufted-cover code compiled from the reference tree against an Eigen interface stub (oracle/Makefile), called exactly as
+the reference calls it; the product must reproduce its vertex dual areas and mean edge length to rounding (live where the
+library exists, and through the committed fixture tests/golden/point_weights_gc.npz everywhere).  Independent checks:
+tangent-plane local Delaunay rings against scipy's Delaunay triangulation, invariants of the cover (closed manifold, area
+preserved by the intrinsic flips, intrinsically Delaunay at the end), closed forms on sampled spheres, and the bunny point
+cloud (= the vertices of data/bunny_small.obj) against that mesh's own mean edge length."""
 import os
 import sys
 
@@ -14,6 +17,59 @@ import shm3d
 from conftest import GOLDEN, ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def golden_clouds():
+    """the clouds of tests/golden/make_golden_point_weights.py"""
+    d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
+    yield "bunny_pc", d["P"], d["N"]
+    rng = np.random.default_rng(3)
+    P = rng.standard_normal((3000, 3))
+    P /= np.linalg.norm(P, axis=1, keepdims=True)
+    yield "random_sphere_3000", P, P.copy()
+    u, v = rng.uniform(0, 2 * np.pi, 4000), rng.uniform(0, 2 * np.pi, 4000)
+    P = np.stack([(2 + 0.7 * np.cos(v)) * np.cos(u), (2 + 0.7 * np.cos(v)) * np.sin(u), 0.7 * np.sin(v)], axis=1)
+    N = np.stack([np.cos(v) * np.cos(u), np.cos(v) * np.sin(u), np.sin(v)], axis=1)
+    yield "random_torus_4000", P, N
+
+
+def test_weights_equal_geometry_central_golden():
+    """vertexDualAreas and meanEdgeLength(tuftedGeom) as geometry-central's own code computes them (fixture)."""
+    g = np.load(os.path.join(GOLDEN, "point_weights_gc.npz"))
+    for name, P, N in golden_clouds():
+        areas, h, n_tris, diag = shm3d.point_weights(P, N, diagnostics=True)
+        assert abs(h - float(g[name + "_h"])) < 1e-12 * h
+        assert np.abs(areas - g[name + "_areas"]).max() < 1e-11 * areas.max()
+        nf, ne = g[name + "_faces_edges"]
+        assert 2 * n_tris == nf and 3 * n_tris == ne          # the cover doubles the soup; closed: E = 3F/2
+
+
+def test_weights_equal_geometry_central_live():
+    """Same comparison against the library itself on clouds the fixture does not hold: lattice ties (cocircular points),
+    a jittered plane with boundary, the knot's vertices with averaged face normals."""
+    from oracle import reference_build as rb
+    if not (rb.build() and rb.gc_available()):
+        pytest.skip("no oracle/_ref/libshm_gc_ref.so")
+    from conftest import load_golden
+    rng = np.random.default_rng(7)
+    gx, gy = np.meshgrid(np.arange(30.0), np.arange(30.0))
+    lattice = np.stack([gx.ravel(), gy.ravel(), np.zeros(900)], axis=1)
+    up = np.tile([0.0, 0.0, 1.0], (900, 1))
+    z, F = load_golden("knot")
+    V = z["V"]
+    Nk = np.zeros_like(V)
+    for f in F:
+        n = np.cross(V[f[1]] - V[f[0]], V[f[2]] - V[f[0]])
+        for v in f:
+            Nk[v] += n
+    Nk /= np.linalg.norm(Nk, axis=1, keepdims=True)
+    for name, P, N in (("lattice", lattice, up), ("jittered", lattice + 1e-3 * rng.standard_normal(lattice.shape), up),
+                       ("knot", V, Nk)):
+        a_ref, h_ref, nf, ne = rb.gc_point_weights(P, N)
+        a, h, n_tris = shm3d.point_weights(P, N)
+        assert abs(h - h_ref) < 1e-12 * h_ref, name
+        assert np.abs(a - a_ref).max() < 1e-10 * a_ref.max(), name
+        assert 2 * n_tris == nf, name
 
 
 def fib_points(n):
