@@ -98,6 +98,7 @@ class Matrix {
     Matrix<Scalar, Dynamic, Dynamic> adjoint() const { return Matrix<Scalar, Dynamic, Dynamic>(); }
     Matrix<Scalar, Dynamic, Dynamic> inverse() const { return Matrix<Scalar, Dynamic, Dynamic>(); }
     Matrix<Scalar, Dynamic, Dynamic> asDiagonal() const { return Matrix<Scalar, Dynamic, Dynamic>(); }
+    Matrix conjugate() const { return Matrix(); }
     Matrix cwiseAbs() const { return Matrix(); }
     Matrix cwiseInverse() const { return Matrix(); }
     Matrix array() const { return Matrix(); }
@@ -348,6 +349,37 @@ template <typename S, int O, typename I>
 SparseMatrix<S, O, I> operator-(const SparseMatrix<S, O, I>&, const SparseMatrix<S, O, I>&) { return SparseMatrix<S, O, I>(); }
 template <typename S, int O, typename I>
 SparseMatrix<S, O, I> operator-(const SparseMatrix<S, O, I>&) { return SparseMatrix<S, O, I>(); }
+
+// sparse direct solvers: declared so that geometry-central's solver wrappers compile; never run on the oracle's path
+template <typename T>
+struct COLAMDOrdering {};
+template <typename T>
+struct AMDOrdering {};
+template <typename T>
+struct NaturalOrdering {};
+template <typename MatrixType>
+class SparseSolverStub {
+  public:
+    typedef typename MatrixType::Scalar Scalar;
+    SparseSolverStub() {}
+    explicit SparseSolverStub(const MatrixType&) { shm_stub_unreachable("sparse factorisation"); }
+    void compute(const MatrixType&) { shm_stub_unreachable("sparse factorisation"); }
+    void analyzePattern(const MatrixType&) { shm_stub_unreachable("sparse factorisation"); }
+    void factorize(const MatrixType&) { shm_stub_unreachable("sparse factorisation"); }
+    template <typename B>
+    Matrix<Scalar, Dynamic, 1> solve(const B&) const { shm_stub_unreachable("sparse solve"); }
+    ComputationInfo info() const { return Success; }
+    Index rank() const { return 0; }
+    void setPivotThreshold(double) {}
+};
+template <typename MatrixType, int UpLo = Lower, typename Ordering = AMDOrdering<int>>
+class SimplicialLDLT : public SparseSolverStub<MatrixType> {};
+template <typename MatrixType, int UpLo = Lower, typename Ordering = AMDOrdering<int>>
+class SimplicialLLT : public SparseSolverStub<MatrixType> {};
+template <typename MatrixType, typename Ordering = COLAMDOrdering<int>>
+class SparseLU : public SparseSolverStub<MatrixType> {};
+template <typename MatrixType, typename Ordering = COLAMDOrdering<int>>
+class SparseQR : public SparseSolverStub<MatrixType> {};
 
 template <typename MatrixType>
 class JacobiSVD {

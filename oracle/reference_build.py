@@ -29,6 +29,8 @@ MC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_mc_ref.so")
 # geometry-central's own point-cloud pipeline (row N1), compiled from the reference's vendored sources against an Eigen
 # interface stub (oracle/ref_shim/eigen_stub)
 GC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_gc_ref.so")
+# the product's drop-in TU compiled against the REAL geometry-central sources (Eigen / polyscope stubbed); needs a GPU
+ADAPTER_GC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_adapter_gc.so")
 REF_ROOT = "/root/reference"
 _LIB = None
 
@@ -41,7 +43,8 @@ def build(force: bool = False) -> bool:
     if os.path.isdir(os.path.join(REF_ROOT, "src")) and (force or not os.path.exists(LIB_PATH)
                                                          or not os.path.exists(ADAPTER_LIB_PATH)
                                                          or not os.path.exists(MC_LIB_PATH)
-                                                         or not os.path.exists(GC_LIB_PATH)):
+                                                         or not os.path.exists(GC_LIB_PATH)
+                                                         or not os.path.exists(ADAPTER_GC_LIB_PATH)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return os.path.exists(LIB_PATH)
 
@@ -244,3 +247,55 @@ def gc_point_weights(P, normals):
     if rc != 0:
         raise RuntimeError("geometry-central: " + _GC.gcref_last_error().decode())
     return areas, h.value, nf.value, ne.value
+
+
+# ------------------------------------------------------------- the drop-in TU behind the real geometry-central (GPU)
+_GCAD = None
+
+
+def _gcad():
+    global _GCAD
+    if _GCAD is None:
+        L = C.CDLL(ADAPTER_GC_LIB_PATH)
+        dp, ip, fp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_float)
+        L.gcad_compute_distance_mesh.argtypes = [dp, C.c_int64, ip, ip, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int,
+                                                 dp, C.c_int64, ip, fp]
+        L.gcad_compute_distance_points.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, dp,
+                                                   C.c_int64, ip, fp]
+        L.gcad_last_error.restype = C.c_char_p
+        _GCAD = L
+    return _GCAD
+
+
+def gc_adapter_compute_distance_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False):
+    """adapter/signed_heat_grid_solver_b200.cpp driven like src/main.cpp drives the class, on a real geometry-central
+    SurfaceMesh / VertexPositionGeometry.  Returns (phi, dims, bbox)."""
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    fv, fo = _flatten(faces)
+    nx = int(2 * 2.0 ** (hCoef + 3))
+    phi = np.empty(nx ** 3)
+    dims = np.zeros(3, dtype=np.int64)
+    bbox = np.zeros(6, dtype=np.float32)
+    L = _gcad()
+    rc = L.gcad_compute_distance_mesh(_dp(V), len(V), _ip(fv), _ip(fo), len(fo) - 1, tCoef, hCoef, scale, int(fast), _dp(phi),
+                                      phi.size, _ip(dims), bbox.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != 0:
+        raise RuntimeError("adapter (geometry-central): " + L.gcad_last_error().decode())
+    return phi, dims, bbox
+
+
+def gc_adapter_compute_distance_points(P, normals, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False):
+    """The point-cloud overload of the drop-in TU on a real PointPositionNormalGeometry (geometry-central's own
+    tufted-cover weights)."""
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    Nn = np.ascontiguousarray(normals, dtype=np.float64)
+    nx = int(2 * 2.0 ** (hCoef + 3))
+    phi = np.empty(nx ** 3)
+    dims = np.zeros(3, dtype=np.int64)
+    bbox = np.zeros(6, dtype=np.float32)
+    L = _gcad()
+    rc = L.gcad_compute_distance_points(_dp(P), _dp(Nn), len(P), tCoef, hCoef, scale, int(fast), _dp(phi), phi.size,
+                                        _ip(dims), bbox.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != 0:
+        raise RuntimeError("adapter (geometry-central): " + L.gcad_last_error().decode())
+    return phi, dims, bbox
