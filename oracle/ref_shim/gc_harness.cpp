@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <string>
 
+#include "geometrycentral/surface/surface_mesh_factories.h"
 #include "signed_heat_3d.h"
 
 namespace {
@@ -36,6 +37,50 @@ int gcref_point_weights(const double* P, const double* N, int64_t nP, double* ar
         for (int64_t i = 0; i < nP; i++) areas_out[i] = pointGeom.tuftedGeom->vertexDualAreas[(size_t)i];  // :165
         if (n_faces_out) *n_faces_out = (int64_t)pointGeom.tuftedMesh->nFaces();
         if (n_edges_out) *n_edges_out = (int64_t)pointGeom.tuftedMesh->nEdges();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// The mesh-side host quantities of the grid solver through the REAL geometry-central containers (rows a4-a6):
+// centroid / radius / meanEdgeLength / setFaceVectorAreas of the reference's src/signed_heat_3d.cpp, and the face
+// barycentres in mesh.faces() order with f.adjacentVertices() (src/signed_heat_grid_solver.cpp:498-503) -- the order that
+// decides which source pins a cell.  Mesh built as src/main.cpp does for OBJ input (makeSurfaceMeshAndGeometry on the
+// polygon soup: general, possibly non-manifold SurfaceMesh).
+int gcref_mesh_sources(const double* V, int64_t nV, const int64_t* face_vertices, const int64_t* face_offsets, int64_t nF,
+                       double* centroid_out, double* radius_out, double* h_out, double* area_out, double* normal_out,
+                       double* bary_out, int64_t* n_edges_out) {
+    try {
+        std::vector<std::vector<size_t>> polygons((size_t)nF);
+        for (int64_t f = 0; f < nF; f++)
+            polygons[(size_t)f].assign(face_vertices + face_offsets[f], face_vertices + face_offsets[f + 1]);
+        std::vector<Vector3> pos((size_t)nV);
+        for (int64_t i = 0; i < nV; i++) pos[(size_t)i] = Vector3{V[3 * i], V[3 * i + 1], V[3 * i + 2]};
+        std::unique_ptr<SurfaceMesh> mesh;
+        std::unique_ptr<VertexPositionGeometry> geometry;
+        std::tie(mesh, geometry) = makeSurfaceMeshAndGeometry(polygons, pos);
+        Vector3 c = centroid(*geometry);
+        for (int a = 0; a < 3; a++) centroid_out[a] = c[a];
+        *radius_out = radius(*geometry, c);
+        *h_out = meanEdgeLength(*geometry);
+        FaceData<double> areas;
+        FaceData<Vector3> normals;
+        setFaceVectorAreas(*geometry, areas, normals);
+        size_t i = 0;
+        for (Face f : mesh->faces()) {
+            Vector3 b = {0, 0, 0};
+            for (Vertex v : f.adjacentVertices()) b += geometry->vertexPositions[v];
+            b /= f.degree();
+            area_out[i] = areas[f];
+            for (int a = 0; a < 3; a++) {
+                normal_out[3 * i + a] = normals[f][a];
+                bary_out[3 * i + a] = b[a];
+            }
+            i++;
+        }
+        if (n_edges_out) *n_edges_out = (int64_t)mesh->nEdges();
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -227,26 +227,50 @@ def gc_available() -> bool:
     return os.path.exists(GC_LIB_PATH)
 
 
-def gc_point_weights(P, normals):
-    """What the reference reads from geometry-central for the point-cloud overload (src/main.cpp:277-285,
-    src/signed_heat_grid_solver.cpp:149-151,165), run through geometry-central's own sources: returns
-    (vertexDualAreas[nP], meanEdgeLength(tuftedGeom), n_faces, n_edges of the tufted mesh)."""
+def _gc():
     global _GC
     if _GC is None:
         L = C.CDLL(GC_LIB_PATH)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
         L.gcref_point_weights.argtypes = [dp, dp, C.c_int64, dp, dp, ip, ip]
+        L.gcref_mesh_sources.argtypes = [dp, C.c_int64, ip, ip, C.c_int64, dp, dp, dp, dp, dp, dp, ip]
         L.gcref_last_error.restype = C.c_char_p
         _GC = L
+    return _GC
+
+
+def gc_point_weights(P, normals):
+    """What the reference reads from geometry-central for the point-cloud overload (src/main.cpp:277-285,
+    src/signed_heat_grid_solver.cpp:149-151,165), run through geometry-central's own sources: returns
+    (vertexDualAreas[nP], meanEdgeLength(tuftedGeom), n_faces, n_edges of the tufted mesh)."""
+    L = _gc()
     P = np.ascontiguousarray(P, dtype=np.float64)
     Nn = np.ascontiguousarray(normals, dtype=np.float64)
     areas = np.empty(len(P))
     h = C.c_double()
     nf, ne = C.c_int64(), C.c_int64()
-    rc = _GC.gcref_point_weights(_dp(P), _dp(Nn), len(P), _dp(areas), C.byref(h), C.byref(nf), C.byref(ne))
+    rc = L.gcref_point_weights(_dp(P), _dp(Nn), len(P), _dp(areas), C.byref(h), C.byref(nf), C.byref(ne))
     if rc != 0:
-        raise RuntimeError("geometry-central: " + _GC.gcref_last_error().decode())
+        raise RuntimeError("geometry-central: " + L.gcref_last_error().decode())
     return areas, h.value, nf.value, ne.value
+
+
+def gc_mesh_sources(V, faces):
+    """Rows a4-a6 through the real geometry-central containers + the reference's src/signed_heat_3d.cpp: centroid, radius,
+    mean edge length, and per face (in mesh.faces() order) area, unit normal, barycentre."""
+    L = _gc()
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    fv, fo = _flatten(faces)
+    nF = len(fo) - 1
+    c = np.zeros(3)
+    r, h = C.c_double(), C.c_double()
+    area, nrm, bary = np.zeros(nF), np.zeros((nF, 3)), np.zeros((nF, 3))
+    ne = C.c_int64()
+    rc = L.gcref_mesh_sources(_dp(V), len(V), _ip(fv), _ip(fo), nF, _dp(c), C.byref(r), C.byref(h), _dp(area), _dp(nrm),
+                              _dp(bary), C.byref(ne))
+    if rc != 0:
+        raise RuntimeError("geometry-central: " + L.gcref_last_error().decode())
+    return dict(centroid=c, radius=r.value, h=h.value, area=area, nrm=nrm, pos=bary, n_edges=ne.value)
 
 
 # ------------------------------------------------------------- the drop-in TU behind the real geometry-central (GPU)

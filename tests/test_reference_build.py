@@ -109,6 +109,31 @@ def test_product_host_half_equals_reference_source():
         assert list(info["dims"]) == [p.nx, p.ny, p.nz]
 
 
+def test_shim_containers_equal_the_real_geometry_central():
+    """The shim that stands in for geometry-central when the reference's two translation units are compiled restates its
+    mesh containers (face order, vertex order inside a face, unique edges).  Here the REAL geometry-central sources
+    (oracle/_ref/libshm_gc_ref.so: SurfaceMesh built with makeSurfaceMeshAndGeometry as src/main.cpp does, the reference's
+    src/signed_heat_3d.cpp on top) give the same host quantities -- to the last bit or two for the shim, to rounding for the oracle
+    and the product -- on triangle, polygon and non-trivial meshes; in particular the source order, which decides the
+    constraint rows, is the input order."""
+    import shm3d
+    if not rb.gc_available():
+        pytest.skip("no oracle/_ref/libshm_gc_ref.so")
+    for name in ("bunny_small", "polygon-bear", "knot"):
+        z, F = load_golden(name)
+        g = rb.gc_mesh_sources(z["V"], F)
+        sh = rb.mesh_scalars(z["V"], F)                      # the shim + the same reference source
+        assert sh["h"] == g["h"] and sh["radius"] == g["radius"] and np.array_equal(sh["centroid"], g["centroid"])
+        assert np.array_equal(sh["area"], g["area"]) and np.abs(sh["nrm"] - g["nrm"]).max() < 1e-15   # last-bit: N / |N|
+        s = o.mesh_sources(z["V"], F)                        # the oracle
+        assert np.array_equal(s["pos"], g["pos"])
+        assert abs(s["h"] - g["h"]) < 1e-13 * g["h"] and np.abs(s["area"] - g["area"]).max() < 1e-13
+        assert np.abs(s["nrm"] - g["nrm"]).max() < 1e-13
+        p, pos, nrm, area, h = shm3d.prepare_mesh(z["V"], F, hCoef=0)   # the product
+        assert np.array_equal(pos, g["pos"]) and abs(h - g["h"]) < 1e-13 * g["h"]
+        assert np.abs(area - g["area"]).max() < 1e-12 and np.abs(nrm - g["nrm"]).max() < 1e-11
+
+
 def test_knot_golden_is_the_reference_sources_output():
     """data/knot.obj at hCoef 1 (30 504 faces x 32^3 nodes, ~1 min single-threaded: the reference recomputes every
     barycentre per pair): the committed golden field the GPU tests compare against is the reference's own result."""
