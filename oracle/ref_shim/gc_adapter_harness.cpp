@@ -1,7 +1,9 @@
-// gc_adapter_harness.cpp -- TEST INFRASTRUCTURE.  The product's drop-in translation unit
-// (adapter/signed_heat_grid_solver_b200.cpp) compiled against the reference's unchanged headers AND the real
-// geometry-central headers / sources from the reference tree (Eigen: interface stub; polyscope: registerVolumeGrid stub
-// over the real glm), driven the way src/main.cpp drives the class: real SurfaceMesh + VertexPositionGeometry built with
+// gc_adapter_harness.cpp -- TEST INFRASTRUCTURE.  A SignedHeatGridSolver translation unit compiled against the
+// reference's unchanged headers AND the real geometry-central headers / sources from the reference tree (Eigen: stub,
+// see ref_shim/eigen_stub; polyscope: registerVolumeGrid stub over the real glm), driven the way src/main.cpp drives the
+// class.  Linked twice (oracle/Makefile): with the PRODUCT's drop-in TU adapter/signed_heat_grid_solver_b200.cpp ->
+// _ref/libshm_adapter_gc.so (needs a GPU), and with the REFERENCE's own src/signed_heat_grid_solver.cpp ->
+// _ref/libshm_ref_gc.so (CPU; the KKT solve goes to the callback set with gcad_set_solver).  Inputs: real SurfaceMesh + VertexPositionGeometry built with
 // makeSurfaceMeshAndGeometry (main.cpp:269-271 via readSurfaceMesh), real PointCloud + PointPositionNormalGeometry
 // (main.cpp:277-285, geometry-central's own tufted-cover weights).  oracle/Makefile -> _ref/libshm_adapter_gc.so.
 #include <cstdint>
@@ -43,6 +45,10 @@ int finish(const Vector<double>& phi, double* phi_out, int64_t capacity, int64_t
 extern "C" {
 
 const char* gcad_last_error(void) { return g_err.c_str(); }
+
+// Used when this harness wraps the REFERENCE's own src/signed_heat_grid_solver.cpp (oracle/_ref/libshm_ref_gc.so): the
+// routine the Eigen stub's SparseLU hands the assembled KKT system to (scipy SuperLU in the tests).  Unused by the adapter.
+void gcad_set_solver(Eigen::shm_stub_solve_fn fn) { Eigen::shm_stub_solver() = fn; }
 
 int gcad_compute_distance_mesh(const double* V, int64_t nV, const int64_t* face_vertices, const int64_t* face_offsets,
                                int64_t nF, double tCoef, double hCoef, double scale, int fast, double* phi_out,

@@ -31,6 +31,9 @@ MC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_mc_ref.so")
 GC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_gc_ref.so")
 # the product's drop-in TU compiled against the REAL geometry-central sources (Eigen / polyscope stubbed); needs a GPU
 ADAPTER_GC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_adapter_gc.so")
+# the REFERENCE's own src/signed_heat_grid_solver.cpp + src/signed_heat_3d.cpp against the real geometry-central sources
+# (Eigen: stub with a working sparse container, SparseLU -> callback; polyscope: stub) -- CPU
+REF_GC_LIB_PATH = os.path.join(_HERE, "_ref", "libshm_ref_gc.so")
 REF_ROOT = "/root/reference"
 _LIB = None
 
@@ -44,7 +47,8 @@ def build(force: bool = False) -> bool:
                                                          or not os.path.exists(ADAPTER_LIB_PATH)
                                                          or not os.path.exists(MC_LIB_PATH)
                                                          or not os.path.exists(GC_LIB_PATH)
-                                                         or not os.path.exists(ADAPTER_GC_LIB_PATH)):
+                                                         or not os.path.exists(ADAPTER_GC_LIB_PATH)
+                                                         or not os.path.exists(REF_GC_LIB_PATH)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return os.path.exists(LIB_PATH)
 
@@ -274,52 +278,85 @@ def gc_mesh_sources(V, faces):
 
 
 # ------------------------------------------------------------- the drop-in TU behind the real geometry-central (GPU)
-_GCAD = None
+_GCAD = {}
 
 
-def _gcad():
-    global _GCAD
-    if _GCAD is None:
-        L = C.CDLL(ADAPTER_GC_LIB_PATH)
+def _gcad(path=None):
+    path = path or ADAPTER_GC_LIB_PATH
+    if path not in _GCAD:
+        L = C.CDLL(path)
         dp, ip, fp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_float)
         L.gcad_compute_distance_mesh.argtypes = [dp, C.c_int64, ip, ip, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int,
                                                  dp, C.c_int64, ip, fp]
         L.gcad_compute_distance_points.argtypes = [dp, dp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int, dp,
                                                    C.c_int64, ip, fp]
+        L.gcad_set_solver.argtypes = [SOLVE_FN]
         L.gcad_last_error.restype = C.c_char_p
-        _GCAD = L
-    return _GCAD
+        _GCAD[path] = L
+    return _GCAD[path]
 
 
-def gc_adapter_compute_distance_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False):
-    """adapter/signed_heat_grid_solver_b200.cpp driven like src/main.cpp drives the class, on a real geometry-central
-    SurfaceMesh / VertexPositionGeometry.  Returns (phi, dims, bbox)."""
+def _gc_harness_mesh(path, what, V, faces, tCoef, hCoef, scale, fast, solver=None):
     V = np.ascontiguousarray(V, dtype=np.float64)
     fv, fo = _flatten(faces)
     nx = int(2 * 2.0 ** (hCoef + 3))
     phi = np.empty(nx ** 3)
     dims = np.zeros(3, dtype=np.int64)
     bbox = np.zeros(6, dtype=np.float32)
-    L = _gcad()
+    L = _gcad(path)
+    if solver is not None:
+        L.gcad_set_solver(solver.fn)
     rc = L.gcad_compute_distance_mesh(_dp(V), len(V), _ip(fv), _ip(fo), len(fo) - 1, tCoef, hCoef, scale, int(fast), _dp(phi),
                                       phi.size, _ip(dims), bbox.ctypes.data_as(C.POINTER(C.c_float)))
     if rc != 0:
-        raise RuntimeError("adapter (geometry-central): " + L.gcad_last_error().decode())
+        raise RuntimeError(what + ": " + L.gcad_last_error().decode())
     return phi, dims, bbox
 
 
-def gc_adapter_compute_distance_points(P, normals, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False):
-    """The point-cloud overload of the drop-in TU on a real PointPositionNormalGeometry (geometry-central's own
-    tufted-cover weights)."""
+def _gc_harness_points(path, what, P, normals, tCoef, hCoef, scale, fast, solver=None):
     P = np.ascontiguousarray(P, dtype=np.float64)
     Nn = np.ascontiguousarray(normals, dtype=np.float64)
     nx = int(2 * 2.0 ** (hCoef + 3))
     phi = np.empty(nx ** 3)
     dims = np.zeros(3, dtype=np.int64)
     bbox = np.zeros(6, dtype=np.float32)
-    L = _gcad()
+    L = _gcad(path)
+    if solver is not None:
+        L.gcad_set_solver(solver.fn)
     rc = L.gcad_compute_distance_points(_dp(P), _dp(Nn), len(P), tCoef, hCoef, scale, int(fast), _dp(phi), phi.size,
                                         _ip(dims), bbox.ctypes.data_as(C.POINTER(C.c_float)))
     if rc != 0:
-        raise RuntimeError("adapter (geometry-central): " + L.gcad_last_error().decode())
+        raise RuntimeError(what + ": " + L.gcad_last_error().decode())
     return phi, dims, bbox
+
+
+def gc_adapter_compute_distance_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False):
+    """adapter/signed_heat_grid_solver_b200.cpp driven like src/main.cpp drives the class, on a real geometry-central
+    SurfaceMesh / VertexPositionGeometry (GPU).  Returns (phi, dims, bbox)."""
+    return _gc_harness_mesh(ADAPTER_GC_LIB_PATH, "adapter (geometry-central)", V, faces, tCoef, hCoef, scale, fast)
+
+
+def gc_adapter_compute_distance_points(P, normals, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False):
+    """The point-cloud overload of the drop-in TU on a real PointPositionNormalGeometry (geometry-central's own
+    tufted-cover weights; GPU)."""
+    return _gc_harness_points(ADAPTER_GC_LIB_PATH, "adapter (geometry-central)", P, normals, tCoef, hCoef, scale, fast)
+
+
+def ref_gc_available() -> bool:
+    return os.path.exists(REF_GC_LIB_PATH)
+
+
+def ref_gc_compute_distance_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False, return_info=False):
+    """The REFERENCE's computeDistance(VertexPositionGeometry&) on the real geometry-central (CPU; KKT solve: scipy
+    SuperLU through the Eigen stub's SparseLU)."""
+    s = _Solver()
+    phi, dims, bbox = _gc_harness_mesh(REF_GC_LIB_PATH, "reference (geometry-central)", V, faces, tCoef, hCoef, scale, fast, s)
+    return (phi, dict(dims=dims, bbox=bbox, solves=s.calls)) if return_info else phi
+
+
+def ref_gc_compute_distance_points(P, normals, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False, return_info=False):
+    """The REFERENCE's computeDistance(PointPositionNormalGeometry&) end to end on the real geometry-central: its own
+    tufted-cover weights, its own grid solver."""
+    s = _Solver()
+    phi, dims, bbox = _gc_harness_points(REF_GC_LIB_PATH, "reference (geometry-central)", P, normals, tCoef, hCoef, scale, fast, s)
+    return (phi, dict(dims=dims, bbox=bbox, solves=s.calls)) if return_info else phi

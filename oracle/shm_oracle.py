@@ -11,9 +11,11 @@ has no tests or golden vectors for this path).  oracle/_ref/libshm_ref.so is src
 src/signed_heat_3d.cpp of the reference compiled unmodified against oracle/ref_shim (a stand-in for the slices of
 geometry-central / Eigen / polyscope they use: the real Eigen is fetched at configure time and absent here, SURVEY.md
 section 0 D7); tests/test_reference_build.py shows this restatement equal to it to ~1e-13 on phi (mesh, polygon,
-point-cloud and fastIntegration paths), with the identical KKT matrix and right-hand side.  NOT pinned: Eigen's
-SparseLU itself (the shim hands the assembled system to scipy SuperLU, the same solver used here) and
-geometry-central's own containers (restated in the shim).  Step 3 is also solved by an fp64 projected CG, which must
+point-cloud and fastIntegration paths), with the identical KKT matrix and right-hand side.  A second build links the
+same two files with geometry-central's REAL sources (oracle/_ref/libshm_ref_gc.so; only Eigen and polyscope stubbed) and
+gives the same fields, including the point-cloud overload end to end with geometry-central's own tufted-cover weights.
+NOT pinned: Eigen itself (its SparseLU: both builds hand the assembled system to scipy SuperLU, the same solver used
+here; its sparse assembly and vector arithmetic are restated in the stubs).  Step 3 is also solved by an fp64 projected CG, which must
 agree with the LU (tests/test_oracle.py).
 
 Nothing here reads /root/reference at run time except the helper readers when a test

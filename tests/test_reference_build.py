@@ -134,6 +134,46 @@ def test_shim_containers_equal_the_real_geometry_central():
         assert np.abs(area - g["area"]).max() < 1e-12 and np.abs(nrm - g["nrm"]).max() < 1e-11
 
 
+def test_reference_source_on_the_real_geometry_central():
+    """oracle/_ref/libshm_ref_gc.so: the reference's own src/signed_heat_grid_solver.cpp + src/signed_heat_3d.cpp linked
+    with geometry-central's REAL sources from the reference tree (mesh containers, point-cloud pipeline, solveSquare /
+    PositiveDefiniteSolver / horizontalStack / verticalStack) -- only Eigen (a stub with a working sparse container; its
+    SparseLU hands the system to scipy SuperLU) and polyscope's registerVolumeGrid are stand-ins -- driven like
+    src/main.cpp drives the class.  Same fields as the committed golden vectors, the shim build and the oracle: mesh,
+    polygon mesh, fastIntegration, and the point-cloud overload END TO END (geometry-central's own tufted-cover weights)."""
+    if not rb.ref_gc_available():
+        pytest.skip("no oracle/_ref/libshm_ref_gc.so")
+    z, F = load_golden("bunny_small")
+    phi, info = rb.ref_gc_compute_distance_mesh(z["V"], F, hCoef=0, return_info=True)
+    assert np.linalg.norm(phi - z["h0_phi"]) / np.linalg.norm(z["h0_phi"]) < 1e-12
+    assert np.abs(phi - rb.compute_distance_mesh(z["V"], F, hCoef=0)).max() < 1e-11
+    assert list(info["dims"]) == [16, 16, 16] and len(info["solves"]) == 1
+    K = info["solves"][0]["A"]                                   # the KKT matrix geometry-central's stacking produced
+    g = o.make_grid(z["centroid"], float(z["radius"]), hCoef=0)
+    s = o.mesh_sources(z["V"], F)
+    _, idx, w = o.constraints(g, s["pos"])
+    A = o.constraint_matrix(g, idx, w)
+    Lm = o.laplacian_matrix(g)
+    ref = sp.bmat([[Lm, A.T], [A, None]], format="csc")
+    assert K.shape == ref.shape and abs(K - ref).max() < 1e-12
+    phif = rb.ref_gc_compute_distance_mesh(z["V"], F, hCoef=0, fast=True)
+    assert np.abs(phif - o.compute_distance_mesh(z["V"], F, hCoef=0, fast=True)).max() < 1e-12
+    zb, Fb = load_golden("polygon-bear")
+    phib = rb.ref_gc_compute_distance_mesh(zb["V"], Fb, hCoef=0)
+    refb = o.compute_distance_mesh(zb["V"], Fb, hCoef=0)
+    assert np.linalg.norm(phib - refb) / np.linalg.norm(refb) < 1e-12
+    import os
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
+    P, N = d["P"], d["N"]
+    phip = rb.ref_gc_compute_distance_points(P, N, hCoef=0)
+    wts = np.load(os.path.join(GOLDEN, "point_weights_gc.npz"))
+    c = P.mean(axis=0)
+    r = np.sqrt(((P - c) ** 2).sum(axis=1)).max()
+    refp = o.compute_distance(P, N, wts["bunny_pc_areas"], float(wts["bunny_pc_h"]), c, r, hCoef=0, scrub_nonfinite=False)
+    assert np.linalg.norm(phip - refp) / np.linalg.norm(refp) < 1e-12
+
+
 def test_knot_golden_is_the_reference_sources_output():
     """data/knot.obj at hCoef 1 (30 504 faces x 32^3 nodes, ~1 min single-threaded: the reference recomputes every
     barycentre per pair): the committed golden field the GPU tests compare against is the reference's own result."""
