@@ -4,7 +4,8 @@ Golden point-cloud weights for row N1, made with geometry-central's OWN pipeline
 it for the point-cloud overload (src/main.cpp:277-285, src/signed_heat_grid_solver.cpp:149-151,165) -- run here, on the
 CPU box; the GPU box has no /root/reference.
 
-Inputs: data/bunny.pc (tests/golden/bunny_pc.npz) and two synthetic clouds built by the formulas below.
+Inputs: data/bunny.pc (tests/golden/bunny_pc.npz) and two synthetic clouds built by the formulas below.  Also stored: the
+reference's end-to-end signed distance for bunny.pc at 32^3 (its own weights + its own grid solver).
 
     python tests/golden/make_golden_point_weights.py     # writes point_weights_gc.npz next to this file
 """
@@ -40,6 +41,13 @@ def main():
         out[name + "_h"] = h
         out[name + "_faces_edges"] = np.array([nf, ne])
         print(name, len(P), "h", h, "faces", nf, "edges", ne, "area", areas.sum())
+    # BASELINE config[2] at 32^3, end to end through the reference: its own computeDistance(PointPositionNormalGeometry&)
+    # linked with the real geometry-central (oracle/_ref/libshm_ref_gc.so: own tufted-cover weights, own grid solver)
+    d = np.load(os.path.join(HERE, "bunny_pc.npz"))
+    phi, info = rb.ref_gc_compute_distance_points(d["P"], d["N"], hCoef=1, return_info=True)
+    out["bunny_pc_h1_phi"] = phi.astype(np.float64)
+    out["bunny_pc_h1_bbox"] = info["bbox"]
+    print("bunny_pc 32^3 reference phi", phi.min(), phi.max())
     np.savez_compressed(os.path.join(HERE, "point_weights_gc.npz"), **out)
 
 

@@ -278,6 +278,10 @@ def test_gpu_point_overload_with_tufted_weights_matches_oracle(gpu_ctx):
     solver = shm3d.SignedHeatGridSolver(context=gpu_ctx)
     phi = np.array(solver.computeDistancePoints(P, N, options=shm3d.SignedHeat3DOptions(hCoef=1)))   # weights: N1
     assert np.linalg.norm(phi - ref) / np.linalg.norm(ref) < 1e-4
+    # ... and against the reference's own end-to-end output (its grid solver linked with the real geometry-central,
+    # geometry-central's own weights; fixture made by tests/golden/make_golden_point_weights.py)
+    gold = np.load(os.path.join(GOLDEN, "point_weights_gc.npz"))["bunny_pc_h1_phi"]
+    assert np.linalg.norm(phi - gold) / np.linalg.norm(gold) < 1e-4
     phi = solver.computeDistancePoints(P, N, options=shm3d.SignedHeat3DOptions(hCoef=4))
     p, st = solver.params, solver.stats
     assert p.nx == 256 and np.isfinite(phi).all() and abs(p.lambda_ - 1.0 / h) < 1e-9 / h
