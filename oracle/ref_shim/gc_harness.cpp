@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <string>
 
+#include "geometrycentral/surface/meshio.h"
 #include "geometrycentral/surface/surface_mesh_factories.h"
 #include "signed_heat_3d.h"
 
@@ -81,6 +82,44 @@ int gcref_mesh_sources(const double* V, int64_t nV, const int64_t* face_vertices
             i++;
         }
         if (n_edges_out) *n_edges_out = (int64_t)mesh->nEdges();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// The input side of the path: geometry-central's own mesh reader as src/main.cpp:269 calls it (readSurfaceMesh ->
+// SimplePolygonMesh OBJ/PLY/... parser, stripUnusedVertices), then the same host quantities as gcref_mesh_sources.
+// Call with the output arrays NULL to get the counts.
+int gcref_read_mesh(const char* path, int64_t* nV_out, int64_t* nF_out, double* centroid_out, double* radius_out,
+                    double* h_out, double* area_out, double* normal_out, double* bary_out) {
+    try {
+        std::unique_ptr<SurfaceMesh> mesh;
+        std::unique_ptr<VertexPositionGeometry> geometry;
+        std::tie(mesh, geometry) = readSurfaceMesh(std::string(path));
+        *nV_out = (int64_t)mesh->nVertices();
+        *nF_out = (int64_t)mesh->nFaces();
+        Vector3 c = centroid(*geometry);
+        for (int a = 0; a < 3; a++) centroid_out[a] = c[a];
+        *radius_out = radius(*geometry, c);
+        *h_out = meanEdgeLength(*geometry);
+        if (!area_out) return 0;
+        FaceData<double> areas;
+        FaceData<Vector3> normals;
+        setFaceVectorAreas(*geometry, areas, normals);
+        size_t i = 0;
+        for (Face f : mesh->faces()) {
+            Vector3 b = {0, 0, 0};
+            for (Vertex v : f.adjacentVertices()) b += geometry->vertexPositions[v];
+            b /= f.degree();
+            area_out[i] = areas[f];
+            for (int a = 0; a < 3; a++) {
+                normal_out[3 * i + a] = normals[f][a];
+                bary_out[3 * i + a] = b[a];
+            }
+            i++;
+        }
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -238,9 +238,25 @@ def _gc():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
         L.gcref_point_weights.argtypes = [dp, dp, C.c_int64, dp, dp, ip, ip]
         L.gcref_mesh_sources.argtypes = [dp, C.c_int64, ip, ip, C.c_int64, dp, dp, dp, dp, dp, dp, ip]
+        L.gcref_read_mesh.argtypes = [C.c_char_p, ip, ip, dp, dp, dp, dp, dp, dp]
         L.gcref_last_error.restype = C.c_char_p
         _GC = L
     return _GC
+
+
+def gc_read_mesh(path):
+    """geometry-central's own readSurfaceMesh (src/main.cpp:269) + the host quantities of the grid solver on the result."""
+    L = _gc()
+    nV, nF = C.c_int64(), C.c_int64()
+    c = np.zeros(3)
+    r, h = C.c_double(), C.c_double()
+    if L.gcref_read_mesh(path.encode(), C.byref(nV), C.byref(nF), _dp(c), C.byref(r), C.byref(h), None, None, None) != 0:
+        raise RuntimeError("geometry-central: " + L.gcref_last_error().decode())
+    area, nrm, bary = np.zeros(nF.value), np.zeros((nF.value, 3)), np.zeros((nF.value, 3))
+    if L.gcref_read_mesh(path.encode(), C.byref(nV), C.byref(nF), _dp(c), C.byref(r), C.byref(h), _dp(area), _dp(nrm),
+                         _dp(bary)) != 0:
+        raise RuntimeError("geometry-central: " + L.gcref_last_error().decode())
+    return dict(n_vertices=nV.value, n_faces=nF.value, centroid=c, radius=r.value, h=h.value, area=area, nrm=nrm, pos=bary)
 
 
 def gc_point_weights(P, normals):

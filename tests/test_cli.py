@@ -48,6 +48,54 @@ def test_cli_dry_run_matches_oracle(tmp_path, name, hc):
     assert np.abs(np.array(d["bbox_min"]) - g.bmin).max() < 1e-12
 
 
+TRICKY_OBJ = """# comments, an unreferenced vertex, all four index syntaxes, a quad (no negative indices: the reference's loader has none)
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+v 5 5 5
+v 0.5 0.5 1
+vn 0 0 1
+vt 0.5 0.5
+f 1/1/1 2/1/1 3/1/1 4/1/1
+f 1//1 2//1 6//1
+f 2 3 6
+f 3/1 4/1 6/1
+f 4 1 6
+"""
+
+
+def test_cli_obj_reader_equals_geometry_central_readSurfaceMesh(tmp_path):
+    """The CLI restates geometry-central's OBJ loader; here the REAL loader (readSurfaceMesh as src/main.cpp:269 calls it:
+    SimplePolygonMesh parser + stripUnusedVertices, compiled from the reference tree into oracle/_ref/libshm_gc_ref.so)
+    reads the same files and the reference's own host code runs on the result."""
+    from oracle import reference_build as rb
+    if not (rb.build() and rb.gc_available()):
+        pytest.skip("no oracle/_ref/libshm_gc_ref.so")
+    paths = []
+    p = str(tmp_path / "tricky.obj")
+    with open(p, "w") as fh:
+        fh.write(TRICKY_OBJ)
+    paths.append(p)
+    for name in ("bunny_small", "polygon-bear"):
+        z, F = load_golden(name)
+        p = str(tmp_path / (name + ".obj"))
+        write_obj(p, z["V"], F, junk_vertices=2)
+        paths.append(p)
+    for name in ("SprayBottle", "knot", "chair", "rocker"):      # the reference's own sample files, where present
+        p = os.path.join("/root/reference/data", name + ".obj")
+        if os.path.exists(p):
+            paths.append(p)
+    for p in paths:
+        g = rb.gc_read_mesh(p)
+        r = subprocess.run([CLI, p, "--dry-run"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        d = json.loads(r.stdout)
+        assert d["vertices"] == g["n_vertices"] and d["sources"] == g["n_faces"], p
+        assert abs(d["h"] - g["h"]) < 1e-13 * g["h"], p
+        assert np.abs(np.array(d["bbox_min"]) - (g["centroid"] - 2.0 * g["radius"])).max() < 1e-12 * (1 + g["radius"]), p
+
+
 def test_cli_reads_pc_files(tmp_path):
     z, F = load_golden("bunny_small")
     s = o.mesh_sources(z["V"], F)
