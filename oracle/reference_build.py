@@ -49,7 +49,7 @@ def build(force: bool = False) -> bool:
                                                          or not os.path.exists(GC_LIB_PATH)
                                                          or not os.path.exists(ADAPTER_GC_LIB_PATH)
                                                          or not os.path.exists(REF_GC_LIB_PATH)):
-        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-j4", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return os.path.exists(LIB_PATH)
 
 
