@@ -567,7 +567,8 @@ def marching_cubes(values, isoval, dims, bound_min=None, bound_max=None):
         if (va < 0) == (vb < 0):
             return
         v = [f32(x), f32(y), f32(z)]
-        v[axis] = f32(v[axis] + f32(va / f32(va - vb)))
+        with np.errstate(invalid="ignore", over="ignore"):     # inf - inf etc. give NaN like the C arithmetic does
+            v[axis] = f32(v[axis] + f32(va / f32(va - vb)))
         edge_vertex[(x, y, z, axis)] = len(verts)
         verts.append(v)
 

@@ -163,6 +163,39 @@ def test_device_logic_non_cubic_and_degenerate(emulator):
     assert np.array_equal(To, Te) and np.array_equal(Vo, Ve, equal_nan=True)
 
 
+def test_device_logic_fuzz_against_the_reference_library(emulator):
+    """Seeded fuzz: small random grids with many exact ties (integer-valued fields, value == isoval, +-0), huge and tiny
+    magnitudes, infinities -- the device logic must agree with the reference's library bit for bit on all of them."""
+    if not (rb.build() and rb.mc_available()):
+        pytest.skip("no oracle/_ref/libshm_mc_ref.so")
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        dims = tuple(int(d) for d in rng.integers(2, 9, size=3))
+        n = dims[0] * dims[1] * dims[2]
+        kind = trial % 6
+        if kind == 0:
+            phi = rng.integers(-2, 3, size=n).astype(np.float64)            # ties with isoval 0 / 1
+        elif kind == 1:
+            phi = rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30)
+        elif kind == 2:
+            phi = np.where(rng.random(n) < 0.3, 0.0, rng.standard_normal(n)) * np.where(rng.random(n) < 0.5, 1.0, -1.0)  # +-0
+        elif kind == 3:
+            phi = rng.standard_normal(n)
+            phi[rng.integers(0, n, size=max(1, n // 10))] = np.inf
+        elif kind == 4:
+            phi = np.round(rng.standard_normal(n) * 4) / 4                   # quarter steps: ties with isoval 0.25
+        else:
+            phi = rng.standard_normal(n).astype(np.float32).astype(np.float64)
+        iso = float(rng.choice([0.0, 1.0, 0.25, -0.5, 1e-3]))
+        if dims[0] == dims[1] == dims[2]:                                    # the reference library assumes a cube (nx = ny = nz)
+            Vr, Tr = rb.isosurface(phi, iso, dims, BMIN, BMAX)
+        else:
+            Vr, Tr = o.marching_cubes(phi, iso, dims, BMIN, BMAX)
+        Ve, Te = emulator(phi, iso, dims, BMIN, BMAX)
+        assert np.array_equal(Tr, Te), (trial, dims, iso)
+        assert np.array_equal(Vr, Ve, equal_nan=True), (trial, dims, iso)
+
+
 def test_device_logic_equals_golden_isosurface_of_the_reference(emulator):
     z, _ = load_golden("bunny_small")
     gi = np.load(os.path.join(GOLDEN, "iso_bunny_small_h1.npz"))
