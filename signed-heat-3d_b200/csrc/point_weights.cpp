@@ -14,9 +14,13 @@
 // triangulation, total area preserved by the flips, the final cover intrinsically Delaunay, closed forms on sampled
 // spheres.  Any positive rescaling of all areas cancels in Steps 1-2 (normalisation) and in the shift (a weighted mean).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "../../include/shm3d_grid.h"
@@ -124,6 +128,25 @@ void local_ring(std::vector<V2> pts, std::vector<size_t>& ring, std::vector<char
     }
 }
 
+// contiguous chunks of [0,n) on the host threads; body(begin, end, chunk_index).  Results are assembled in chunk order,
+// so the output does not depend on the number of threads.
+template <typename Body>
+int parallel_chunks(int64_t n, Body body) {
+    unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (n < 4096) T = 1;
+    const int64_t chunk = (n + T - 1) / T;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; t++)
+        th.emplace_back([=, &body] { body(std::min(n, (int64_t)t * chunk), std::min(n, (int64_t)(t + 1) * chunk), (int)t); });
+    body(0, std::min(n, chunk), 0);
+    for (std::thread& x : th) x.join();
+    return (int)T;
+}
+int chunk_count(int64_t n) {
+    unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    return n < 4096 ? 1 : (int)T;
+}
+
 // exact k nearest neighbours (self excluded), ascending distance then index -- a uniform hash grid
 void knn_all(const double* P, int64_t n, int k, std::vector<int64_t>& nbr) {
     nbr.assign((size_t)n * k, -1);
@@ -139,43 +162,60 @@ void knn_all(const double* P, int64_t n, int k, std::vector<int64_t>& nbr) {
     auto cell_of = [&](const double* q, int c[3]) {
         for (int a = 0; a < 3; a++) c[a] = std::min(g - 1, std::max(0, (int)((q[a] - lo[a]) / cs)));
     };
-    std::vector<std::vector<int64_t>> bucket((size_t)g * g * g);
+    // points grouped by cell (counting sort), positions copied in that order: a cell's candidates are one contiguous run
+    const size_t n_cells = (size_t)g * g * g;
+    std::vector<int64_t> start(n_cells + 1, 0), order((size_t)n);
+    std::vector<int32_t> cell_id((size_t)n);
     for (int64_t i = 0; i < n; i++) {
         int c[3];
         cell_of(P + 3 * i, c);
-        bucket[(size_t)c[0] + (size_t)c[1] * g + (size_t)c[2] * g * g].push_back(i);
+        cell_id[(size_t)i] = (int32_t)((size_t)c[0] + (size_t)c[1] * g + (size_t)c[2] * g * g);
+        start[(size_t)cell_id[(size_t)i] + 1]++;
     }
-    std::vector<std::pair<double, int64_t>> cand;
-    for (int64_t i = 0; i < n; i++) {
-        int c[3];
-        cell_of(P + 3 * i, c);
-        cand.clear();
-        for (int ring = 0; ring <= g; ring++) {
-            for (int dz = -ring; dz <= ring; dz++)
-                for (int dy = -ring; dy <= ring; dy++)
-                    for (int dx = -ring; dx <= ring; dx++) {
-                        if (std::max({std::abs(dx), std::abs(dy), std::abs(dz)}) != ring) continue;
-                        const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
-                        if (x < 0 || y < 0 || z < 0 || x >= g || y >= g || z >= g) continue;
-                        for (int64_t j : bucket[(size_t)x + (size_t)y * g + (size_t)z * g * g]) {
-                            if (j == i) continue;
-                            double d = 0;
-                            for (int a = 0; a < 3; a++) {
-                                const double t = P[3 * i + a] - P[3 * j + a];
-                                d += t * t;
+    for (size_t c = 0; c < n_cells; c++) start[c + 1] += start[c];
+    {
+        std::vector<int64_t> fill(start.begin(), start.end() - 1);
+        for (int64_t i = 0; i < n; i++) order[(size_t)fill[(size_t)cell_id[(size_t)i]]++] = i;  // ascending index inside a cell
+    }
+    std::vector<double> Q((size_t)3 * n);
+    for (int64_t s = 0; s < n; s++)
+        for (int a = 0; a < 3; a++) Q[(size_t)3 * s + a] = P[3 * order[(size_t)s] + a];
+    parallel_chunks(n, [&](int64_t s_begin, int64_t s_end, int) {
+        std::vector<std::pair<double, int64_t>> cand;
+        for (int64_t s = s_begin; s < s_end; s++) {  // sorted order: neighbouring points share their candidate cells
+            const int64_t i = order[(size_t)s];
+            const double* qi = &Q[(size_t)3 * s];
+            int c[3];
+            cell_of(qi, c);
+            cand.clear();
+            for (int ring = 0; ring <= g; ring++) {
+                for (int dz = -ring; dz <= ring; dz++)
+                    for (int dy = -ring; dy <= ring; dy++)
+                        for (int dx = -ring; dx <= ring; dx++) {
+                            if (std::max({std::abs(dx), std::abs(dy), std::abs(dz)}) != ring) continue;
+                            const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+                            if (x < 0 || y < 0 || z < 0 || x >= g || y >= g || z >= g) continue;
+                            const size_t cell = (size_t)x + (size_t)y * g + (size_t)z * g * g;
+                            for (int64_t u = start[cell]; u < start[cell + 1]; u++) {
+                                if (u == s) continue;
+                                double d = 0;
+                                for (int a = 0; a < 3; a++) {
+                                    const double t = qi[a] - Q[(size_t)3 * u + a];
+                                    d += t * t;
+                                }
+                                cand.emplace_back(d, order[(size_t)u]);
                             }
-                            cand.emplace_back(d, j);
                         }
-                    }
-            if ((int)cand.size() >= k) {
-                std::nth_element(cand.begin(), cand.begin() + (k - 1), cand.end());
-                // everything in the rings searched so far that is closer than ring*cs is final
-                if (std::sqrt(cand[k - 1].first) <= ring * cs) break;
+                if ((int)cand.size() >= k) {
+                    std::nth_element(cand.begin(), cand.begin() + (k - 1), cand.end());
+                    // everything in the rings searched so far that is closer than ring*cs is final
+                    if (std::sqrt(cand[k - 1].first) <= ring * cs) break;
+                }
             }
+            std::partial_sort(cand.begin(), cand.begin() + k, cand.end());
+            for (int t = 0; t < k; t++) nbr[(size_t)i * k + t] = cand[t].second;
         }
-        std::sort(cand.begin(), cand.end());
-        for (int t = 0; t < k; t++) nbr[(size_t)i * k + t] = cand[t].second;
-    }
+    });
 }
 
 // ---------------------------------------------------------------- tufted cover + intrinsic Delaunay flips
@@ -397,15 +437,21 @@ int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_
     if ((int64_t)k + 1 > nP) return SHM3D_ERR_INVALID_ARG;  // "k+1 is greater than number of points" (knn.cpp:53)
     for (int64_t i = 0; i < 3 * nP; i++)
         if (!std::isfinite(P[i]) || !std::isfinite(N[i])) return SHM3D_ERR_NONFINITE;
+    const bool dbg = std::getenv("SHM3D_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     std::vector<int64_t> nbr;
     knn_all(P, nP, k, nbr);
+    if (dbg) std::fprintf(stderr, "[shm3d] point_weights: kNN %.3fs", now() - t0), t0 = now();
 
     // soup triangles (p, a, b) from every point's local triangulation
-    std::vector<int64_t> tris;
+    std::vector<std::vector<int64_t>> tris_of_chunk((size_t)chunk_count(nP));
+    parallel_chunks(nP, [&](int64_t p_begin, int64_t p_end, int chunk) {
+    std::vector<int64_t>& tris = tris_of_chunk[(size_t)chunk];
     std::vector<V2> pts((size_t)k);
     std::vector<size_t> ring;
     std::vector<char> tri_after;
-    for (int64_t p = 0; p < nP; p++) {
+    for (int64_t p = p_begin; p < p_end; p++) {
         const double* c = P + 3 * p;
         const double nl = std::sqrt(N[3 * p] * N[3 * p] + N[3 * p + 1] * N[3 * p + 1] + N[3 * p + 2] * N[3 * p + 2]);
         const double nrm[3] = {N[3 * p], N[3 * p + 1], N[3 * p + 2]};
@@ -434,7 +480,11 @@ int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_
                 tris.push_back(nbr[(size_t)p * k + ring[(i + 1) % ring.size()]]);
             }
     }
+    });
+    std::vector<int64_t> tris;  // chunks in point order: the soup is ordered by centre point, like the reference's
+    for (const std::vector<int64_t>& t : tris_of_chunk) tris.insert(tris.end(), t.begin(), t.end());
     const int64_t T = (int64_t)tris.size() / 3;
+    if (dbg) std::fprintf(stderr, "  local triangulations %.3fs", now() - t0), t0 = now();
     if (n_triangles_out) *n_triangles_out = T;
     for (int64_t i = 0; i < nP; i++) areas_out[i] = 0;
     if (T == 0) {
@@ -443,6 +493,7 @@ int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_
     }
     CoverStats cs;
     tufted_cover_weights(P, nP, tris, areas_out, h_out, cs);
+    if (dbg) std::fprintf(stderr, "  cover + flips %.3fs (%lld flips)\n", now() - t0, (long long)cs.flips);
     if (n_flips_out) *n_flips_out = cs.flips;
     if (min_cotan_out) *min_cotan_out = cs.min_cotan;
     if (area_before_out) *area_before_out = cs.area_before;
