@@ -245,27 +245,44 @@ void tufted_cover_weights(const double* P, int64_t nP, const std::vector<int64_t
     struct SoupEdge {
         int64_t v0;                 // tail of the first halfedge created on the edge (defines orientation = true)
         double len;
-        std::vector<int64_t> hes;   // front halfedges 3f + s in creation order h_1 .. h_n
+        size_t begin, count;        // its front halfedges 3f + s in creation order h_1 .. h_n: sorted[begin .. begin + count)
     };
     std::vector<SoupEdge> edges;
     std::vector<int64_t> he_edge((size_t)3 * T);
+    // halfedges ordered by (min vertex, max vertex, halfedge index): counting sort on the min vertex (ascending halfedge
+    // index inside a bucket by construction), then each small bucket by (max vertex, index)
+    std::vector<std::pair<std::pair<int64_t, int64_t>, int64_t>> sorted((size_t)3 * T);
     {
-        std::vector<std::pair<std::pair<int64_t, int64_t>, int64_t>> keyed((size_t)3 * T);
+        std::vector<int64_t> start((size_t)nP + 1, 0);
         for (int64_t h = 0; h < 3 * T; h++) {
             const int64_t f = h / 3, sl = h % 3, a = tris[3 * f + sl], b = tris[3 * f + (sl + 1) % 3];
-            keyed[h] = {{std::min(a, b), std::max(a, b)}, h};
+            start[(size_t)std::min(a, b) + 1]++;
         }
-        std::vector<std::pair<std::pair<int64_t, int64_t>, int64_t>> sorted = keyed;
-        std::sort(sorted.begin(), sorted.end());  // group by key; within a key ascending halfedge index = creation order
-        std::vector<int64_t> first_of_group;      // creation order of edges = order of their first halfedge
+        for (int64_t v = 0; v < nP; v++) start[(size_t)v + 1] += start[(size_t)v];
+        {
+            std::vector<int64_t> fill(start.begin(), start.end() - 1);
+            for (int64_t h = 0; h < 3 * T; h++) {
+                const int64_t f = h / 3, sl = h % 3, a = tris[3 * f + sl], b = tris[3 * f + (sl + 1) % 3];
+                sorted[(size_t)fill[(size_t)std::min(a, b)]++] = {{std::min(a, b), std::max(a, b)}, h};
+            }
+        }
+        parallel_chunks(nP, [&](int64_t v_begin, int64_t v_end, int) {
+            for (int64_t v = v_begin; v < v_end; v++)
+                std::sort(sorted.begin() + start[(size_t)v], sorted.begin() + start[(size_t)v + 1]);
+        });
+        // creation order of edges = order of their first (lowest) halfedge: mark it, then walk the halfedges in order
+        std::vector<int64_t> group_of_first((size_t)3 * T, -1);
         for (size_t i = 0; i < sorted.size();) {
             size_t j = i;
             while (j < sorted.size() && sorted[j].first == sorted[i].first) j++;
-            first_of_group.push_back((int64_t)i);
+            group_of_first[(size_t)sorted[i].second] = (int64_t)i;
             i = j;
         }
-        std::sort(first_of_group.begin(), first_of_group.end(),
-                  [&](int64_t x, int64_t y) { return sorted[x].second < sorted[y].second; });
+        std::vector<int64_t> first_of_group;
+        first_of_group.reserve((size_t)3 * T / 2 + 1);
+        for (int64_t h = 0; h < 3 * T; h++)
+            if (group_of_first[(size_t)h] >= 0) first_of_group.push_back(group_of_first[(size_t)h]);
+        edges.reserve(first_of_group.size());
         for (int64_t gi : first_of_group) {
             SoupEdge e;
             const int64_t h1 = sorted[gi].second;
@@ -273,11 +290,13 @@ void tufted_cover_weights(const double* P, int64_t nP, const std::vector<int64_t
             const double* a = P + 3 * sorted[gi].first.first;
             const double* b = P + 3 * sorted[gi].first.second;
             e.len = std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+            e.begin = (size_t)gi;
+            e.count = 0;
             for (size_t i = (size_t)gi; i < sorted.size() && sorted[i].first == sorted[gi].first; i++) {
-                e.hes.push_back(sorted[i].second);
+                e.count++;
                 he_edge[sorted[i].second] = (int64_t)edges.size();
             }
-            edges.push_back(std::move(e));
+            edges.push_back(e);
         }
     }
     // ---- intrinsic mollification (intrinsic_mollification.cpp:7-38)
@@ -308,12 +327,13 @@ void tufted_cover_weights(const double* P, int64_t nP, const std::vector<int64_t
         }
     auto front_of = [&](int64_t soup_he) { return 6 * (soup_he / 3) + soup_he % 3; };
     auto other = [&](int64_t h) { return (h % 6) < 3 ? h + 3 : h - 3; };
+    std::vector<int64_t> F;
     for (const SoupEdge& e : edges) {
         // e.adjacentHalfedges(): h_1, then the sibling chain h_n, h_{n-1}, ..., h_2 (surface_mesh.cpp:187-203)
-        const size_t n = e.hes.size();
-        std::vector<int64_t> F(n);
-        F[0] = front_of(e.hes[0]);
-        for (size_t i = 1; i < n; i++) F[i] = front_of(e.hes[n - i]);
+        const size_t n = e.count;
+        F.resize(n);
+        F[0] = front_of(sorted[e.begin].second);
+        for (size_t i = 1; i < n; i++) F[i] = front_of(sorted[e.begin + n - i].second);
         // orientation(): front halfedge = (tail == tail of h_1); the inverted back copy has the opposite flag
         auto orient = [&](int64_t h) { return vert[h] == e.v0; };
         // tufted_laplacian.cpp:103-113
