@@ -165,7 +165,8 @@ int shm3d_prepare_points(const double* P, int64_t nP, double h, double tCoef, do
  * local_triangulation.cpp:10-210), the triangle soup of all local triangles, intrinsic mollification, the tufted cover
  * (src/surface/tufted_laplacian.cpp:39-121) and intrinsic Delaunay flips (src/surface/simple_idt.cpp).  Equal to
  * geometry-central's own code (its sources compiled for the tests, oracle/_ref/libshm_gc_ref.so) to <= 1e-12 relative on
- * areas and h (tests/test_point_weights.py).
+ * areas and h, degenerate inputs included: the kNN restates nanoflann's kd-tree (tie-breaking by visiting order), the
+ * in-circle test Eigen 3.3's determinant expression (tests/test_point_weights.py, tests/test_cli.py).
  * Optional diagnostics: number of flips, smallest edge cotan weight after the flips (>= -1e-6 = intrinsically
  * Delaunay), total cover area before the flips (= sum of areas_out).  Host only; no device work. */
 int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_neighbors, double* areas_out,

@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <string>
 
+#include "geometrycentral/pointcloud/local_triangulation.h"
 #include "geometrycentral/surface/meshio.h"
 #include "geometrycentral/surface/surface_mesh_factories.h"
 #include "signed_heat_3d.h"
@@ -120,6 +121,38 @@ int gcref_read_mesh(const char* path, int64_t* nV_out, int64_t* nF_out, double* 
             }
             i++;
         }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// Intermediate results of the same pipeline, for diagnosing differences: the k nearest neighbours of every point
+// (nanoflann order) and the triangle soup of all local triangulations (point_position_geometry.cpp:166-169).
+// neighbors_out: int64[nP][k]; tris_out: int64[capacity][3]; returns the number of soup triangles in *n_tris_out.
+int gcref_local_triangulations(const double* P, const double* N, int64_t nP, int64_t k, int64_t* neighbors_out,
+                               int64_t* tris_out, int64_t capacity, int64_t* n_tris_out) {
+    try {
+        pointcloud::PointCloud cloud((size_t)nP);
+        pointcloud::PointData<Vector3> pointPositions(cloud), pointNormals(cloud);
+        for (int64_t i = 0; i < nP; i++) {
+            pointPositions[(size_t)i] = Vector3{P[3 * i], P[3 * i + 1], P[3 * i + 2]};
+            pointNormals[(size_t)i] = Vector3{N[3 * i], N[3 * i + 1], N[3 * i + 2]};
+        }
+        pointcloud::PointPositionNormalGeometry geom(cloud, pointPositions, pointNormals);
+        geom.requireNeighbors();
+        for (int64_t i = 0; i < nP; i++) {
+            const std::vector<pointcloud::Point>& nb = geom.neighbors->neighbors[(size_t)i];
+            for (int64_t j = 0; j < k; j++) neighbors_out[i * k + j] = j < (int64_t)nb.size() ? (int64_t)nb[(size_t)j].getIndex() : -1;
+        }
+        geom.requireTangentCoordinates();
+        pointcloud::PointData<std::vector<std::array<pointcloud::Point, 3>>> local = pointcloud::buildLocalTriangulations(cloud, geom, true);
+        std::vector<std::vector<size_t>> all = pointcloud::handleToFlatInds(cloud, local);
+        *n_tris_out = (int64_t)all.size();
+        if ((int64_t)all.size() > capacity) return 2;
+        for (size_t t = 0; t < all.size(); t++)
+            for (int a = 0; a < 3; a++) tris_out[3 * t + a] = (int64_t)all[t][a];
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -5,10 +5,15 @@ cd "$(dirname "$0")"
 NCCL_INC=${NCCL_INC:-/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/include}
 OUT=../lib/libshm3d_grid.so
 mkdir -p ../lib
+# point_weights.cpp (row N1, host only) is compiled without floating-point contraction: its degenerate-case decisions
+# (cocircular / collinear / equidistant points) must follow geometry-central's expressions bit for bit, whatever FMA the
+# host compiler would like to form
+mkdir -p ../build
+g++ -std=c++17 -O3 -fPIC -pthread -ffp-contract=off -Wall -c point_weights.cpp -o ../build/point_weights.o
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
      -Xcompiler -fPIC,-pthread,-mavx2,-mfma,-Wall \
      -I"$NCCL_INC" -shared -o $OUT \
-     k_sum.cu grid_ops.cu projector.cu sources.cu dist.cu isosurface.cu solver.cu host_api.cu host_blas.cpp point_weights.cpp \
+     k_sum.cu grid_ops.cu projector.cu sources.cu dist.cu isosurface.cu solver.cu host_api.cu host_blas.cpp ../build/point_weights.o \
      -ldl -lpthread "$@"
 echo "built $OUT"
 # headless driver on top of the C++ mirror (include/shm3d/signed_heat_grid_solver.hpp)

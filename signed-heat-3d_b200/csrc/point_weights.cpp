@@ -14,11 +14,13 @@
 // triangulation, total area preserved by the flips, the final cover intrinsically Delaunay, closed forms on sampled
 // spheres.  Any positive rescaling of all areas cancels in Steps 1-2 (normalisation) and in the shift (a weighted mean).
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <numeric>
 #include <thread>
 #include <vector>
@@ -34,15 +36,17 @@ inline double cross2(const V2& a, const V2& b) { return a.x * b.y - a.y * b.x; }
 inline double dot2(const V2& a, const V2& b) { return a.x * b.x + a.y * b.y; }
 inline double norm2v(const V2& a) { return a.x * a.x + a.y * a.y; }
 
-double det3(double a, double b, double c, double d, double e, double f, double g, double h, double i) {
-    return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-}
-// deps/geometry-central/src/utilities/elementary_geometry.cpp:8-18: det of rows (x, y, |p|^2, 1) > 0
+// deps/geometry-central/src/utilities/elementary_geometry.cpp:8-18: sign of the 4x4 determinant with rows
+// (x, y, |p|^2, 1).  For (nearly) cocircular points -- vertices of structured meshes -- that sign is decided by rounding,
+// so the determinant is evaluated by the very expression Eigen 3.3 (geometry-central's pin) uses for fixed 4x4 matrices
+// (Eigen/src/LU/Determinant.h, bruteforce_det4_helper: 2x2 minors of columns 0-1 times 2x2 minors of columns 2-3), with
+// floating-point contraction off so that the host compiler's FMA choices cannot change it.
 bool in_circle(const V2& A, const V2& B, const V2& C, const V2& T) {
-    const double a2 = norm2v(A), b2 = norm2v(B), c2 = norm2v(C), t2 = norm2v(T);
-    // expand along the last column (all ones)
-    const double d = -det3(B.x, B.y, b2, C.x, C.y, c2, T.x, T.y, t2) + det3(A.x, A.y, a2, C.x, C.y, c2, T.x, T.y, t2) -
-                     det3(A.x, A.y, a2, B.x, B.y, b2, T.x, T.y, t2) + det3(A.x, A.y, a2, B.x, B.y, b2, C.x, C.y, c2);
+    const double m[4][4] = {{A.x, A.y, norm2v(A), 1.}, {B.x, B.y, norm2v(B), 1.}, {C.x, C.y, norm2v(C), 1.}, {T.x, T.y, norm2v(T), 1.}};
+    auto h = [&m](int j, int k, int a, int b) {
+        return (m[j][0] * m[k][1] - m[k][0] * m[j][1]) * (m[a][2] * m[b][3] - m[b][2] * m[a][3]);
+    };
+    const double d = h(0, 1, 2, 3) - h(0, 2, 1, 3) + h(0, 3, 1, 2) + h(1, 2, 0, 3) - h(1, 3, 0, 2) + h(2, 3, 0, 1);
     return d > 0.;
 }
 
@@ -64,7 +68,8 @@ void local_ring(std::vector<V2> pts, std::vector<size_t>& ring, std::vector<char
         V2& q = pts[i];
         const double dist = std::sqrt(norm2v(q));
         if (dist < lenScale * THRESH) {
-            V2 dir{q.x / dist, q.y / dist};
+            const double rq = 1. / std::sqrt(q.x * q.x + q.y * q.y);  // Vector2::normalize multiplies by the reciprocal
+            V2 dir{q.x * rq, q.y * rq};
             if (!std::isfinite(dir.x) || !std::isfinite(dir.y)) {
                 const double th = (2. * M_PI * (double)i) / (double)n;
                 dir = V2{std::cos(th), std::sin(th)};
@@ -77,8 +82,8 @@ void local_ring(std::vector<V2> pts, std::vector<size_t>& ring, std::vector<char
     std::vector<double> ang(n);
     const double BAD = -777;
     for (size_t i = 0; i < n; i++) {
-        const double l = std::sqrt(norm2v(pts[i]));
-        double a = std::atan2(pts[i].y / l, pts[i].x / l);
+        const double r = 1. / std::sqrt(pts[i].x * pts[i].x + pts[i].y * pts[i].y);  // arg(unit(p)), vector2.ipp:72-75,126
+        double a = std::atan2(pts[i].y * r, pts[i].x * r);
         if (!std::isfinite(a)) a = BAD;
         sortInds[i] = i;
         ang[i] = a;
@@ -147,73 +152,248 @@ int chunk_count(int64_t n) {
     return n < 4096 ? 1 : (int)T;
 }
 
-// exact k nearest neighbours (self excluded), ascending distance then index -- a uniform hash grid
-void knn_all(const double* P, int64_t n, int k, std::vector<int64_t>& nbr) {
-    nbr.assign((size_t)n * k, -1);
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int64_t i = 0; i < n; i++)
+// k nearest neighbours of every point, self excluded, EXACTLY as geometry-central gets them
+// (NearestNeighborFinder::kNearestNeighbors, src/utilities/knn.cpp:49-72: a (k+1)-search around the point itself, then the
+// point is erased from the list).  Point sets with exactly equidistant neighbours -- the vertices of structured meshes --
+// make the k-th neighbour a matter of tie-breaking, and nanoflann (the library behind it; vendored by the reference,
+// deps/geometry-central/deps/nanoflann/include/nanoflann.hpp) breaks ties by the order in which its kd-tree visits
+// points.  So the tree and the search are restated here step by step:
+//   build   KDTreeBaseClass::divideTree / middleSplit_ / planeSplit (:858-1003), leaf size 10, root box = data bounds
+//   search  KDTreeSingleIndexAdaptor::searchLevel (:1347-1411) with KNNResultSet::addPoint (:175-202): nearer child first,
+//           the other one if its box distance does not exceed the current worst; inside a leaf the worst distance is read
+//           once; a candidate equal to a stored distance goes behind it, and is dropped when the set is full
+//   metric  L2_Simple_Adaptor (:432-445): sum of squared differences, x then y then z
+class KdTree {
+  public:
+    KdTree(const double* P, int64_t n) : P_(P), n_((size_t)n), vind_((size_t)n) {
+        for (size_t i = 0; i < n_; i++) vind_[i] = i;
+        for (int a = 0; a < 3; a++) root_[a].low = root_[a].high = pt(0, a);  // computeBoundingBox (:1313-1335)
+        for (size_t k = 1; k < n_; k++)
+            for (int a = 0; a < 3; a++) {
+                if (pt(k, a) < root_[a].low) root_[a].low = pt(k, a);
+                if (pt(k, a) > root_[a].high) root_[a].high = pt(k, a);
+            }
+        nodes_.reserve(n_ / 4 + 16);
+        root_node_ = divide(0, n_, root_);
+    }
+    // indices of the `count` nearest points to q (ascending distance, ties in visiting order), like knnSearch (:1251-1258)
+    void knn(const double* q, size_t count, size_t* idx, double* dist) const {
+        Result r{idx, dist, count, 0};
+        dist[count - 1] = std::numeric_limits<double>::max();
+        double dists[3] = {0., 0., 0.};
+        double distsq = 0;  // computeInitialDistances (:1006-1023)
         for (int a = 0; a < 3; a++) {
-            lo[a] = std::min(lo[a], P[3 * i + a]);
-            hi[a] = std::max(hi[a], P[3 * i + a]);
+            if (q[a] < root_[a].low) {
+                dists[a] = (q[a] - root_[a].low) * (q[a] - root_[a].low);
+                distsq += dists[a];
+            }
+            if (q[a] > root_[a].high) {
+                dists[a] = (q[a] - root_[a].high) * (q[a] - root_[a].high);
+                distsq += dists[a];
+            }
         }
-    const double ext = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-300});
-    const int g = std::max(1, (int)std::cbrt((double)n / 4.0));
-    const double cs = ext / g * (1 + 1e-12);
-    auto cell_of = [&](const double* q, int c[3]) {
-        for (int a = 0; a < 3; a++) c[a] = std::min(g - 1, std::max(0, (int)((q[a] - lo[a]) / cs)));
+        search(r, q, root_node_, distsq, dists);
+    }
+
+  private:
+    struct Interval {
+        double low, high;
     };
-    // points grouped by cell (counting sort), positions copied in that order: a cell's candidates are one contiguous run
-    const size_t n_cells = (size_t)g * g * g;
-    std::vector<int64_t> start(n_cells + 1, 0), order((size_t)n);
-    std::vector<int32_t> cell_id((size_t)n);
-    for (int64_t i = 0; i < n; i++) {
-        int c[3];
-        cell_of(P + 3 * i, c);
-        cell_id[(size_t)i] = (int32_t)((size_t)c[0] + (size_t)c[1] * g + (size_t)c[2] * g * g);
-        start[(size_t)cell_id[(size_t)i] + 1]++;
+    typedef std::array<Interval, 3> Box;
+    struct Node {
+        int64_t child1 = -1, child2 = -1;  // -1, -1: leaf
+        size_t left = 0, right = 0;        // leaf: vind_[left .. right)
+        int divfeat = 0;
+        double divlow = 0, divhigh = 0;
+    };
+    struct Result {
+        size_t* indices;
+        double* dists;
+        size_t capacity, count;
+        double worst() const { return dists[capacity - 1]; }
+        void add(double dist, size_t index) {
+            size_t i;
+            for (i = count; i > 0; --i) {
+                if (dists[i - 1] > dist) {
+                    if (i < capacity) {
+                        dists[i] = dists[i - 1];
+                        indices[i] = indices[i - 1];
+                    }
+                } else
+                    break;
+            }
+            if (i < capacity) {
+                dists[i] = dist;
+                indices[i] = index;
+            }
+            if (count < capacity) count++;
+        }
+    };
+    const double* P_;
+    size_t n_;
+    std::vector<size_t> vind_;
+    std::vector<Node> nodes_;
+    Box root_;
+    int64_t root_node_ = -1;
+    static constexpr size_t kLeafMax = 10;
+
+    double pt(size_t i, int a) const { return P_[3 * i + a]; }
+    void min_max(const size_t* ind, size_t count, int a, double& lo, double& hi) const {
+        lo = hi = pt(ind[0], a);
+        for (size_t i = 1; i < count; ++i) {
+            const double v = pt(ind[i], a);
+            if (v < lo) lo = v;
+            if (v > hi) hi = v;
+        }
     }
-    for (size_t c = 0; c < n_cells; c++) start[c + 1] += start[c];
-    {
-        std::vector<int64_t> fill(start.begin(), start.end() - 1);
-        for (int64_t i = 0; i < n; i++) order[(size_t)fill[(size_t)cell_id[(size_t)i]]++] = i;  // ascending index inside a cell
+    int64_t divide(size_t left, size_t right, Box& bbox) {
+        const int64_t me = (int64_t)nodes_.size();
+        nodes_.emplace_back();
+        if (right - left <= kLeafMax) {
+            nodes_[(size_t)me].left = left;
+            nodes_[(size_t)me].right = right;
+            for (int a = 0; a < 3; a++) bbox[a].low = bbox[a].high = pt(vind_[left], a);
+            for (size_t k = left + 1; k < right; ++k)
+                for (int a = 0; a < 3; a++) {
+                    if (bbox[a].low > pt(vind_[k], a)) bbox[a].low = pt(vind_[k], a);
+                    if (bbox[a].high < pt(vind_[k], a)) bbox[a].high = pt(vind_[k], a);
+                }
+            return me;
+        }
+        size_t idx;
+        int cutfeat;
+        double cutval;
+        middle_split(&vind_[0] + left, right - left, idx, cutfeat, cutval, bbox);
+        Box lb(bbox);
+        lb[cutfeat].high = cutval;
+        const int64_t c1 = divide(left, left + idx, lb);
+        Box rb(bbox);
+        rb[cutfeat].low = cutval;
+        const int64_t c2 = divide(left + idx, right, rb);
+        Node& nd = nodes_[(size_t)me];
+        nd.child1 = c1;
+        nd.child2 = c2;
+        nd.divfeat = cutfeat;
+        nd.divlow = lb[cutfeat].high;
+        nd.divhigh = rb[cutfeat].low;
+        for (int a = 0; a < 3; a++) {
+            bbox[a].low = std::min(lb[a].low, rb[a].low);
+            bbox[a].high = std::max(lb[a].high, rb[a].high);
+        }
+        return me;
     }
-    std::vector<double> Q((size_t)3 * n);
-    for (int64_t s = 0; s < n; s++)
-        for (int a = 0; a < 3; a++) Q[(size_t)3 * s + a] = P[3 * order[(size_t)s] + a];
-    parallel_chunks(n, [&](int64_t s_begin, int64_t s_end, int) {
-        std::vector<std::pair<double, int64_t>> cand;
-        for (int64_t s = s_begin; s < s_end; s++) {  // sorted order: neighbouring points share their candidate cells
-            const int64_t i = order[(size_t)s];
-            const double* qi = &Q[(size_t)3 * s];
-            int c[3];
-            cell_of(qi, c);
-            cand.clear();
-            for (int ring = 0; ring <= g; ring++) {
-                for (int dz = -ring; dz <= ring; dz++)
-                    for (int dy = -ring; dy <= ring; dy++)
-                        for (int dx = -ring; dx <= ring; dx++) {
-                            if (std::max({std::abs(dx), std::abs(dy), std::abs(dz)}) != ring) continue;
-                            const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
-                            if (x < 0 || y < 0 || z < 0 || x >= g || y >= g || z >= g) continue;
-                            const size_t cell = (size_t)x + (size_t)y * g + (size_t)z * g * g;
-                            for (int64_t u = start[cell]; u < start[cell + 1]; u++) {
-                                if (u == s) continue;
-                                double d = 0;
-                                for (int a = 0; a < 3; a++) {
-                                    const double t = qi[a] - Q[(size_t)3 * u + a];
-                                    d += t * t;
-                                }
-                                cand.emplace_back(d, order[(size_t)u]);
-                            }
-                        }
-                if ((int)cand.size() >= k) {
-                    std::nth_element(cand.begin(), cand.begin() + (k - 1), cand.end());
-                    // everything in the rings searched so far that is closer than ring*cs is final
-                    if (std::sqrt(cand[k - 1].first) <= ring * cs) break;
+    void middle_split(size_t* ind, size_t count, size_t& index, int& cutfeat, double& cutval, const Box& bbox) const {
+        const double EPS = static_cast<double>(0.00001);
+        double max_span = bbox[0].high - bbox[0].low;
+        for (int a = 1; a < 3; a++) {
+            const double span = bbox[a].high - bbox[a].low;
+            if (span > max_span) max_span = span;
+        }
+        double max_spread = -1;
+        cutfeat = 0;
+        for (int a = 0; a < 3; a++) {
+            const double span = bbox[a].high - bbox[a].low;
+            if (span > (1 - EPS) * max_span) {
+                double lo, hi;
+                min_max(ind, count, a, lo, hi);
+                const double spread = hi - lo;
+                if (spread > max_spread) {
+                    cutfeat = a;
+                    max_spread = spread;
                 }
             }
-            std::partial_sort(cand.begin(), cand.begin() + k, cand.end());
-            for (int t = 0; t < k; t++) nbr[(size_t)i * k + t] = cand[t].second;
+        }
+        const double split_val = (bbox[cutfeat].low + bbox[cutfeat].high) / 2;
+        double lo, hi;
+        min_max(ind, count, cutfeat, lo, hi);
+        if (split_val < lo) cutval = lo;
+        else if (split_val > hi) cutval = hi;
+        else cutval = split_val;
+        size_t lim1, lim2;
+        plane_split(ind, count, cutfeat, cutval, lim1, lim2);
+        if (lim1 > count / 2) index = lim1;
+        else if (lim2 < count / 2) index = lim2;
+        else index = count / 2;
+    }
+    // unsigned index arithmetic on purpose (the "!right" exits are part of the library's behaviour)
+    void plane_split(size_t* ind, const size_t count, int cutfeat, double& cutval, size_t& lim1, size_t& lim2) const {
+        size_t left = 0;
+        size_t right = count - 1;
+        for (;;) {
+            while (left <= right && pt(ind[left], cutfeat) < cutval) ++left;
+            while (right && left <= right && pt(ind[right], cutfeat) >= cutval) --right;
+            if (left > right || !right) break;
+            std::swap(ind[left], ind[right]);
+            ++left;
+            --right;
+        }
+        lim1 = left;
+        right = count - 1;
+        for (;;) {
+            while (left <= right && pt(ind[left], cutfeat) <= cutval) ++left;
+            while (right && left <= right && pt(ind[right], cutfeat) > cutval) --right;
+            if (left > right || !right) break;
+            std::swap(ind[left], ind[right]);
+            ++left;
+            --right;
+        }
+        lim2 = left;
+    }
+    void search(Result& r, const double* q, int64_t node, double mindistsq, double* dists) const {
+        const Node& nd = nodes_[(size_t)node];
+        if (nd.child1 < 0 && nd.child2 < 0) {
+            const double worst = r.worst();
+            for (size_t i = nd.left; i < nd.right; ++i) {
+                const size_t index = vind_[i];
+                double dist = 0;
+                for (int a = 0; a < 3; a++) {
+                    const double diff = q[a] - pt(index, a);
+                    dist += diff * diff;
+                }
+                if (dist < worst) r.add(dist, index);
+            }
+            return;
+        }
+        const int idx = nd.divfeat;
+        const double val = q[idx];
+        const double diff1 = val - nd.divlow, diff2 = val - nd.divhigh;
+        int64_t best, other;
+        double cut_dist;
+        if ((diff1 + diff2) < 0) {
+            best = nd.child1;
+            other = nd.child2;
+            cut_dist = (val - nd.divhigh) * (val - nd.divhigh);
+        } else {
+            best = nd.child2;
+            other = nd.child1;
+            cut_dist = (val - nd.divlow) * (val - nd.divlow);
+        }
+        search(r, q, best, mindistsq, dists);
+        const double dst = dists[idx];
+        mindistsq = mindistsq + cut_dist - dst;
+        dists[idx] = cut_dist;
+        if (mindistsq * 1.0f <= r.worst()) search(r, q, other, mindistsq, dists);
+        dists[idx] = dst;
+    }
+};
+
+void knn_all(const double* P, int64_t n, int k, std::vector<int64_t>& nbr) {
+    nbr.assign((size_t)n * k, -1);
+    const KdTree tree(P, n);
+    parallel_chunks(n, [&](int64_t i_begin, int64_t i_end, int) {
+        std::vector<size_t> idx((size_t)k + 1);
+        std::vector<double> dist((size_t)k + 1);
+        for (int64_t i = i_begin; i < i_end; i++) {
+            tree.knn(P + 3 * i, (size_t)k + 1, idx.data(), dist.data());
+            // remove the source from the list; if it did not appear, drop the last entry (knn.cpp:56-71)
+            size_t self = (size_t)k;
+            for (size_t t = 0; t <= (size_t)k; t++)
+                if (idx[t] == (size_t)i) {
+                    self = t;
+                    break;
+                }
+            for (size_t t = 0, o = 0; t <= (size_t)k; t++)
+                if (t != self) nbr[(size_t)i * k + o++] = (int64_t)idx[t];
         }
     });
 }
@@ -416,6 +596,51 @@ void tufted_cover_weights(const double* P, int64_t nP, const std::vector<int64_t
     *h_out = hs / (double)E;
 }
 
+// soup triangles (p, a, b) from every point's local triangulation, ordered by centre point like the reference's
+// (point_position_geometry.cpp:113-134 for the tangent coordinates, local_triangulation.cpp for the rings)
+void build_soup(const double* P, const double* N, int64_t nP, int k, const std::vector<int64_t>& nbr, std::vector<int64_t>& tris_out) {
+    std::vector<std::vector<int64_t>> tris_of_chunk((size_t)chunk_count(nP));
+    parallel_chunks(nP, [&](int64_t p_begin, int64_t p_end, int chunk) {
+    std::vector<int64_t>& tris = tris_of_chunk[(size_t)chunk];
+    std::vector<V2> pts((size_t)k);
+    std::vector<size_t> ring;
+    std::vector<char> tri_after;
+    for (int64_t p = p_begin; p < p_end; p++) {
+        const double* c = P + 3 * p;
+        // geometry-central normalises by multiplying with the reciprocal length (vector3.ipp:132-135); the last bit matters
+        // for the degenerate decisions below, so the same is done here
+        const double rn = 1. / std::sqrt(N[3 * p] * N[3 * p] + N[3 * p + 1] * N[3 * p + 1] + N[3 * p + 2] * N[3 * p + 2]);
+        const double nrm[3] = {N[3 * p], N[3 * p + 1], N[3 * p + 2]};
+        const double u[3] = {nrm[0] * rn, nrm[1] * rn, nrm[2] * rn};
+        // Vector3::buildTangentBasis (utilities/vector3.ipp:148-159)
+        double t[3] = {1., 0., 0.};
+        if (std::fabs(u[0]) > 0.9) { t[0] = 0.; t[1] = 1.; }
+        double bx[3] = {t[1] * u[2] - t[2] * u[1], t[2] * u[0] - t[0] * u[2], t[0] * u[1] - t[1] * u[0]};
+        double l = 1. / std::sqrt(bx[0] * bx[0] + bx[1] * bx[1] + bx[2] * bx[2]);
+        for (double& v : bx) v *= l;
+        double by[3] = {u[1] * bx[2] - u[2] * bx[1], u[2] * bx[0] - u[0] * bx[2], u[0] * bx[1] - u[1] * bx[0]};
+        l = 1. / std::sqrt(by[0] * by[0] + by[1] * by[1] + by[2] * by[2]);
+        for (double& v : by) v *= l;
+        for (int j = 0; j < k; j++) {  // tangent coordinates (point_position_geometry.cpp:113-134)
+            const double* q = P + 3 * nbr[(size_t)p * k + j];
+            double v[3] = {q[0] - c[0], q[1] - c[1], q[2] - c[2]};
+            const double dn = nrm[0] * v[0] + nrm[1] * v[1] + nrm[2] * v[2];  // removeComponent(normal), normal as given
+            for (int a = 0; a < 3; a++) v[a] -= nrm[a] * dn;
+            pts[j] = V2{bx[0] * v[0] + bx[1] * v[1] + bx[2] * v[2], by[0] * v[0] + by[1] * v[1] + by[2] * v[2]};
+        }
+        local_ring(pts, ring, tri_after);
+        for (size_t i = 0; i < ring.size(); i++)
+            if (tri_after[i]) {
+                tris.push_back(p);
+                tris.push_back(nbr[(size_t)p * k + ring[i]]);
+                tris.push_back(nbr[(size_t)p * k + ring[(i + 1) % ring.size()]]);
+            }
+    }
+    });
+    tris_out.clear();  // chunks in point order
+    for (const std::vector<int64_t>& t : tris_of_chunk) tris_out.insert(tris_out.end(), t.begin(), t.end());
+}
+
 }  // namespace
 
 extern "C" {
@@ -464,45 +689,8 @@ int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_
     knn_all(P, nP, k, nbr);
     if (dbg) std::fprintf(stderr, "[shm3d] point_weights: kNN %.3fs", now() - t0), t0 = now();
 
-    // soup triangles (p, a, b) from every point's local triangulation
-    std::vector<std::vector<int64_t>> tris_of_chunk((size_t)chunk_count(nP));
-    parallel_chunks(nP, [&](int64_t p_begin, int64_t p_end, int chunk) {
-    std::vector<int64_t>& tris = tris_of_chunk[(size_t)chunk];
-    std::vector<V2> pts((size_t)k);
-    std::vector<size_t> ring;
-    std::vector<char> tri_after;
-    for (int64_t p = p_begin; p < p_end; p++) {
-        const double* c = P + 3 * p;
-        const double nl = std::sqrt(N[3 * p] * N[3 * p] + N[3 * p + 1] * N[3 * p + 1] + N[3 * p + 2] * N[3 * p + 2]);
-        const double nrm[3] = {N[3 * p], N[3 * p + 1], N[3 * p + 2]};
-        const double u[3] = {nrm[0] / nl, nrm[1] / nl, nrm[2] / nl};
-        // Vector3::buildTangentBasis (utilities/vector3.ipp:148-159)
-        double t[3] = {1., 0., 0.};
-        if (std::fabs(u[0]) > 0.9) { t[0] = 0.; t[1] = 1.; }
-        double bx[3] = {t[1] * u[2] - t[2] * u[1], t[2] * u[0] - t[0] * u[2], t[0] * u[1] - t[1] * u[0]};
-        double l = std::sqrt(bx[0] * bx[0] + bx[1] * bx[1] + bx[2] * bx[2]);
-        for (double& v : bx) v /= l;
-        double by[3] = {u[1] * bx[2] - u[2] * bx[1], u[2] * bx[0] - u[0] * bx[2], u[0] * bx[1] - u[1] * bx[0]};
-        l = std::sqrt(by[0] * by[0] + by[1] * by[1] + by[2] * by[2]);
-        for (double& v : by) v /= l;
-        for (int j = 0; j < k; j++) {  // tangent coordinates (point_position_geometry.cpp:113-134)
-            const double* q = P + 3 * nbr[(size_t)p * k + j];
-            double v[3] = {q[0] - c[0], q[1] - c[1], q[2] - c[2]};
-            const double dn = nrm[0] * v[0] + nrm[1] * v[1] + nrm[2] * v[2];  // removeComponent(normal), normal as given
-            for (int a = 0; a < 3; a++) v[a] -= nrm[a] * dn;
-            pts[j] = V2{bx[0] * v[0] + bx[1] * v[1] + bx[2] * v[2], by[0] * v[0] + by[1] * v[1] + by[2] * v[2]};
-        }
-        local_ring(pts, ring, tri_after);
-        for (size_t i = 0; i < ring.size(); i++)
-            if (tri_after[i]) {
-                tris.push_back(p);
-                tris.push_back(nbr[(size_t)p * k + ring[i]]);
-                tris.push_back(nbr[(size_t)p * k + ring[(i + 1) % ring.size()]]);
-            }
-    }
-    });
-    std::vector<int64_t> tris;  // chunks in point order: the soup is ordered by centre point, like the reference's
-    for (const std::vector<int64_t>& t : tris_of_chunk) tris.insert(tris.end(), t.begin(), t.end());
+    std::vector<int64_t> tris;
+    build_soup(P, N, nP, k, nbr, tris);
     const int64_t T = (int64_t)tris.size() / 3;
     if (dbg) std::fprintf(stderr, "  local triangulations %.3fs", now() - t0), t0 = now();
     if (n_triangles_out) *n_triangles_out = T;

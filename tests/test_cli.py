@@ -113,6 +113,30 @@ def test_cli_reads_pc_files(tmp_path):
     assert abs(d["h"] - h) < 1e-12 * h
 
 
+def test_cli_point_clouds_of_the_reference_get_geometry_centrals_h():
+    """The reference's sample .pc files through the CLI's reader and the library's tufted-cover weights, against
+    geometry-central's own pipeline (oracle/_ref/libshm_gc_ref.so) on the same points: same mean edge length, hence the
+    same lambda and grid.  Only where the reference tree is present."""
+    from oracle import reference_build as rb
+    if not (rb.build() and rb.gc_available()):
+        pytest.skip("no oracle/_ref/libshm_gc_ref.so")
+    seen = 0
+    for name in ("bunny", "chair", "rocker", "knot", "SprayBottle"):
+        path = os.path.join("/root/reference/data", name + ".pc")
+        if not os.path.exists(path):
+            continue
+        seen += 1
+        P, N = o.read_pc(path)
+        _, h_ref, _, _ = rb.gc_point_weights(P, N)
+        r = subprocess.run([CLI, path, "--dry-run"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        d = json.loads(r.stdout)
+        assert d["sources"] == len(P) and abs(d["h"] - h_ref) < 1e-12 * h_ref, name
+        assert abs(d["lambda"] - 1.0 / h_ref) < 1e-9 / h_ref, name
+    if seen == 0:
+        pytest.skip("no reference data files here")
+
+
 def test_cli_bad_input_fails_cleanly(tmp_path):
     r = subprocess.run([CLI, str(tmp_path / "missing.obj"), "--dry-run"], capture_output=True, text=True)
     assert r.returncode == 3 and "cannot read mesh" in r.stderr
