@@ -19,7 +19,8 @@ from synth import fibonacci_sphere  # noqa: E402
 
 
 def lib():
-    so = "/tmp/libfarfield.so"
+    import tempfile
+    so = os.path.join(tempfile.gettempdir(), "libfarfield_probe.so")
     subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", so,
                            os.path.join(HERE, "farfield_probe.c"), "-lm"])
     L = C.CDLL(so)
