@@ -454,7 +454,7 @@ def consumer_leg(n):
     in: a separate context, and nothing it does can take the main line down.  Not part of `value` / `e2e`."""
     try:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_consumer.py"), "--n", str(n)],
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=180)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)
