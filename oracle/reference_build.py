@@ -117,6 +117,27 @@ class _Solver:
         np.ctypeslib.as_array(x, shape=(n,))[:] = spla.splu(A).solve(b)
 
 
+class _AssembleOnly(_Solver):
+    """Records the system the reference assembled and returns x = 0 without factorising it: lets a test look at the KKT
+    matrix and right-hand side of grids far too large for the LU."""
+
+    def _solve(self, n, nnz, colptr, rowidx, val, rhs, x):
+        import scipy.sparse as sp
+        cp = np.ctypeslib.as_array(colptr, shape=(n + 1,)).copy()
+        ri = np.ctypeslib.as_array(rowidx, shape=(nnz,)).copy()
+        v = np.ctypeslib.as_array(val, shape=(nnz,)).copy()
+        self.calls.append(dict(n=int(n), nnz=int(nnz), A=sp.csc_matrix((v, ri, cp), shape=(n, n)),
+                               rhs=np.ctypeslib.as_array(rhs, shape=(n,)).copy()))
+        np.ctypeslib.as_array(x, shape=(n,))[:] = 0.0
+
+
+def ref_gc_assemble_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0):
+    """The KKT matrix and right-hand side the REFERENCE (on the real geometry-central) hands to solveSquare."""
+    s = _AssembleOnly()
+    _gc_harness_mesh(REF_GC_LIB_PATH, "reference (geometry-central)", V, faces, tCoef, hCoef, scale, False, s)
+    return s.calls[0]["A"], s.calls[0]["rhs"]
+
+
 def compute_distance_mesh(V, faces, tCoef=1.0, hCoef=0.0, scale=2.0, fast=False, return_info=False):
     """SignedHeatGridSolver::computeDistance(VertexPositionGeometry&, options) of the reference itself."""
     V = np.ascontiguousarray(V, dtype=np.float64)

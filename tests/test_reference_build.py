@@ -174,6 +174,28 @@ def test_reference_source_on_the_real_geometry_central():
     assert np.linalg.norm(phip - refp) / np.linalg.norm(refp) < 1e-12
 
 
+def test_constraint_rows_and_rhs_at_64_equal_the_reference():
+    """A grid far beyond the reference's LU (64^3): the system it ASSEMBLES (on the real geometry-central, factorisation
+    skipped) against the product's constraint rows -- same m, same nodes, same trilinear weights -- and the oracle's
+    right-hand side D^T Y."""
+    import shm3d
+    if not rb.ref_gc_available():
+        pytest.skip("no oracle/_ref/libshm_ref_gc.so")
+    z, F = load_golden("polygon-bear")
+    K, rhs = rb.ref_gc_assemble_mesh(z["V"], F, hCoef=2)
+    N = 64 ** 3
+    A_ref = K.tocsr()[N:, :N]
+    p, pos, nrm, area, h = shm3d.prepare_mesh(z["V"], F, hCoef=2)
+    src, node, w = shm3d.debug_constraints(p, pos)
+    assert A_ref.shape[0] == len(src)
+    A = sp.coo_matrix((w.ravel(), (np.repeat(np.arange(len(src)), 8), node.ravel())), shape=(len(src), N)).tocsr()
+    assert abs(A_ref - A).max() < 1e-13
+    g = o.make_grid(z["centroid"], float(z["radius"]), hCoef=2)
+    s = o.mesh_sources(z["V"], F)
+    b = o.div_rhs(g, o.step12(g, o.lambda_from_h(s["h"]), s["pos"], s["nrm"], s["area"]))
+    assert np.linalg.norm(rhs[:N] - b) / np.linalg.norm(b) < 1e-12 and not rhs[N:].any()
+
+
 def test_knot_golden_is_the_reference_sources_output():
     """data/knot.obj at hCoef 1 (30 504 faces x 32^3 nodes, ~1 min single-threaded: the reference recomputes every
     barycentre per pair): the committed golden field the GPU tests compare against is the reference's own result."""
