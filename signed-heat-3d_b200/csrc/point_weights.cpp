@@ -414,7 +414,8 @@ inline V2 layout_vertex(const V2& pA, const V2& pB, double lBC, double lCA) {
     const double lAB = std::sqrt((pB.x - pA.x) * (pB.x - pA.x) + (pB.y - pA.y) * (pB.y - pA.y));
     const double h = 2. * tri_area(lAB, lBC, lCA) / lAB;
     const double w = (lAB * lAB - lBC * lBC + lCA * lCA) / (2. * lAB);
-    const V2 n{(pB.x - pA.x) / lAB, (pB.y - pA.y) / lAB};
+    const double rAB = 1. / lAB;  // Vector2::operator/(double) multiplies by the reciprocal (vector2.ipp:17-20)
+    const V2 n{(pB.x - pA.x) * rAB, (pB.y - pA.y) * rAB};
     return V2{pA.x + w * n.x - h * n.y, pA.y + w * n.y + h * n.x};
 }
 
@@ -508,6 +509,14 @@ void tufted_cover_weights(const double* P, int64_t nP, const std::vector<int64_t
     auto front_of = [&](int64_t soup_he) { return 6 * (soup_he / 3) + soup_he % 3; };
     auto other = [&](int64_t h) { return (h % 6) < 3 ? h + 3 : h - 3; };
     std::vector<int64_t> F;
+    const int64_t n_soup_edges = (int64_t)edges.size();
+    {
+        size_t total = 0;
+        for (const SoupEdge& e : edges) total += e.count;
+        elen.assign(total, 0.);
+    }
+    std::vector<int64_t> edge_he(elen.size(), -1);
+    int64_t n_new = 0, soup_index = 0;
     for (const SoupEdge& e : edges) {
         // e.adjacentHalfedges(): h_1, then the sibling chain h_n, h_{n-1}, ..., h_2 (surface_mesh.cpp:187-203)
         const size_t n = e.count;
@@ -524,15 +533,18 @@ void tufted_cover_weights(const double* P, int64_t nP, const std::vector<int64_t
             if (orient(curr) == orient(nxt)) nxt = other(nxt);
             twin[curr] = nxt;
             twin[nxt] = curr;
-            hedge[curr] = hedge[nxt] = (int64_t)elen.size();
-            elen.push_back(e.len);
+            // SurfaceMesh::separateToNewEdge (surface_mesh.cpp:930-964): every pair but the last one moves to a NEW edge
+            // (appended behind all existing ones, with the first halfedge of the pair as its halfedge); the last pair
+            // keeps the original edge.  Edge order = order of the flip queue and of the final sums.
+            const int64_t id = (i + 1 < n) ? n_soup_edges + n_new++ : soup_index;
+            hedge[curr] = hedge[nxt] = id;
+            elen[(size_t)id] = e.len;
+            edge_he[(size_t)id] = curr;
             curr = other(nxt);
         }
+        soup_index++;
     }
     const int64_t E = (int64_t)elen.size();
-    std::vector<int64_t> edge_he(E, -1);
-    for (int64_t h = 0; h < H; h++)
-        if (hedge[h] >= 0 && edge_he[hedge[h]] < 0) edge_he[hedge[h]] = h;
     auto face_area = [&](int64_t h) { return tri_area(elen[hedge[h]], elen[hedge[next[h]]], elen[hedge[next[next[h]]]]); };
     for (int64_t f = 0; f < 2 * T; f++) st.area_before += face_area(3 * f);
     // ---- intrinsic flips to Delaunay (simple_idt.cpp:11-188, Euclidean, eps 1e-6)

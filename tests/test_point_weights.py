@@ -72,6 +72,51 @@ def test_weights_equal_geometry_central_live():
         assert 2 * n_tris == nf, name
 
 
+def test_weights_equal_geometry_central_on_degenerate_clouds():
+    """Structured and damaged inputs, where every discrete decision is a tie or nearly one: surface lattices of a cube
+    (coincident points along its edges), cylinder, latitude-longitude sphere, hexagonal plane; exact duplicates;
+    coordinates quantised to 1e-3 (activates the intrinsic mollification).  Same soup, same areas, same h."""
+    from oracle import reference_build as rb
+    if not (rb.build() and rb.gc_available()):
+        pytest.skip("no oracle/_ref/libshm_gc_ref.so")
+    rng = np.random.default_rng(42)
+    clouds = []
+    g = np.linspace(-1, 1, 21)
+    pts, nrm = [], []
+    for ax in range(3):
+        for sgn in (-1.0, 1.0):
+            u, v = np.meshgrid(g, g)
+            p = np.zeros((u.size, 3))
+            p[:, ax], p[:, (ax + 1) % 3], p[:, (ax + 2) % 3] = sgn, u.ravel(), v.ravel()
+            n = np.zeros_like(p)
+            n[:, ax] = sgn
+            pts.append(p)
+            nrm.append(n)
+    clouds.append(("cube lattice", np.concatenate(pts), np.concatenate(nrm)))
+    th, zz = np.meshgrid(np.linspace(0, 2 * np.pi, 64, endpoint=False), np.linspace(-1, 1, 33))
+    cyl = np.stack([np.cos(th).ravel(), np.sin(th).ravel(), zz.ravel()], axis=1)
+    clouds.append(("cylinder lattice", cyl, cyl * [1.0, 1.0, 0.0]))
+    th, ph = np.meshgrid(np.linspace(0, 2 * np.pi, 48, endpoint=False), np.linspace(0.05, np.pi - 0.05, 40))
+    sph = np.stack([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)], axis=-1).reshape(-1, 3)
+    clouds.append(("lat-long sphere", sph, sph.copy()))
+    a, b = np.meshgrid(np.arange(40), np.arange(40))
+    hexp = np.stack([a.ravel() + 0.5 * (b.ravel() % 2), b.ravel() * np.sqrt(3) / 2, 0.0 * a.ravel()], axis=1)
+    clouds.append(("hex lattice", hexp, np.tile([0.0, 0.0, 1.0], (len(hexp), 1))))
+    P = rng.standard_normal((1500, 3))
+    P /= np.linalg.norm(P, axis=1, keepdims=True)
+    P = np.concatenate([P, P[:200]])
+    clouds.append(("200 duplicated points", P, P.copy()))
+    P = rng.standard_normal((3000, 3))
+    P = np.round(P / np.linalg.norm(P, axis=1, keepdims=True), 3)
+    clouds.append(("quantised coordinates", P, P / np.linalg.norm(P, axis=1, keepdims=True)))
+    for name, P, N in clouds:
+        a_ref, h_ref, nf, ne = rb.gc_point_weights(P, N)
+        a, h, n_tris = shm3d.point_weights(P, N)
+        assert 2 * n_tris == nf, name
+        assert abs(h - h_ref) < 1e-12 * h_ref, name
+        assert np.abs(a - a_ref).max() < 1e-10 * a_ref.max(), name
+
+
 def fib_points(n):
     i = np.arange(n) + 0.5
     phi = np.arccos(1 - 2 * i / n)
