@@ -1,4 +1,4 @@
-// point_weights.cpp -- host-side source weights for the point-cloud overload (partial).
+// point_weights.cpp -- host-side source weights for the point-cloud overload.
 //
 // The reference reads two things from geometry-central's tufted triangulation of the cloud
 // (src/signed_heat_grid_solver.cpp:149-151,165): per-point vertex dual areas and the mean edge length h.
@@ -9,10 +9,17 @@
 // All of it is restated here from the cited sources: the soup mesh's edge / sibling order (surface_mesh.cpp:60-205), the
 // mollification (intrinsic_mollification.cpp:7-38), the gluing rule of the cover (tufted_laplacian.cpp:39-121, the
 // position-free "natural ordering" branch the point-cloud path takes), the Euclidean intrinsic flips (simple_idt.cpp:11-188,
-// SurfaceMesh::flip :848-928).  It CANNOT be checked against geometry-central here (that library needs Eigen, absent
-// from this image): the tests check what can be checked without it -- every local star against scipy's Delaunay
-// triangulation, total area preserved by the flips, the final cover intrinsically Delaunay, closed forms on sampled
-// spheres.  Any positive rescaling of all areas cancels in Steps 1-2 (normalisation) and in the shift (a weighted mean).
+// SurfaceMesh::flip :848-928), and -- because structured inputs make every discrete decision a tie -- also the things that
+// decide ties: nanoflann's kd-tree (visiting order = which of several equidistant points is the 30th neighbour),
+// geometry-central's multiply-by-reciprocal normalisations, Eigen 3.3's 4x4 determinant expression in the in-circle test,
+// the numbering of the cover's edges (= order of the flip queue).  This file is compiled WITHOUT floating-point contraction
+// (csrc/build.sh) so that those expressions round the same on every host.
+// Checked against geometry-central's own sources (compiled from the reference tree against an Eigen stub,
+// oracle/_ref/libshm_gc_ref.so): areas and h equal to <= 1e-12 on all of the reference's sample clouds and on lattice /
+// duplicated / quantised clouds (tests/test_point_weights.py); independent checks: every local star against scipy's
+// Delaunay triangulation, total area preserved by the flips, the final cover intrinsically Delaunay, closed forms on
+// sampled spheres.  Any positive rescaling of all areas cancels in Steps 1-2 (normalisation) and in the shift.
+// kNN queries and local triangulations run on the host threads (chunks assembled in point order: thread-count independent).
 #include <algorithm>
 #include <array>
 #include <chrono>
