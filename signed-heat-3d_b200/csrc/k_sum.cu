@@ -244,6 +244,7 @@ k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict_
     if (ix < P.nx && iy < P.ny) {
         if (iz0 < nzl) {
             float s = fmaxf(fmaxf(fabsf(X00), fabsf(X01)), fabsf(X02));
+            if (P.uf_enable && log2f(s) - cm0 < P.uf_thr) s = __int_as_float(0x7fc00000);  // NaN: see SumParams
             float a = X00 / s, b = X01 / s, c = X02 / s;
             float nrm = sqrtf(a * a + b * b + c * c);
             size_t idx = (size_t)ix + (size_t)iy * P.nx + (size_t)iz0 * P.nx * P.ny;
@@ -253,6 +254,7 @@ k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict_
         }
         if (iz1 < nzl) {
             float s = fmaxf(fmaxf(fabsf(X10), fabsf(X11)), fabsf(X12));
+            if (P.uf_enable && log2f(s) - cm1 < P.uf_thr) s = __int_as_float(0x7fc00000);
             float a = X10 / s, b = X11 / s, c = X12 / s;
             float nrm = sqrtf(a * a + b * b + c * c);
             size_t idx = (size_t)ix + (size_t)iy * P.nx + (size_t)iz1 * P.nx * P.ny;

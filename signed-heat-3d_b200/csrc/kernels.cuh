@@ -13,6 +13,11 @@ struct SumParams {
     float lam2;  // lambda * log2(e)
     float tol;   // tau / lambda (distance units); +inf = keep everything
     int n_clusters;
+    // SHM3D_FLAG_FP64_UNDERFLOW: a node whose largest |component| of the TRUE sum X is below 2^-537.5 gets NaN (the
+    // reference's X.norm() is zero there).  The kernel holds X~ = wscale * 2^(lam2*m) * X, so the test is
+    // log2(max|X~|) - lam2*m < uf_thr with uf_thr = -537.5 + log2(wscale); uf_enable = 0 skips it.
+    int uf_enable;
+    float uf_thr;
 };
 // Y: component-major, component a of local node idx at Y[a*ystride + idx]
 void launch_heat_sum(const SumParams& P, const float4* cl_bounds, const int2* cl_range, const float4* src_pos,

@@ -495,6 +495,8 @@ struct Solver {
         double tau = p->cull_tau > 0 ? p->cull_tau : 10.0;
         P.tol = std::isinf(tau) ? INFINITY : (float)(tau / p->lambda);
         P.n_clusters = (int)cs.bounds.size();
+        P.uf_enable = (p->flags & SHM3D_FLAG_FP64_UNDERFLOW) ? 1 : 0;
+        P.uf_thr = (float)(-537.5 + std::log2(cs.wscale));
         SHM3D_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), s));
         SHM3D_CUDA_CHECK(cudaMemsetAsync(c->Ybuf.p, 0, 3 * ycomp() * sizeof(float), s));
         pending_sum_timer.reset(new Timer(s));

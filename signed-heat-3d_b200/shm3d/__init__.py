@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libshm3d_grid.so")
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_FACTORIZATION, ERR_NO_CONVERGENCE, ERR_NCCL = range(7)
 FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_PROFILE = 1, 2, 4, 8, 16, 32
+FLAG_FP64_UNDERFLOW = 64  # reproduce the reference's fp64 underflow in X.norm() at far nodes (include/shm3d_grid.h)
 
 
 class Params(C.Structure):
