@@ -437,6 +437,7 @@ class SignedHeatGridSolver:
 
     def __init__(self, device=0, context: Context | None = None, reuse_output: bool = True):
         self.VERBOSE = False
+        self.reference_underflow = False   # SHM3D_FLAG_FP64_UNDERFLOW (include/shm3d_grid.h); off in this version
         # True: computeDistance returns a view of a solver-owned page-locked buffer that the NEXT call overwrites
         # (fast D2H, no per-call 1 GB allocation); False: every call returns a freshly allocated array it owns.
         self.reuse_output = reuse_output
@@ -450,6 +451,8 @@ class SignedHeatGridSolver:
             p.flags |= FLAG_VERBOSE
         if options.fastIntegration:
             p.flags |= FLAG_FAST
+        if self.reference_underflow:
+            p.flags |= FLAG_FP64_UNDERFLOW
         n = self.ctx.local_n(p)
         if not self.reuse_output:
             phi, st = self.ctx.solve(p, pos, nrm, area)
