@@ -120,13 +120,19 @@ __global__ void k_slice(int nx, int ny, int nz, const float* __restrict__ field,
     const size_t total = (size_t)nu * nv;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
         const double a = (double)(q % nu), b = (double)(q / nu);
-        const double qx = ox + a * ux + b * vx, qy = oy + a * uy + b * vy, qz = oz + a * uz + b * vz;
+        // every product and sum rounded on its own (no FMA contraction), like the reference's expressions evaluated by a
+        // compiler that does not contract and like the oracle's numpy: one ulp in q decides which cell a sample on a
+        // cell face belongs to
+        const double qx = __dadd_rn(__dadd_rn(ox, __dmul_rn(a, ux)), __dmul_rn(b, vx));
+        const double qy = __dadd_rn(__dadd_rn(oy, __dmul_rn(a, uy)), __dmul_rn(b, vy));
+        const double qz = __dadd_rn(__dadd_rn(oz, __dmul_rn(a, uz)), __dmul_rn(b, vz));
         const double fi = floor((qx - bx) / cell), fj = floor((qy - by) / cell), fk = floor((qz - bz) / cell);
         float r = nanf("");
         if (fi >= 0 && fj >= 0 && fk >= 0 && fi < nx - 1 && fj < ny - 1 && fk < nz - 1) {
             const int i = (int)fi, j = (int)fj, k = (int)fk;
-            const double tx = (qx - (bx + i * cell)) / cell, ty = (qy - (by + j * cell)) / cell,
-                         tz = (qz - (bz + k * cell)) / cell;
+            const double tx = (qx - __dadd_rn(bx, __dmul_rn((double)i, cell))) / cell,
+                         ty = (qy - __dadd_rn(by, __dmul_rn((double)j, cell))) / cell,
+                         tz = (qz - __dadd_rn(bz, __dmul_rn((double)k, cell))) / cell;
             const float* p = field + (size_t)i + (size_t)j * nx + (size_t)k * nx * ny;
             const size_t sy = (size_t)nx, sz = (size_t)nx * ny;
             const double v00 = p[0] * (1. - tx) + p[1] * tx, v01 = p[sz] * (1. - tx) + p[sz + 1] * tx;

@@ -107,7 +107,9 @@ __global__ void k_source_average(LevelDims L, double bx, double by, double bz, d
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < M; s += (int64_t)gridDim.x * blockDim.x) {
         double qx = pos[3 * s], qy = pos[3 * s + 1], qz = pos[3 * s + 2];
         int i = (int)floor((qx - bx) / cell), j = (int)floor((qy - by) / cell), k = (int)floor((qz - bz) / cell);
-        double tx = (qx - (bx + i * cell)) / cell, ty = (qy - (by + j * cell)) / cell, tz = (qz - (bz + k * cell)) / cell;
+        // node position rounded like bboxMin + cell*i without contraction (reference :510-514 as the oracle evaluates it)
+        double tx = (qx - __dadd_rn(bx, __dmul_rn((double)i, cell))) / cell, ty = (qy - __dadd_rn(by, __dmul_rn((double)j, cell))) / cell,
+               tz = (qz - __dadd_rn(bz, __dmul_rn((double)k, cell))) / cell;
         double A = area[s];
         double v = 0;
 #pragma unroll
