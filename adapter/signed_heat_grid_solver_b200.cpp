@@ -75,7 +75,7 @@ Vector<double> SignedHeatGridSolver::computeDistance(VertexPositionGeometry& geo
     for (int a = 0; a < 3; a++) p.bbox_min[a] = bboxMin[a];
     p.cell = cellSize;
     p.lambda = std::sqrt(1. / shortTime);
-    p.flags = SHM3D_FLAG_SCRUB_NONFINITE | (VERBOSE ? SHM3D_FLAG_VERBOSE : 0u) | (options.fastIntegration ? SHM3D_FLAG_FAST : 0u);
+    p.flags = SHM3D_FLAG_SCRUB_NONFINITE | SHM3D_FLAG_FP64_UNDERFLOW | (VERBOSE ? SHM3D_FLAG_VERBOSE : 0u) | (options.fastIntegration ? SHM3D_FLAG_FAST : 0u);
 
     setFaceVectorAreas(geometry, faceAreas, faceNormals);  // :47
     const size_t F = mesh.nFaces();
@@ -129,7 +129,7 @@ Vector<double> SignedHeatGridSolver::computeDistance(pointcloud::PointPositionNo
     for (int a = 0; a < 3; a++) p.bbox_min[a] = bboxMin[a];
     p.cell = cellSize;
     p.lambda = std::sqrt(1. / shortTime);
-    p.flags = (VERBOSE ? SHM3D_FLAG_VERBOSE : 0u) | (options.fastIntegration ? SHM3D_FLAG_FAST : 0u);  // no scrub (:180)
+    p.flags = SHM3D_FLAG_FP64_UNDERFLOW | (VERBOSE ? SHM3D_FLAG_VERBOSE : 0u) | (options.fastIntegration ? SHM3D_FLAG_FAST : 0u);  // no scrub (:180)
 
     const size_t P = pointGeom.cloud.nPoints();
     std::vector<double> pos(3 * P), nrm(3 * P), area(P);

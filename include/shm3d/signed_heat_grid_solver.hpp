@@ -82,8 +82,9 @@ class SignedHeatGridSolver {
 
     bool VERBOSE = true;
     // Reproduce the reference's double-precision underflow of X.norm() at far nodes (SHM3D_FLAG_FP64_UNDERFLOW,
-    // include/shm3d_grid.h).  Off in this version.
-    bool referenceUnderflow = false;
+    // include/shm3d_grid.h): on, because a drop-in returns what the reference returns (validated on the B200 against the
+    // reference's own output and the fp64 oracle, tests/test_gpu_baseline_configs.py).  false = Steps 1-2 finite everywhere.
+    bool referenceUnderflow = true;
 
     // Mesh overload.  Returns phi at the nx*ny*nz nodes, index i + j*nx + k*nx*ny (x fastest).
     std::vector<double> computeDistance(const PolygonMesh& mesh, const SignedHeat3DOptions& options = SignedHeat3DOptions()) {
@@ -175,6 +176,7 @@ class SignedHeatGridSolver {
         if (VERBOSE) p.flags |= SHM3D_FLAG_VERBOSE;
         if (options.fastIntegration) p.flags |= SHM3D_FLAG_FAST;
         if (referenceUnderflow) p.flags |= SHM3D_FLAG_FP64_UNDERFLOW;
+        else p.flags &= ~SHM3D_FLAG_FP64_UNDERFLOW;
         p.cull_tau = solverParams.cull_tau;
         p.cg_rel_tol = solverParams.cg_rel_tol;
         p.cg_max_iters = solverParams.cg_max_iters;

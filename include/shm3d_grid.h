@@ -51,15 +51,19 @@ extern "C" {
 #define SHM3D_FLAG_VERBOSE 4u          /* SignedHeatGridSolver::VERBOSE */
 #define SHM3D_FLAG_NO_MG 8u            /* diagnostics: plain projected CG (no multigrid preconditioner) */
 #define SHM3D_FLAG_PROFILE 32u         /* time selected kernels with CUDA events on the solver's stream (fills the ms_pcg_* stats) */
-#define SHM3D_FLAG_FP64_UNDERFLOW 64u  /* reproduce a floating-point artefact of the reference: where every component of the
-                                        * summed field X is below 2^-537.5 (lambda * distance-to-the-surface >~ 355: far corners
-                                        * of the box for finely triangulated inputs such as data/SprayBottle.obj), its
-                                        * X /= X.norm() (src/signed_heat_grid_solver.cpp:61) squares to zero in double precision
-                                        * and Y becomes non-finite there; the mesh overload then zeroes the right-hand-side
-                                        * entries that touch such a node (:72-74), the point overload throws.  Steps 1-2 here
-                                        * are range-shifted and finite everywhere; with this flag those nodes are made
-                                        * non-finite as well, so that phi follows the reference (2e-2 relative L2 on
-                                        * SprayBottle otherwise).  Off by default in this version: see DESIGN.md section 9. */
+#define SHM3D_FLAG_FP64_UNDERFLOW 64u  /* follow a floating-point artefact of the reference: where the summed field X is so small
+                                        * (lambda * distance-to-the-surface >~ 355: far corners of the box for finely
+                                        * triangulated inputs such as data/SprayBottle.obj) that its X /= X.norm()
+                                        * (src/signed_heat_grid_solver.cpp:61, plain double) loses precision (max|X| < 2^-511)
+                                        * or squares to zero (max|X| < 2^-537.5), Y is of the wrong length or non-finite; the
+                                        * mesh overload then zeroes the right-hand-side entries that touch a non-finite node
+                                        * (:72-74), the point overload throws.  Steps 1-2 here are range-shifted and finite
+                                        * everywhere; with this flag Step 2 evaluates the reference's expression in IEEE double
+                                        * on the true values at those nodes, so phi follows the reference (2e-2 relative L2
+                                        * on SprayBottle otherwise).  Set by shm3d_prepare_mesh / shm3d_prepare_points, the
+                                        * adapter and the class mirrors (a drop-in returns what the reference returns); a
+                                        * caller filling shm3d_params by hand opts in. */
+#define SHM3D_FLAG_NO_TMA 128u          /* diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones */
 #define SHM3D_FLAG_PLAIN_MG 16u        /* unconstrained Poisson V-cycle as preconditioner, projector on the fine level only */
 
 typedef struct shm3d_ctx shm3d_ctx;
@@ -228,6 +232,14 @@ int shm3d_debug_constraints(const shm3d_params* p, int64_t n_sources, const doub
 int shm3d_debug_factor_solve(const shm3d_params* p, int64_t n_sources, const double* pos, int32_t uniform,
                              double* v /*[m] in/out*/, int32_t m_expected, double* factor_megabytes,
                              int32_t* tree_height);
+
+/* GPU-test probe: one stencil operation of the PCG / V-cycle (op: 0 p-update + K'p + p.q, 1 Jacobi sweep, 2 sweep + the
+ * PCG dots, 3 residual, 4 the two fused first sweeps) on padded vectors of (k1-k0)+2 planes, through the row-streaming
+ * kernels (use_tma = 0) or the TMA-staged marching kernels (use_tma = 1); tests/test_gpu_march.py requires identical
+ * results.  scal: {mean, beta | omega, omega2}.  reps > 0: also the device time per launch over `reps` launches. */
+int shm3d_debug_stencil_op(shm3d_ctx* ctx, int32_t op, int32_t nx, int32_t ny, int32_t nz, int32_t k0, int32_t k1,
+                           const float* in0, const float* in1, const float* pw, const double* scal, int32_t use_tma,
+                           float* out0, float* out1, double* red /*[2]*/, int32_t reps, double* ms_per_launch);
 
 /* Library / build identification ("shm3d-b200 <version> sm_100a"). */
 const char* shm3d_version(void);

@@ -566,6 +566,11 @@ inline unsigned int nblk_rows(const LevelDims& L) {
     size_t b = (rows + kT / 32 - 1) / (kT / 32);
     return (unsigned int)std::max<size_t>(1, std::min<size_t>(b, kMaxBlocks));
 }
+
+// TMA-staged marching kernels (grid_march.cuh): bound per host thread at every API entry like the reduction scratch
+thread_local bool g_march_disabled = false;
+thread_local int g_march_sms = 148;
+#include "grid_march.cuh"
 // ---------------------------------------------------------------- fastIntegration (reference integrateGreedily, :224-275)
 // The reference runs a FIFO breadth-first search from node (0,0,0), visiting neighbours in the order -x,+x,-y,+y,-z,+z,
 // and sets phi[q] = phi[p] + normalize(Y_p + Y_q) . (q - p) for the first p that reaches q.  On the full box the BFS
@@ -655,6 +660,10 @@ void set_reduction_scratch(double* partials, unsigned int* counter) {
     t_scratch.partials = partials;
     t_scratch.counter = counter;
 }
+void set_march_config(bool enabled, int sm_count) {
+    g_march_disabled = !enabled;
+    g_march_sms = sm_count > 0 ? sm_count : 148;
+}
 size_t reduction_scratch_doubles() { return (size_t)kMaxBlocks * 4; }
 
 #define POST() \
@@ -717,26 +726,31 @@ void launch_mg_smooth0(const LevelDims& L, float* x, const float* b, const doubl
 }
 void launch_mg_smooth(const LevelDims& L, float* xo, const float* x, const float* b, const double* sum_b,
                       double n_global, float omega, cudaStream_t s) {
-    if (vec4(L)) k_row_smooth<false><<<nblk_rows(L), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, RedScratch{}, nullptr);
+    if (march_ok(L)) march_launch<OpSmooth<false>>(L, x, nullptr, b, xo, nullptr, {sum_b, n_global, omega}, RedScratch{}, nullptr, s);
+    else if (vec4(L)) k_row_smooth<false><<<nblk_rows(L), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, RedScratch{}, nullptr);
     else k_mg_smooth<1, false><<<nblk(L.n()), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, RedScratch{}, nullptr);
     POST();
 }
 void launch_mg_smooth_dot(const LevelDims& L, float* xo, const float* x, const float* b, const double* sum_b,
                           double n_global, float omega, double* acc, cudaStream_t s) {
-    if (vec4(L)) k_row_smooth<true><<<nblk_rows(L), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, red_scratch(), acc);
+    if (march_ok(L)) march_launch<OpSmooth<true>>(L, x, nullptr, b, xo, nullptr, {sum_b, n_global, omega}, red_scratch(), acc, s);
+    else if (vec4(L)) k_row_smooth<true><<<nblk_rows(L), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, red_scratch(), acc);
     else k_mg_smooth<1, true><<<nblk(L.n()), kT, 0, s>>>(L, xo, x, b, sum_b, n_global, omega, red_scratch(), acc);
     POST();
 }
 void launch_mg_smooth01(const LevelDims& L, float* xo, const float* b, const double* sum_b, double n_global, float omega,
                         float omega2, cudaStream_t s) {
-    if (vec4(L)) k_row_smooth01<<<nblk_rows(L), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega, omega2);
+    if (march_ok(L)) march_launch<OpSmooth01>(L, b, nullptr, nullptr, xo, nullptr, {sum_b, n_global, omega, omega2}, RedScratch{}, nullptr, s);
+    else if (vec4(L)) k_row_smooth01<<<nblk_rows(L), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega, omega2);
     else k_mg_smooth01<1><<<nblk(L.n()), kT, 0, s>>>(L, xo, b, sum_b, n_global, omega, omega2);
     POST();
 }
 void launch_update_p_stencil(const LevelDims& L, float* p_new, const float* p_old, const float* z, float* q,
                              const double* sum_z, double n_global, const double* rho_new, const double* rho_old, int first,
                              double* acc, cudaStream_t s) {
-    if (vec4(L))
+    if (march_ok(L))
+        march_launch<OpUpdateP>(L, z, p_old, nullptr, p_new, q, {sum_z, rho_new, rho_old, n_global, first}, red_scratch(), acc, s);
+    else if (vec4(L))
         k_row_update_p_stencil<<<nblk_rows(L), kT, 0, s>>>(L, p_new, p_old, z, q, sum_z, n_global, rho_new, rho_old, first,
                                                            red_scratch(), acc);
     else
@@ -746,7 +760,8 @@ void launch_update_p_stencil(const LevelDims& L, float* p_new, const float* p_ol
 }
 void launch_mg_residual(const LevelDims& L, const float* x, const float* b, const double* sum_b, double n_global,
                         float* r, cudaStream_t s) {
-    if (vec4(L)) k_row_residual<<<nblk_rows(L), kT, 0, s>>>(L, x, b, sum_b, n_global, r);
+    if (march_ok(L)) march_launch<OpResidual>(L, x, nullptr, b, r, nullptr, {sum_b, n_global}, RedScratch{}, nullptr, s);
+    else if (vec4(L)) k_row_residual<<<nblk_rows(L), kT, 0, s>>>(L, x, b, sum_b, n_global, r);
     else k_mg_residual<1><<<nblk(L.n()), kT, 0, s>>>(L, x, b, sum_b, n_global, r);
     POST();
 }

@@ -60,7 +60,9 @@ int shm3d_prepare_mesh(const double* V, int64_t nV, const int64_t* face_vertices
     for (int a = 0; a < 3; a++) out->bbox_min[a] = c[a] - s;
     out->cell = 2. * s / (nx - 1);
     out->lambda = std::sqrt(1. / (tCoef * h * h));
-    out->flags = SHM3D_FLAG_SCRUB_NONFINITE;  // the mesh overload scrubs non-finite rhs entries
+    // the mesh overload scrubs non-finite rhs entries (:72-74); Step 2 follows the reference's double-precision
+    // X /= X.norm() where it underflows (:61), so the drop-in returns what the reference returns
+    out->flags = SHM3D_FLAG_SCRUB_NONFINITE | SHM3D_FLAG_FP64_UNDERFLOW;
 
     if (pos_out && nrm_out && area_out) {
         for (int64_t f = 0; f < nF; f++) {
@@ -105,7 +107,9 @@ int shm3d_prepare_points(const double* P, int64_t nP, double h, double tCoef, do
     for (int a = 0; a < 3; a++) out->bbox_min[a] = c[a] - s;
     out->cell = 2. * s / (nx - 1);
     out->lambda = std::sqrt(1. / (tCoef * h * h));
-    out->flags = 0;  // the point overload does not scrub (src/signed_heat_grid_solver.cpp:180)
+    // the point overload does not scrub (src/signed_heat_grid_solver.cpp:180): where the reference's X.norm() underflows
+    // (:171) its solve throws on the non-finite right-hand side, and so does this one
+    out->flags = SHM3D_FLAG_FP64_UNDERFLOW;
     return SHM3D_OK;
 }
 

@@ -67,6 +67,33 @@ __device__ __forceinline__ void update_ref(float px, float py, float pz, const f
     }
 }
 
+// Step 2 for one node: Y = X / |X|.  The kernel holds X~ = wscale * 2^cm * X (cm = lam2 * running reference distance).
+// Default: scale by the largest component, normalise in fp32 -- finite wherever X~ is.
+// SHM3D_FLAG_FP64_UNDERFLOW: where the TRUE X is small enough for the reference's `X /= X.norm()`
+// (src/signed_heat_grid_solver.cpp:61, plain sqrt(x*x + y*y + z*z) in double) to lose precision -- squares below the
+// normal range, i.e. max|X| < 2^-511 -- or to underflow to zero altogether (max|X| < 2^-537.5: Y non-finite), that very
+// expression is evaluated in IEEE double (subnormals included, no contraction) on the true values, so Y equals the
+// reference's there: non-finite in the core, of wrong length in the gradual-underflow shell around it.
+__device__ __forceinline__ void normalise_node(const SumParams& P, float x, float y, float z, float cm, float& a, float& b,
+                                               float& c) {
+    const float s = fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z));
+    if (P.uf_enable && log2f(s) - cm < P.uf_thr + 28.f) {
+        const double sc = exp2((double)P.uf_log2_unscale - (double)cm);  // X = X~ * sc; >= 2^-1022 wherever X~ is normal
+        const double xd = __dmul_rn((double)x, sc), yd = __dmul_rn((double)y, sc), zd = __dmul_rn((double)z, sc);
+        const double n = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(xd, xd), __dmul_rn(yd, yd)), __dmul_rn(zd, zd)));
+        a = (float)(xd / n);
+        b = (float)(yd / n);
+        c = (float)(zd / n);
+        return;
+    }
+    const float u = x / s, v = y / s, w = z / s;
+    const float nrm = sqrtf(u * u + v * v + w * w);
+    a = u / nrm;
+    b = v / nrm;
+    c = w / nrm;
+}
+
+
 __global__ void __launch_bounds__(kThreads, 3)
 k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict__ cl_range,
       const float4* __restrict__ src_pos, const float4* __restrict__ src_wn, float* __restrict__ Y, size_t ystride,
@@ -243,24 +270,20 @@ k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict_
     const size_t nloc = ystride;
     if (ix < P.nx && iy < P.ny) {
         if (iz0 < nzl) {
-            float s = fmaxf(fmaxf(fabsf(X00), fabsf(X01)), fabsf(X02));
-            if (P.uf_enable && log2f(s) - cm0 < P.uf_thr) s = __int_as_float(0x7fc00000);  // NaN: see SumParams
-            float a = X00 / s, b = X01 / s, c = X02 / s;
-            float nrm = sqrtf(a * a + b * b + c * c);
+            float a, b, c;
+            normalise_node(P, X00, X01, X02, cm0, a, b, c);
             size_t idx = (size_t)ix + (size_t)iy * P.nx + (size_t)iz0 * P.nx * P.ny;
-            Y[idx] = a / nrm;
-            Y[idx + nloc] = b / nrm;
-            Y[idx + 2 * nloc] = c / nrm;
+            Y[idx] = a;
+            Y[idx + nloc] = b;
+            Y[idx + 2 * nloc] = c;
         }
         if (iz1 < nzl) {
-            float s = fmaxf(fmaxf(fabsf(X10), fabsf(X11)), fabsf(X12));
-            if (P.uf_enable && log2f(s) - cm1 < P.uf_thr) s = __int_as_float(0x7fc00000);
-            float a = X10 / s, b = X11 / s, c = X12 / s;
-            float nrm = sqrtf(a * a + b * b + c * c);
+            float a, b, c;
+            normalise_node(P, X10, X11, X12, cm1, a, b, c);
             size_t idx = (size_t)ix + (size_t)iy * P.nx + (size_t)iz1 * P.nx * P.ny;
-            Y[idx] = a / nrm;
-            Y[idx + nloc] = b / nrm;
-            Y[idx + 2 * nloc] = c / nrm;
+            Y[idx] = a;
+            Y[idx + nloc] = b;
+            Y[idx + 2 * nloc] = c;
         }
     }
     if (pair_counter) {

@@ -13,11 +13,13 @@ struct SumParams {
     float lam2;  // lambda * log2(e)
     float tol;   // tau / lambda (distance units); +inf = keep everything
     int n_clusters;
-    // SHM3D_FLAG_FP64_UNDERFLOW: a node whose largest |component| of the TRUE sum X is below 2^-537.5 gets NaN (the
-    // reference's X.norm() is zero there).  The kernel holds X~ = wscale * 2^(lam2*m) * X, so the test is
-    // log2(max|X~|) - lam2*m < uf_thr with uf_thr = -537.5 + log2(wscale); uf_enable = 0 skips it.
+    // SHM3D_FLAG_FP64_UNDERFLOW: where the TRUE sum X is so small that the reference's X.norm() loses precision or is
+    // zero in double (max|X| < 2^-511 / 2^-537.5), the normalisation is evaluated like the reference's (k_sum.cu,
+    // normalise_node).  The kernel holds X~ = wscale * 2^(lam2*m) * X: log2 max|X| = log2 max|X~| - lam2*m - log2(wscale),
+    // uf_thr = -537.5 + log2(wscale), uf_log2_unscale = -log2(wscale); uf_enable = 0 skips it.
     int uf_enable;
     float uf_thr;
+    float uf_log2_unscale;
 };
 // Y: component-major, component a of local node idx at Y[a*ystride + idx]
 void launch_heat_sum(const SumParams& P, const float4* cl_bounds, const int2* cl_range, const float4* src_pos,
@@ -71,6 +73,8 @@ void launch_fast_integrate_z(const LevelDims& L, float cell, const float* Y_padd
 // deterministic-reduction scratch of the calling context (bound per host thread at every API entry)
 void set_reduction_scratch(double* partials, unsigned int* counter);
 size_t reduction_scratch_doubles();
+// TMA-staged marching stencil kernels (grid_march.cuh): on/off and the SM count of the calling context's device
+void set_march_config(bool enabled, int sm_count);
 
 // generic helpers
 void launch_fill(float* p, size_t n, float v, cudaStream_t s);

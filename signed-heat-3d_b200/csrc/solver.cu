@@ -64,6 +64,7 @@ struct shm3d_ctx {
     DevBuf<float4> d_spos, d_swn, d_cbounds;
     DevBuf<int2> d_crange;
     DevBuf<double> d_pos, d_area, d_nrm;
+    int sm_count = 148;
     PVec Y[1];  // component-major: 3 padded components stored back to back
     DevBuf<float> Ybuf;
     PVec vx, vr, vp, vp2, vq;
@@ -388,6 +389,7 @@ struct Solver {
         use_mg = !(prm->flags & SHM3D_FLAG_NO_MG);
         prof.on = (prm->flags & SHM3D_FLAG_PROFILE) != 0;
         constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
+        set_march_config(!(prm->flags & SHM3D_FLAG_NO_TMA), c->sm_count);
         cmg_from = prm->mg_constrained_from == 0 ? 2 : std::max(0, prm->mg_constrained_from);
         if (const char* e = getenv("SHM3D_CMG_FROM")) cmg_from = atoi(e);
         if (const char* e = getenv("SHM3D_NU_COARSE")) nu_coarse = atoi(e);
@@ -499,6 +501,7 @@ struct Solver {
         P.n_clusters = (int)cs.bounds.size();
         P.uf_enable = (p->flags & SHM3D_FLAG_FP64_UNDERFLOW) ? 1 : 0;
         P.uf_thr = (float)(-537.5 + std::log2(cs.wscale));
+        P.uf_log2_unscale = (float)(-std::log2(cs.wscale));
         SHM3D_CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long), s));
         SHM3D_CUDA_CHECK(cudaMemsetAsync(c->Ybuf.p, 0, 3 * ycomp() * sizeof(float), s));
         pending_sum_timer.reset(new Timer(s));
@@ -904,7 +907,8 @@ struct Solver {
     if (!(ctx)) return SHM3D_ERR_INVALID_ARG;                  \
     try {                                                      \
         SHM3D_CUDA_CHECK(cudaSetDevice((ctx)->device));        \
-        set_reduction_scratch((ctx)->red_partials.p, (ctx)->red_counter.p);
+        set_reduction_scratch((ctx)->red_partials.p, (ctx)->red_counter.p); \
+        set_march_config(true, (ctx)->sm_count);
 #define SHM3D_API_END(ctx)                                     \
     }                                                          \
     catch (const shm3d::Error& e) {                            \
@@ -944,6 +948,7 @@ static int create_common(shm3d_ctx** out, int device, int rank, int world, const
     try {
         SHM3D_CUDA_CHECK(cudaSetDevice(device));
         SHM3D_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SHM3D_CUDA_CHECK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         set_host_ranks_hint(world);
         c->red_partials.alloc(reduction_scratch_doubles());
         c->red_counter.alloc(1);
@@ -1189,6 +1194,56 @@ int shm3d_debug_factor_solve(const shm3d_params* p, int64_t M, const double* pos
         return e.code;
     }
     return SHM3D_OK;
+}
+
+// One stencil operation of the PCG / V-cycle on caller-supplied PADDED vectors ((k1-k0) + 2 planes of nx*ny floats each,
+// ghost planes first and last), once through the row-streaming kernels and once through the TMA-staged marching
+// kernels: the GPU tests require identical fields.  op: 0 update_p_stencil (in0 = z, in1 = p_old; scal = mean, beta),
+// 1 smooth (in0 = x, pw = b; scal = mean, omega), 2 smooth + dots, 3 residual, 4 smooth01 (in0 = b; scal = mean, omega, omega2).
+int shm3d_debug_stencil_op(shm3d_ctx* ctx, int32_t op, int32_t nx, int32_t ny, int32_t nz, int32_t k0, int32_t k1,
+                           const float* in0, const float* in1, const float* pw, const double* scal, int32_t use_tma,
+                           float* out0, float* out1, double* red, int32_t reps, double* ms_per_launch) {
+    SHM3D_API_BEGIN(ctx)
+    const LevelDims L{nx, ny, nz, k0, k1};
+    if (nx < 4 || ny < 4 || k1 <= k0 || k0 < 0 || k1 > nz || !in0 || !out0 || !scal) throw Error(SHM3D_ERR_INVALID_ARG, "bad argument");
+    const size_t pl = L.plane(), tot = L.n() + 2 * pl;
+    cudaStream_t s = ctx->stream;
+    DevBuf<float> d0(tot), d1(tot), dp(tot), o0(tot), o1(tot);
+    DevBuf<double> sc(8);
+    SHM3D_CUDA_CHECK(cudaMemsetAsync(o0.p, 0, tot * 4, s));
+    SHM3D_CUDA_CHECK(cudaMemsetAsync(o1.p, 0, tot * 4, s));
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(d0.p, in0, tot * 4, cudaMemcpyHostToDevice, s));
+    if (in1) SHM3D_CUDA_CHECK(cudaMemcpyAsync(d1.p, in1, tot * 4, cudaMemcpyHostToDevice, s));
+    if (pw) SHM3D_CUDA_CHECK(cudaMemcpyAsync(dp.p, pw, tot * 4, cudaMemcpyHostToDevice, s));
+    // device scalars: [0] = sum (mean * N), [1] = rho_new (= beta), [2] = rho_old (= 1), [4..5] reductions
+    const double ng = (double)nx * ny * nz;
+    const double h[8] = {scal[0] * ng, scal[1], 1.0, 0, 0, 0, 0, 0};
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(sc.p, h, sizeof(h), cudaMemcpyHostToDevice, s));
+    set_march_config(use_tma != 0, ctx->sm_count);
+    float *a = d0.p + pl, *b = d1.p + pl, *w = dp.p + pl, *x0 = o0.p + pl, *x1 = o1.p + pl;
+    auto run = [&]() {
+        switch (op) {
+            case 0: launch_update_p_stencil(L, x0, b, a, x1, sc.p, ng, sc.p + 1, sc.p + 2, 0, sc.p + 4, s); break;
+            case 1: launch_mg_smooth(L, x0, a, w, sc.p, ng, (float)scal[1], s); break;
+            case 2: launch_mg_smooth_dot(L, x0, a, w, sc.p, ng, (float)scal[1], sc.p + 4, s); break;
+            case 3: launch_mg_residual(L, a, w, sc.p, ng, x0, s); break;
+            case 4: launch_mg_smooth01(L, x0, a, sc.p, ng, (float)scal[1], (float)scal[2], s); break;
+            default: throw Error(SHM3D_ERR_INVALID_ARG, "unknown op");
+        }
+    };
+    run();
+    if (reps > 0 && ms_per_launch) {  // device time per launch (CUDA events on the solver's stream)
+        Timer t(s);
+        t.start();
+        for (int i = 0; i < reps; i++) run();
+        t.stop();
+        *ms_per_launch = t.ms() / reps;
+    }
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(out0, o0.p, tot * 4, cudaMemcpyDeviceToHost, s));
+    if (out1) SHM3D_CUDA_CHECK(cudaMemcpyAsync(out1, o1.p, tot * 4, cudaMemcpyDeviceToHost, s));
+    if (red) SHM3D_CUDA_CHECK(cudaMemcpyAsync(red, sc.p + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
+    SHM3D_API_END(ctx)
 }
 
 // ---- row N3: consumer of phi on the device (isosurface.cu) -------------------------------------------------------

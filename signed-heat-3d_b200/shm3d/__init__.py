@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libshm3d_grid.so")
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_FACTORIZATION, ERR_NO_CONVERGENCE, ERR_NCCL = range(7)
 FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_PROFILE = 1, 2, 4, 8, 16, 32
+FLAG_NO_TMA = 128         # diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones
 FLAG_FP64_UNDERFLOW = 64  # reproduce the reference's fp64 underflow in X.norm() at far nodes (include/shm3d_grid.h)
 
 
@@ -66,7 +67,7 @@ EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
            "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points", "shm3d_point_weights",
            "shm3d_debug_local_ring", "shm3d_debug_tufted_weights", "shm3d_isosurface", "shm3d_isosurface_fetch",
-           "shm3d_isosurface_device", "shm3d_slice"]
+           "shm3d_isosurface_device", "shm3d_slice", "shm3d_debug_stencil_op"]
 
 _lib = None
 
@@ -109,6 +110,7 @@ def lib():
         L.shm3d_isosurface_fetch.argtypes = [vp, fp, C.POINTER(C.c_uint32)]
         L.shm3d_isosurface_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
         L.shm3d_slice.argtypes = [vp, PP, vp, C.c_int32, dp, dp, dp, C.c_int32, C.c_int32, fp]
+        L.shm3d_debug_stencil_op.argtypes = [vp] + [C.c_int32] * 6 + [fp, fp, fp, dp, C.c_int32, fp, fp, dp, C.c_int32, dp]
         L.shm3d_ctx_stream.argtypes = [vp]
         L.shm3d_ctx_stream.restype = vp
         L.shm3d_host_alloc.argtypes = [C.c_size_t]
@@ -400,6 +402,22 @@ class Context:
         return out
 
 
+    def debug_stencil_op(self, op, dims, k0, k1, in0, in1, pw, scal, use_tma, reps=0):
+        """One PCG / V-cycle stencil operation on padded float32 vectors [(k1-k0)+2, ny, nx] (include/shm3d_grid.h)."""
+        nx, ny, nz = dims
+        a = np.ascontiguousarray(in0, dtype=np.float32)
+        b = None if in1 is None else np.ascontiguousarray(in1, dtype=np.float32)
+        w = None if pw is None else np.ascontiguousarray(pw, dtype=np.float32)
+        sc = np.zeros(4)
+        sc[:len(scal)] = scal
+        o0, o1, red = np.empty_like(a), np.empty_like(a), np.zeros(2)
+        ms = C.c_double(0.0)
+        self._check(lib().shm3d_debug_stencil_op(self._h, op, nx, ny, nz, k0, k1, _fp(a), None if b is None else _fp(b),
+                                                 None if w is None else _fp(w), _dp(sc), 1 if use_tma else 0, _fp(o0), _fp(o1),
+                                                 _dp(red), reps, C.byref(ms)))
+        return (o0, o1, red, ms.value) if reps else (o0, o1, red)
+
+
 def slab_range(rank, world, nz):
     k0, k1 = C.c_int32(), C.c_int32()
     rc = lib().shm3d_slab_range(rank, world, nz, C.byref(k0), C.byref(k1))
@@ -437,7 +455,7 @@ class SignedHeatGridSolver:
 
     def __init__(self, device=0, context: Context | None = None, reuse_output: bool = True):
         self.VERBOSE = False
-        self.reference_underflow = False   # SHM3D_FLAG_FP64_UNDERFLOW (include/shm3d_grid.h); off in this version
+        self.reference_underflow = True    # SHM3D_FLAG_FP64_UNDERFLOW (include/shm3d_grid.h): follow the reference's X.norm() underflow
         # True: computeDistance returns a view of a solver-owned page-locked buffer that the NEXT call overwrites
         # (fast D2H, no per-call 1 GB allocation); False: every call returns a freshly allocated array it owns.
         self.reuse_output = reuse_output
@@ -453,6 +471,8 @@ class SignedHeatGridSolver:
             p.flags |= FLAG_FAST
         if self.reference_underflow:
             p.flags |= FLAG_FP64_UNDERFLOW
+        else:
+            p.flags &= ~FLAG_FP64_UNDERFLOW
         n = self.ctx.local_n(p)
         if not self.reuse_output:
             phi, st = self.ctx.solve(p, pos, nrm, area)

@@ -110,7 +110,7 @@ static bool write_npy(const std::string& path, const std::vector<double>& v, siz
 static void usage() {
     std::fprintf(stderr,
                  "usage: shm3d_cli INPUT.{obj,pc} [-g|--grid] [--h K] [--t TCOEF] [-f|--fast] [-V|--verbose] [--device D]\n"
-                 "                 [-o OUT.{npy,raw}] [--isoval C --iso-out SURFACE.obj] [--reference-underflow] [--dry-run]\n"
+                 "                 [-o OUT.{npy,raw}] [--isoval C --iso-out SURFACE.obj] [--no-reference-underflow] [--dry-run]\n"
                  "  Generalized signed distance to INPUT on an nx^3 grid, nx = 16*2^K (B200 grid solver; %s)\n",
                  shm3d_version());
 }
@@ -119,7 +119,7 @@ int main(int argc, char** argv) {
     std::string input, output, iso_output;
     float isoval = 0.f;
     shm3d::SignedHeat3DOptions opts;
-    bool verbose = false, dry = false, ref_underflow = false;
+    bool verbose = false, dry = false, ref_underflow = true;
     int device = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -140,7 +140,8 @@ int main(int argc, char** argv) {
         else if (a == "-o") output = need("-o");
         else if (a == "--isoval") isoval = (float)std::atof(need("--isoval"));
         else if (a == "--iso-out") iso_output = need("--iso-out");
-        else if (a == "--reference-underflow") ref_underflow = true;
+        else if (a == "--reference-underflow") ref_underflow = true;  // (the default)
+        else if (a == "--no-reference-underflow") ref_underflow = false;
         else if (a == "--dry-run") dry = true;
         else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); usage(); return 2; }
         else input = a;
