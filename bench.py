@@ -9,16 +9,21 @@ B200-native signed-heat grid solver, and the reference arm beside it.
 One "step" = one complete computeDistance over the workload (BASELINE.json metric):
   value  : N_grid_nodes * K / device-event time of K steps, sources already resident in HBM (shm3d_solve_device),
            result left on the device as float32 -- max over ranks;
-  e2e    : the same through the reference-facing interface (SignedHeatGridSolver.computeDistance mirror ->
-           shm3d_solve) with HOST buffers: H2D of the sources and D2H of the double field inside the timed region;
-  roofline     : the PCG fused p-update + stencil-apply + dot kernel (HBM-bound; 16 B/node/launch algorithmic)
-  roofline_sum : the Step 1-2 summation kernel (SFU-bound: 2 MUFU per evaluated pair at 16/clk/SM)
+  e2e    : the same through the public, reference-facing call SignedHeatGridSolver.computeDistance(V, F, options)
+           (-> shm3d_prepare_mesh -> shm3d_solve): the mesh-level host half (rows a4-a6), H2D of the sources and D2H of
+           the double field are all inside the timed region;
+  roofline     : the dominant kernel, k_sum (Steps 1-2; SFU-bound: 2 MUFU per evaluated pair at 16/clk/SM);
+  roofline_pcg : the PCG's fused p-update + stencil-apply + dot kernel (HBM-bound; 16 B/node/launch algorithmic);
+  pcg_whole    : the whole Step-3 iteration against the HBM roofline, by SURVEY 8(d)'s 44 B/node/iteration formula and
+                 by the bytes the V-cycle-preconditioned iteration really has to move;
   cpu_baseline : the reference's own computeDistance (oracle/_ref: its sources compiled against a shim) on the
                  workload's sources at 16^3, single-threaded; cpu_baseline_port_all_threads: the oracle's C port of the
                  Step 1-2 loop with OpenMP on a bounded sample of the real grid.
 N > 1: the grid is z-slab partitioned over the ranks (NCCL halo exchange + all-reduces).  Default workloads keep
 ~512^3 nodes per GPU (512^3, 640^3, 768^3, 1024^3 at 1, 2, 4, 8 GPUs -> "scaling": "weak"); --workload sphereN fixes
-the grid for strong-scaling runs.
+the grid for strong-scaling runs.  At N > 1 the line also carries `dist_parity` (the slab-partitioned solve of a 256^3
+case against the single-GPU solve of rank 0: rel-L2, iteration counts) and `strong` (the same grid solved by rank 0
+alone -> speed-up of the N-GPU run).
 """
 import argparse
 import json
@@ -198,13 +203,15 @@ def reference_build_sample(name):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle/_ref: its translation units compiled unmodified), on
+    this box's host cores.  Nothing of the product is imported or loaded here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import shm3d
-    p, pos, nrm, area, desc = prepare(args.workload)  # host-only calls (no device code)
     from oracle import shm_oracle as o
-    M = len(area)
+    V, F, n_grid, desc = make_workload(args.workload)
+    M = len(F)
+    scaling = "weak" if args.workload == DEFAULT_BY_GPUS.get(args.gpus, "sphere512") else "strong"
     first = reference_build_sample(args.workload)  # also serves as warm-up
     if first is not None:
         t_tot, n_tot, text = 0.0, 0, first[2]
@@ -215,33 +222,48 @@ def run_reference(args):
         v = n_tot / t_tot
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
-                "scaling": "weak" if args.workload == DEFAULT_BY_GPUS.get(args.gpus, "sphere512") else "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "grid": [p.nx, p.ny, p.nz], "sources": M},
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "same_config": False, "extrapolated": True,
+                "config": {"workload": f"16^3 PROXY of: {desc} -- the workload's {M} sources on the reference's smallest grid "
+                                       f"(hCoef 0 = 16^3); its sparse LU of the KKT system is infeasible beyond 64^3, so "
+                                       f"the {n_grid}^3 grid itself cannot be run; nodes/s at 16^3 is an upper bound for it",
+                           "grid": [16, 16, 16], "grid_of_the_gpu_arm": [n_grid] * 3, "sources": M},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "per step: " + text},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
+    # oracle/_ref absent: the oracle's port of the Step 1-2 loop on a bounded sample of the real grid
+    s_ = o.mesh_sources(V, F.tolist() if hasattr(F, "tolist") else F)
+    hc = max(int(round(np.log2(n_grid / 16.0))), 0)
+    g = o.make_grid(s_["centroid"], s_["radius"], hc)
+    lam = o.lambda_from_h(s_["h"])
     threads = o.max_threads()
-    rows = cpu_sample_plan(p, M, threads, seconds=6.0)
+    rows = int(max(1, min(g.ny, round(7e7 * threads * 6.0 / (g.nx * float(M))))))
+
+    def sample(nrows):
+        k, j0 = g.nz // 2, max(0, g.ny // 2 - nrows // 2)
+        t0 = time.perf_counter()
+        Y = o.step12_box(g, lam, s_["pos"], s_["nrm"], s_["area"], j0, j0 + nrows, k, k + 1, threads=threads)
+        dt = time.perf_counter() - t0
+        assert np.isfinite(Y).all()
+        return nrows * g.nx, dt
     for _ in range(args.warmup):
-        cpu_step12_sample(p, pos, nrm, area, max(1, rows // 8), threads)
+        sample(max(1, rows // 8))
     t_tot, n_tot = 0.0, 0
     for _ in range(args.steps):
-        n, dt = cpu_step12_sample(p, pos, nrm, area, rows, threads)
+        n, dt = sample(rows)
         n_tot += n
         t_tot += dt
     v = n_tot / t_tot
-    sample = (f"per step: Steps 1-2 (fp64 oracle port of the reference loop, OpenMP, {threads} threads) on {rows} rows "
-              f"of one plane = {rows * p.nx} nodes x {M} sources; Step 3 excluded (reference sparse LU infeasible "
-              f"beyond 64^3) -> upper bound on the CPU path's nodes/s; the reference itself is single-threaded and "
-              f"cannot be compiled here (Eigen not vendored)")
+    text = (f"per step: Steps 1-2 (fp64 oracle port of the reference loop, OpenMP, {threads} threads) on {rows} rows "
+            f"of one plane = {rows * g.nx} nodes x {M} sources; Step 3 excluded (reference sparse LU infeasible "
+            f"beyond 64^3) -> upper bound on the CPU path's nodes/s; oracle/_ref (the reference's own source) is absent")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
-            "scaling": "weak" if args.workload == DEFAULT_BY_GPUS.get(args.gpus, "sphere512") else "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "grid": [p.nx, p.ny, p.nz], "sources": M},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "same_config": False, "extrapolated": True,
+            "config": {"workload": "Steps 1-2 ONLY on a bounded sample of: " + desc, "grid": [g.nx, g.ny, g.nz], "sources": M},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": text},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -299,6 +321,11 @@ def run_ours(args):
         q.flags |= flags
         return ctx.solve_device(q, d_pos.data_ptr(), d_nrm.data_ptr(), d_area.data_ptr(), d_phi.data_ptr(), M)
 
+    # ---- N > 1: the slab-partitioned solve against the single-GPU solve of the same (256^3) problem, before timing
+    dist_parity = None
+    if world > 1 and not args.no_parity:
+        dist_parity = dist_parity_check(ctx, dist, dev, rank, world, local)
+
     # ---- device-resident arm
     for _ in range(args.warmup):
         step_device()
@@ -342,7 +369,8 @@ def run_ours(args):
         pass
     prof = _Agg()
     for k in ("pcg_stencil_launches", "ms_pcg_stencil", "pairs_evaluated", "pairs_bruteforce", "ms_sum", "ms_pcg_vcycle",
-              "ms_pcg_projector", "ms_pcg_update"):
+              "ms_pcg_projector", "ms_pcg_update", "pcg_vcycles", "pcg_projector_applies", "ms_pcg", "cg_iters",
+              "graph_replays"):
         setattr(prof, k, sum(getattr(st, k) for st in prof_steps))
     hbm_peak, sm_max, peak_src = peaks()
     traffic = None
@@ -352,41 +380,63 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(args.workload, {}).get("pcg_update_p_stencil_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = None
+    roofline_pcg = None
     if prof.pcg_stencil_launches > 0 and prof.ms_pcg_stencil > 0:
         # fused PCG kernel: p <- (z - mean) + beta p ; q = K p ; p.q  -- reads z, p and writes p, q: 4 words = 16 B per node
         # (SURVEY.md section 8(d) counts the unfused pair as 2 + 3 words)
         bytes_per_launch = 16.0 * n_local
         ach = bytes_per_launch * prof.pcg_stencil_launches / (prof.ms_pcg_stencil * 1e-3) / 1e9
-        roofline = {"kernel": "k_row_update_p_stencil (PCG: p update + q = K p + p.q in one pass)", "bound": "hbm", "achieved": ach,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-                    "peak_source": peak_src, "launches": int(prof.pcg_stencil_launches),
-                    "avg_launch_us": 1e3 * prof.ms_pcg_stencil / prof.pcg_stencil_launches,
-                    "algorithmic_bytes_per_launch": bytes_per_launch}
+        roofline_pcg = {"kernel": "k_march<OpUpdateP> (PCG: p update + q = K p + p.q in one TMA-staged pass)", "bound": "hbm",
+                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                        "peak_source": peak_src, "launches": int(prof.pcg_stencil_launches),
+                        "avg_launch_us": 1e3 * prof.ms_pcg_stencil / prof.pcg_stencil_launches,
+                        "algorithmic_bytes_per_launch": bytes_per_launch,
+                        "note": "CUDA-event pairs around the launches of the first PCG iterations of every timed step (the "
+                                "rest of each solve replays the same kernels from a CUDA graph)"}
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
     sfu_peak = 16.0 * 148 * sm_mhz * 1e6  # MUFU ops/s at the clock observed under load
-    roofline_sum = {"kernel": "k_sum (Steps 1-2)", "bound": "sfu", "achieved": 2.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3),
-                    "peak": sfu_peak, "unit": "MUFU op/s", "frac": 2.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3) / sfu_peak,
-                    "pairs_evaluated": int(prof.pairs_evaluated // args.steps),
-                    "pairs_bruteforce": int(prof.pairs_bruteforce // args.steps),
-                    "bruteforce_equivalent_pairs_per_s": prof.pairs_bruteforce / (prof.ms_sum * 1e-3),
-                    "fp32_flops_per_s": 17.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3), "ms": prof.ms_sum / args.steps,
-                    "note": "rank 0 slab" if world > 1 else ""}
+    mufu = 2.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3)
+    roofline = {"kernel": "k_sum (Steps 1-2: heat-kernel summation + normalisation) -- the dominant kernel of the step",
+                "bound": "sfu", "achieved": mufu / 1e9, "peak": sfu_peak / 1e9, "unit": "GMUFU-op/s", "frac": mufu / sfu_peak,
+                "traffic": None, "share_of_step": prof.ms_sum / dev_ms if world == 1 else None,
+                "peak_source": "16 MUFU/clk/SM x 148 SMs x SM clock sampled under load (B300_MICROARCH.md pipe table); "
+                               "not HBM- or tensor-bound: 12 B/node written, no contraction",
+                "algorithmic_ops_per_launch": 2.0 * prof.pairs_evaluated / args.steps,
+                "pairs_evaluated": int(prof.pairs_evaluated // args.steps),
+                "pairs_bruteforce": int(prof.pairs_bruteforce // args.steps),
+                "bruteforce_equivalent_pairs_per_s": prof.pairs_bruteforce / (prof.ms_sum * 1e-3),
+                "fp32_flops_per_s": 17.0 * prof.pairs_evaluated / (prof.ms_sum * 1e-3), "ms": prof.ms_sum / args.steps,
+                "note": "rank 0 slab" if world > 1 else ""}
+    # the whole Step 3 against the HBM roofline: (a) SURVEY 8(d)'s textbook count, 44 B per node and CG iteration;
+    # (b) what one V(2,2)-preconditioned iteration has to move: fine level 8+12+4.5+8.5+12+12 (V-cycle) + 16 (p/q) + 24
+    # (x/r) = 97 B/node, x 8/7 for the coarser levels' share of the V-cycle part
+    its = max(1, prof.cg_iters)
+    pcg_s = prof.ms_pcg * 1e-3
+    b_vc = (57.0 * 8.0 / 7.0 + 40.0) * n_local
+    pcg_whole = {"ms_per_iteration": prof.ms_pcg / its, "iterations": int(prof.cg_iters // args.steps),
+                 "survey_44B": {"GBps": 44.0 * n_local * its / pcg_s / 1e9, "frac": 44.0 * n_local * its / pcg_s / 1e9 / hbm_peak},
+                 "vcycle_inclusive": {"bytes_per_node_iteration": b_vc / n_local, "GBps": b_vc * its / pcg_s / 1e9,
+                                      "frac": b_vc * its / pcg_s / 1e9 / hbm_peak},
+                 "graph_replays_per_step": prof.graph_replays / args.steps}
 
-    # ---- end-to-end arm through the reference-facing interface, host buffers (pinned result buffer owned by the solver)
+    # ---- end-to-end arm: the public, reference-facing call with HOST inputs -- computeDistance(V, F, options) runs the
+    # mesh-level host half (rows a4-a6: areas, normals, barycentres, mean edge length, grid), uploads the sources, solves,
+    # and downloads the double field into the solver-owned page-locked buffer -- all inside the timed region
     solver = shm3d.SignedHeatGridSolver(context=ctx)
-    opts = shm3d.SignedHeat3DOptions()
-    # page-locked host copies of the source arrays (the H2D inside every step starts from pinned memory)
-    pins = [shm3d.PinnedArray(a.shape) for a in (pos, nrm, area)]
-    for pin, a in zip(pins, (pos, nrm, area)):
-        pin.array[...] = a
-    h_pos, h_nrm, h_area = (pin.array for pin in pins)
+    Vw, Fw, n_w, _ = make_workload(args.workload)
+    hc = int(round(np.log2(n_w / 16.0)))
+    opts = shm3d.SignedHeat3DOptions(hCoef=max(hc, 0))
+    producible = (16 << max(hc, 0)) == n_w   # grids the reference itself produces: 16 * 2^h
 
     def step_host():
-        # the mesh-level host work of the adapter (areas/normals/barycentres, rows a4-a6) is done once above, like the
-        # device arm; each step uploads the flat source arrays and downloads the double field
-        q = shm3d.Params.from_buffer_copy(p)
-        return solver._finish(q, h_pos, h_nrm, h_area, opts)
+        if producible:
+            return solver.computeDistance(Vw, Fw, opts)
+        # 640^3 / 768^3 (weak-scaling fillers) are not 16 * 2^h: same host half, then the box resampled to n nodes per axis
+        q, ps, nr, ar, _ = shm3d.prepare_mesh(Vw, Fw, hCoef=max(hc, 0))
+        side = q.cell * (q.nx - 1)
+        q.nx = q.ny = q.nz = n_w
+        q.cell = side / (n_w - 1)
+        return solver._finish(q, ps, nr, ar, opts)
 
     for _ in range(min(args.warmup, 2)):
         step_host()
@@ -406,7 +456,15 @@ def run_ours(args):
     e2e_value = N * args.steps / float(te[0])
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(7 * 8 * M * world),
            "d2h_bytes_per_step": int(8 * N), "ms_per_step": 1e3 * float(te[0]) / args.steps,
-           "api": "shm3d.SignedHeatGridSolver -> shm3d_solve (host double arrays in, double field out)"}
+           "api": "shm3d.SignedHeatGridSolver.computeDistance(V, F, options) -> shm3d_prepare_mesh + shm3d_solve: host "
+                  "vertex/face arrays in, double field out; the a4-a6 host half (~40 ms at 1e5 faces), H2D and D2H are all "
+                  "INSIDE the timed region" + ("" if producible else " (grid resampled to a non-16*2^h size via the class's "
+                  "internal entry after the same host half)")}
+
+    # ---- N > 1: the same grid on ONE GPU (rank 0 alone) -> strong-scaling speed-up of this run
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = strong_block(p, d_pos, d_nrm, d_area, M, N, dev_ms / args.steps, local, rank, world, barrier)
 
     default_wl = args.workload == DEFAULT_BY_GPUS.get(world, "sphere512")
     scaling = "weak" if default_wl else "strong"
@@ -430,16 +488,21 @@ def run_ours(args):
                            "nodes_per_gpu": N // world, "scaling_note": scaling_note,
                            "cull_tau": 10.0, "timing": "CUDA events on the solver's stream, max over ranks"},
                 "wall_ms_per_step": wall_ms / args.steps, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roofline, "roofline_sum": roofline_sum, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roofline, "roofline_pcg": roofline_pcg, "pcg_whole": pcg_whole,
+                "dist_parity": dist_parity, "strong": strong, "cpu_baseline": cpu,
                 "cpu_baseline_port_all_threads": cpu_port,
                 "stages_ms": {"h2d+cluster": stats.ms_h2d, "sum(step1-2)": stats.ms_sum, "rhs": stats.ms_rhs,
                               "constraints+factor(host, overlapped with sum)": stats.ms_constraints,
                               "pcg": stats.ms_pcg, "shift": stats.ms_shift, "total": stats.ms_total},
                 "pcg": {"iters": int(stats.cg_iters), "rel_residual": stats.cg_rel_residual,
                         "m_constraints": int(stats.m_constraints),
-                        "profiled_ms_per_step": {"stencil": prof.ms_pcg_stencil / args.steps, "vcycle": prof.ms_pcg_vcycle / args.steps,
-                                                 "projector": prof.ms_pcg_projector / args.steps,
-                                                 "update": prof.ms_pcg_update / args.steps}},
+                        "tail_ops": int(stats.tail_ops), "graph_replays": int(stats.graph_replays),
+                        "profiled_ms_per_iteration": {
+                            "p_update+stencil": prof.ms_pcg_stencil / max(1, prof.pcg_stencil_launches),
+                            "vcycle": prof.ms_pcg_vcycle / max(1, prof.pcg_vcycles),
+                            "projector(2 applications)": 2 * prof.ms_pcg_projector / max(1, prof.pcg_projector_applies),
+                            "x/r update": prof.ms_pcg_update / max(1, prof.pcg_stencil_launches),
+                            "whole iteration (pcg ms / iterations, graph replay)": prof.ms_pcg / its}},
                 "checksum": checksum}
         if world == 1 and not args.no_cpu:
             line["consumer_n3"] = consumer_leg(min(p.nx, 512))
@@ -447,6 +510,61 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+def dist_parity_check(ctx, dist, dev, rank, world, local):
+    """sphere256 solved on the `world` z-slabs and by rank 0 alone: the slabs are gathered on the ranks and compared."""
+    import torch
+    import shm3d
+    if 256 % world:
+        return {"error": f"256 planes do not split evenly over {world} ranks"}
+    p, pos, nrm, area, _ = prepare("sphere256")
+    phi_slab, st = ctx.solve(p, pos, nrm, area)
+    t = torch.from_numpy(np.ascontiguousarray(phi_slab, dtype=np.float64)).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = None
+    if rank == 0:
+        solo = shm3d.Context(local)
+        full, st1 = solo.solve(p, pos, nrm, area)
+        solo.close()
+        joined = torch.cat(parts).cpu().numpy()
+        err = float(np.linalg.norm(joined - full) / np.linalg.norm(full))
+        out = {"workload": "sphere256 (1e5-triangle sphere, 256^3)", "rel_l2_vs_single_gpu": err,
+               "max_abs_diff": float(np.abs(joined - full).max()), "iters_dist": int(st.cg_iters),
+               "iters_single": int(st1.cg_iters), "ranks": world}
+    dist.barrier()
+    return out
+
+
+def strong_block(p, d_pos, d_nrm, d_area, M, N, ms_per_step_dist, local, rank, world, barrier):
+    """The SAME grid solved by rank 0 alone (one warm-up + one timed step, CUDA events on its stream)."""
+    import torch
+    import shm3d
+    out = None
+    if rank == 0:
+        try:
+            solo = shm3d.Context(local)
+            d_phi = torch.empty(N, dtype=torch.float32, device=d_pos.device)
+            st = None
+            ms = []
+            for i in range(2):
+                stream = torch.cuda.ExternalStream(solo.stream, device=d_pos.device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                st = solo.solve_device(shm3d.Params.from_buffer_copy(p), d_pos.data_ptr(), d_nrm.data_ptr(),
+                                       d_area.data_ptr(), d_phi.data_ptr(), M)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            solo.close()
+            out = {"grid": [p.nx, p.ny, p.nz], "ms_per_step_1gpu": ms[-1], "ms_per_step_this_run": ms_per_step_dist,
+                   "speedup": ms[-1] / ms_per_step_dist, "gpus": world, "iters_1gpu": int(st.cg_iters),
+                   "stages_ms_1gpu": {"sum": st.ms_sum, "pcg": st.ms_pcg, "constraints(host)": st.ms_constraints}}
+        except Exception as e:  # e.g. the grid does not fit one GPU
+            out = {"error": repr(e)[:300]}
+    barrier()
+    return out
 
 
 def consumer_leg(n):
@@ -472,6 +590,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="default: ~512^3 nodes per GPU (sphere512 / 640 / 768 / 1024 at 1 / 2 / 4 / 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the dist_parity block")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling block")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = DEFAULT_BY_GPUS.get(args.gpus, "sphere512")

@@ -64,6 +64,10 @@ extern "C" {
                                         * adapter and the class mirrors (a drop-in returns what the reference returns); a
                                         * caller filling shm3d_params by hand opts in. */
 #define SHM3D_FLAG_NO_TMA 128u          /* diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones */
+#define SHM3D_FLAG_NO_CLUSTER_TAIL 256u /* diagnostics: every multigrid level / projector tree level as its own launch instead of
+                                          the single-launch cluster programs (csrc/mg_tail.cuh) */
+#define SHM3D_FLAG_NO_GRAPH 512u        /* diagnostics: launch every PCG iteration kernel by kernel instead of replaying the
+                                          captured CUDA graph */
 #define SHM3D_FLAG_PLAIN_MG 16u        /* unconstrained Poisson V-cycle as preconditioner, projector on the fine level only */
 
 typedef struct shm3d_ctx shm3d_ctx;
@@ -107,6 +111,10 @@ typedef struct shm3d_stats {
     double ms_pcg_projector;  /* device time inside fine-level projector applications, summed */
     int64_t pcg_projector_applies;
     double ms_pcg_update;     /* device time inside the fused x/r update kernel, summed */
+    int64_t pcg_vcycles;      /* V-cycles the ms_pcg_vcycle sum covers (SHM3D_FLAG_PROFILE times the first iterations only;
+                                 the rest of the solve replays a CUDA graph) */
+    int32_t tail_ops;         /* ops of the V-cycle tail's cluster program (0: every level runs as separate launches) */
+    int32_t graph_replays;    /* PCG iterations executed as CUDA-graph replays */
 } shm3d_stats;
 
 /* Context: one per GPU.  device = CUDA ordinal.  Returns SHM3D_ERR_CUDA when no usable device. */

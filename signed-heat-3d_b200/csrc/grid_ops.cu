@@ -15,8 +15,11 @@
 // Reductions are fp64 and deterministic: one partial per CTA, the last CTA to finish (ticket) folds them in a fixed
 // order.
 #include <algorithm>
+#include <functional>
 
-#include "kernels.cuh"
+#include <cooperative_groups.h>
+
+#include "proj_dev.cuh"
 
 namespace shm3d {
 
@@ -571,6 +574,7 @@ inline unsigned int nblk_rows(const LevelDims& L) {
 thread_local bool g_march_disabled = false;
 thread_local int g_march_sms = 148;
 #include "grid_march.cuh"
+#include "mg_tail.cuh"
 // ---------------------------------------------------------------- fastIntegration (reference integrateGreedily, :224-275)
 // The reference runs a FIFO breadth-first search from node (0,0,0), visiting neighbours in the order -x,+x,-y,+y,-z,+z,
 // and sets phi[q] = phi[p] + normalize(Y_p + Y_q) . (q - p) for the first p that reaches q.  On the full box the BFS
@@ -783,6 +787,25 @@ void launch_fast_integrate_z(const LevelDims& L, float cell, const float* Y, siz
     k_fast_z<<<(unsigned)((L.plane() + kT - 1) / kT), kT, 0, s>>>(L, cell, Y, cs, phi);
     POST();
 }
+void launch_cluster_program(const TailOp* d_ops, int n_ops, float* v, const float* w, const double* shift_num,
+                            double shift_den, cudaStream_t s) {
+    if (n_ops <= 0) return;
+    const int cs = tail_cluster_size();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(kTailThreads);
+    cfg.dynamicSmemBytes = kTailSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = cs;
+    at.val.clusterDim.y = at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    SHM3D_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_cluster_program, d_ops, n_ops, v, w, shift_num, shift_den));
+    POST();
+}
+
 void launch_mg_coarse_solve(int n3, const float* pinv, const float* b, float* x, cudaStream_t s) {
     k_mg_coarse<<<1, 512, 0, s>>>(n3, pinv, b, x);
     POST();

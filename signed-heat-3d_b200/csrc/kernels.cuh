@@ -110,7 +110,38 @@ void launch_mg_prolong_add(const LevelDims& Lf, const LevelDims& Lc, float* x_pa
 // coarsest level: x = Kc^+ b via a precomputed dense pseudo-inverse (n^3 <= 512 unknowns)
 void launch_mg_coarse_solve(int n3, const float* pinv, const float* b, float* x, cudaStream_t s);
 
-// ---------------------------------------------------------------- constraints / projector (projector.cu)
-struct DeviceConstraints;  // defined in projector.cuh
+// ---------------------------------------------------------------- cluster programs (mg_tail.cuh)
+// A sequence of latency-bound multigrid / projector operations executed by ONE launch of one thread-block cluster,
+// with the hardware cluster barrier between consecutive ops.  Vector operands are interior pointers of padded level
+// vectors; kTailSlotV / kTailSlotW stand for the v / w arguments of the launch.
+struct ProjDev;  // proj_dev.cuh
+enum TailCode : int {
+    kTSmooth0 = 0,  // o = omega a / d                    (level L)
+    kTSmooth,       // o = b + omega (a - K'b) / d        (level L)
+    kTResidual,     // o = a - K'b                        (level L)
+    kTRestrict,     // o (level Lc) = 0.5 P^T a (level L)
+    kTProlong,      // o (level L) += P a (level Lc)
+    kTCoarse,       // o = pinv(a) b, dense h x h
+    kTCopy,         // o = a                              (level L)
+    kTGather,       // proj: rhs = A (a - b - shift); h != 0: shift = the launch's *shift_num / shift_den
+    kTFwd,          // proj: forward sweep of tree height h
+    kTBwd,          // proj: backward sweep of tree height h
+    kTScatter       // proj: o -= D^-1 A^T sol
+};
+struct TailOp {
+    int code;
+    int h;
+    float omega;
+    int reserved;
+    LevelDims L, Lc;
+    const float* a;
+    const float* b;
+    float* o;
+    const ProjDev* proj;
+};
+#define kTailSlotV (reinterpret_cast<const float*>(uintptr_t(8)))
+#define kTailSlotW (reinterpret_cast<const float*>(uintptr_t(16)))
+void launch_cluster_program(const TailOp* d_ops, int n_ops, float* v, const float* w, const double* shift_num,
+                            double shift_den, cudaStream_t s);
 
 }  // namespace shm3d

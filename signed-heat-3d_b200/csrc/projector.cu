@@ -12,7 +12,7 @@
 
 #include <cooperative_groups.h>
 
-#include "projector.cuh"
+#include "proj_dev.cuh"
 
 namespace shm3d {
 
@@ -273,175 +273,27 @@ void set_host_ranks_hint(int ranks_on_node) { g_ranks_on_node = std::max(1, rank
 // ================================================================================================
 namespace {
 
-__global__ void k_proj_gather(int m, const int64_t* __restrict__ rnode, const double* __restrict__ rw,
-                              const int* __restrict__ rperm, const float* __restrict__ v, const float* __restrict__ w,
-                              const double* shift_num, double shift_den, double* __restrict__ rhs) {
+__global__ void k_proj_gather(ProjDev A, const float* __restrict__ v, const float* __restrict__ w, const double* shift_num,
+                              double shift_den) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= m) return;
-    const double shift = shift_num ? *shift_num / shift_den : 0.0;
-    double acc = 0;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        int64_t n = rnode[(size_t)r * 8 + c];
-        if (n >= 0) {
-            double val = (double)v[n] - shift;
-            if (w) val -= (double)w[n];
-            acc += rw[(size_t)r * 8 + c] * val;
-        }
-    }
-    rhs[rperm[r]] = acc;
+    if (r >= A.m) return;
+    proj_gather_row(A, r, v, w, shift_num ? *shift_num / shift_den : 0.0);
 }
 
-using NodeDescD = ProjNodeDesc;
-
-// forward: for every row R of every supernode at this height:  val = <FWD[R, 0:s], v[s0:s0+s]>;
-// R < s -> y[s0+R] = val ; else v[B[R-s]] -= val
-__global__ void k_proj_fwd(int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local,
-                           const NodeDescD* __restrict__ nodes, const double* __restrict__ mat,
-                           const int* __restrict__ bidx, double* v, double* __restrict__ y) {
+// one warp per matrix row of the supernodes at one tree height (proj_dev.cuh)
+__global__ void k_proj_fwd(ProjDev A, int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local) {
     int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (R >= n_rows) return;
-    const NodeDescD nd = nodes[row_node[R]];
-    const int rl = row_local[R];
-    const double* row = mat + nd.fwd + (long long)rl * nd.s;
-    const double* x = v + nd.s0;
-    double acc = 0;
-    const int cend = rl < nd.s ? rl + 1 : nd.s;  // W is lower triangular
-    for (int c = lane; c < cend; c += 32) acc += row[c] * x[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-        if (rl < nd.s)
-            y[nd.s0 + rl] = acc;
-        else
-            atomicAdd(&v[bidx[nd.bidx + rl - nd.s]], -acc);
-    }
+    if (R < n_rows) proj_fwd_row(A, row_node, row_local, R, threadIdx.x & 31);
 }
 
-// backward: x[s0+R] = <BWD[R, 0:s], y[s0:]> + <BWD[R, s:s+b], x[B]>
-__global__ void k_proj_bwd(int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local,
-                           const NodeDescD* __restrict__ nodes, const double* __restrict__ mat,
-                           const int* __restrict__ bidx, const double* __restrict__ y, double* x) {
+__global__ void k_proj_bwd(ProjDev A, int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local) {
     int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (R >= n_rows) return;
-    const NodeDescD nd = nodes[row_node[R]];
-    const int rl = row_local[R];
-    const int f = nd.s + nd.b;
-    const double* row = mat + nd.bwd + (long long)rl * f;
-    double acc = 0;
-    for (int c = rl + lane; c < nd.s; c += 32) acc += row[c] * y[nd.s0 + c];  // W^T is upper triangular
-    const int* bi = bidx + nd.bidx;
-    for (int c = lane; c < nd.b; c += 32) acc += row[nd.s + c] * x[bi[c]];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) x[nd.s0 + rl] = acc;
+    if (R < n_rows) proj_bwd_row(A, row_node, row_local, R, threadIdx.x & 31);
 }
 
-__global__ void k_proj_scatter(int n_touched, const int64_t* __restrict__ tnode, const int* __restrict__ tptr,
-                               const int* __restrict__ trow, const double* __restrict__ tw,
-                               const double* __restrict__ sol, float* __restrict__ v) {
+__global__ void k_proj_scatter(ProjDev A, float* __restrict__ v) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_touched) return;
-    double acc = 0;
-    for (int e = tptr[t]; e < tptr[t + 1]; e++) acc += tw[e] * sol[trow[e]];
-    int64_t n = tnode[t];
-    v[n] = (float)((double)v[n] - acc);
-}
-
-
-// Single-launch projector application: gather, forward sweep, backward sweep and scatter in one cooperative
-// kernel, with grid-wide barriers between the levels of the elimination tree (replaces ~2*height+2 launches).
-struct FusedArgs {
-    int m, n_touched, n_levels;
-    const int64_t* rnode;
-    const double* rw;
-    const int* rperm;
-    const ProjLevelInfo* levels;
-    const int* rowmaps;
-    const ProjNodeDesc* nodes;
-    const double* mat;
-    const int* bidx;
-    const int64_t* tnode;
-    const int* tptr;
-    const int* trow;
-    const double* tw;
-    double *rhs, *y, *sol;
-};
-
-__global__ void __launch_bounds__(256) k_proj_fused(FusedArgs A, float* v, const float* w, const double* shift_num,
-                                                        double shift_den) {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31, gwarp = tid >> 5, nwarps = nthreads >> 5;
-    // gather: rhs = A (v - w - shift)
-    const double shift = shift_num ? *shift_num / shift_den : 0.0;
-    for (int r = tid; r < A.m; r += nthreads) {
-        double acc = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            int64_t n = A.rnode[(size_t)r * 8 + c];
-            if (n >= 0) {
-                double val = (double)v[n] - shift;
-                if (w) val -= (double)w[n];
-                acc += A.rw[(size_t)r * 8 + c] * val;
-            }
-        }
-        A.rhs[A.rperm[r]] = acc;
-    }
-    grid.sync();
-    // forward sweep, leaves first
-    for (int h = 0; h < A.n_levels; h++) {
-        const ProjLevelInfo li = A.levels[h];
-        const int* row_node = A.rowmaps + li.fwd_node;
-        const int* row_local = A.rowmaps + li.fwd_local;
-        for (int R = gwarp; R < li.n_fwd; R += nwarps) {
-            const ProjNodeDesc nd = A.nodes[row_node[R]];
-            const int rl = row_local[R];
-            const double* row = A.mat + nd.fwd + (long long)rl * nd.s;
-            const double* x = A.rhs + nd.s0;
-            double acc = 0;
-            const int cend = rl < nd.s ? rl + 1 : nd.s;
-            for (int c = lane; c < cend; c += 32) acc += row[c] * x[c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                if (rl < nd.s)
-                    A.y[nd.s0 + rl] = acc;
-                else
-                    atomicAdd(&A.rhs[A.bidx[nd.bidx + rl - nd.s]], -acc);
-            }
-        }
-        grid.sync();
-    }
-    // backward sweep, root first
-    for (int h = A.n_levels - 1; h >= 0; h--) {
-        const ProjLevelInfo li = A.levels[h];
-        const int* row_node = A.rowmaps + li.bwd_node;
-        const int* row_local = A.rowmaps + li.bwd_local;
-        for (int R = gwarp; R < li.n_bwd; R += nwarps) {
-            const ProjNodeDesc nd = A.nodes[row_node[R]];
-            const int rl = row_local[R];
-            const int f = nd.s + nd.b;
-            const double* row = A.mat + nd.bwd + (long long)rl * f;
-            double acc = 0;
-            for (int c = rl + lane; c < nd.s; c += 32) acc += row[c] * A.y[nd.s0 + c];
-            const int* bi = A.bidx + nd.bidx;
-            for (int c = lane; c < nd.b; c += 32) acc += row[nd.s + c] * A.sol[bi[c]];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) A.sol[nd.s0 + rl] = acc;
-        }
-        grid.sync();
-    }
-    // scatter: v -= D^-1 A^T sol
-    for (int t = tid; t < A.n_touched; t += nthreads) {
-        double acc = 0;
-        for (int e = A.tptr[t]; e < A.tptr[t + 1]; e++) acc += A.tw[e] * A.sol[A.trow[e]];
-        int64_t n = A.tnode[t];
-        v[n] = (float)((double)v[n] - acc);
-    }
+    if (t < A.n_touched) proj_scatter_node(A, t, v);
 }
 
 }  // namespace
@@ -805,7 +657,8 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
                  o_rperm = B.take<int>(m), o_tnode = B.take<int64_t>(n_touched), o_tptr = B.take<int>(n_touched + 1),
                  o_trow = B.take<int>(ent.size()), o_tw = B.take<double>(ent.size()),
                  o_nodes = B.take<ProjNodeDesc>(descs.size()), o_bidx = B.take<int>(hf.bidx.size()),
-                 o_rowmaps = B.take<int>(n_rowmaps), o_levels = B.take<ProjLevelInfo>(max_h + 1);
+                 o_rowmaps = B.take<int>(n_rowmaps), o_levels = B.take<ProjLevelInfo>(max_h + 1),
+                 o_self = B.take<ProjDev>(1), o_prog = B.take<TailOp>(2 * (size_t)(max_h + 1) + 2);
     const size_t upload_bytes = B.off;
     const size_t o_rhs = B.take<double>(m), o_y = B.take<double>(m), o_sol = B.take<double>(m);
     if (upload_bytes > h_arena_cap_) {
@@ -884,7 +737,6 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
         }
     }
     n_levels_ = max_h + 1;
-    SHM3D_CUDA_CHECK(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
     d_rnode_ = (int64_t*)(D + o_rnode);
     d_rw_ = (double*)(D + o_rw);
     d_rperm_ = (int*)(D + o_rperm);
@@ -899,19 +751,18 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
     d_rhs_ = (double*)(D + o_rhs);
     d_y_ = (double*)(D + o_y);
     d_sol_ = (double*)(D + o_sol);
-    // The single-launch cooperative variant (grid barriers between tree levels) measured SLOWER on B200 than one small
-    // launch per level (420 vs 260 us per application at m = 1e5): kept only as an opt-in experiment.
-    if (coop_blocks_ == 0 && getenv("SHM3D_FUSED_PROJ")) {
-        int dev = 0, coop = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_proj_fused, 256, 0);
-        if (const char* e = getenv("SHM3D_PROJ_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
-        // all co-resident CTAs: the sweeps are bound by the latency of ~5e5 short dependent row products, so the
-        // kernel wants every warp slot of the machine
-        coop_blocks_ = (coop && per_sm > 0) ? sms * per_sm : 0;
+    d_self_ = (ProjDev*)(D + o_self);
+    *(ProjDev*)(H + o_self) = dev_view();
+    cluster_prog_ = nullptr;
+    cluster_prog_len_ = 0;
+    if (m <= kClusterMaxRows) {
+        std::vector<TailOp> prog;
+        record_apply(prog, const_cast<float*>(kTailSlotV), kTailSlotW, /*shifted=*/true);
+        memcpy(H + o_prog, prog.data(), prog.size() * sizeof(TailOp));
+        cluster_prog_ = (TailOp*)(D + o_prog);
+        cluster_prog_len_ = (int)prog.size();
     }
+    SHM3D_CUDA_CHECK(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
     if (getenv("SHM3D_DEBUG"))
         fprintf(stderr, "[shm3d] projector m=%d: factor %.1f ms, maps+upload issue %.1f ms\n", m, (tb1 - tb0) * 1e3,
                 (wall() - tb1) * 1e3);
@@ -919,46 +770,8 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
     // synchronisation, so the copies issued here have completed by then
 }
 
-void Projector::gather(const float* v, const float* w, const double* shift_num, double shift_den,
-                       cudaStream_t s) const {
-    if (!m_) return;
-    k_proj_gather<<<(m_ + 127) / 128, 128, 0, s>>>(m_, d_rnode_, d_rw_, d_rperm_, v, w, shift_num, shift_den, d_rhs_);
-    SHM3D_LAUNCHED();
-    if (reduce_hook_) reduce_hook_(d_rhs_, m_, s);
-}
-
-void Projector::solve(cudaStream_t s) const {
-    if (!m_) return;
-    const NodeDescD* nodes = (const NodeDescD*)d_nodes_;
-    const int H = (int)fwd_levels_.size();
-    for (int h = 0; h < H; h++) {
-        const LevelBatch& lb = fwd_levels_[h];
-        if (!lb.n_rows) continue;
-        k_proj_fwd<<<(lb.n_rows * 32 + 255) / 256, 256, 0, s>>>(lb.n_rows, lb.row_node, lb.row_local, nodes, d_mat_,
-                                                                 d_bidx_, d_rhs_, d_y_);
-        SHM3D_LAUNCHED();
-    }
-    for (int h = H - 1; h >= 0; h--) {
-        const LevelBatch& lb = fwd_levels_[h];
-        const int nr = lb.n_nodes;
-        if (!nr) continue;
-        k_proj_bwd<<<(nr * 32 + 255) / 256, 256, 0, s>>>(nr, d_rowmaps_ + bwd_off_[4 * h + 2],
-                                                          d_rowmaps_ + bwd_off_[4 * h + 3], nodes, d_mat_, d_bidx_, d_y_,
-                                                          d_sol_);
-        SHM3D_LAUNCHED();
-    }
-    SHM3D_CUDA_CHECK(cudaGetLastError());
-}
-
-void Projector::scatter_sub(float* v, cudaStream_t s) const {
-    if (!m_ || !n_touched_) return;
-    k_proj_scatter<<<(n_touched_ + 127) / 128, 128, 0, s>>>(n_touched_, d_tnode_, d_tptr_, d_trow_, d_tw_, d_sol_, v);
-    SHM3D_LAUNCHED();
-}
-
-void Projector::apply_fused(float* v, const float* w, const double* shift_num, double shift_den,
-                            cudaStream_t s) const {
-    FusedArgs A;
+ProjDev Projector::dev_view() const {
+    ProjDev A;
     A.m = m_;
     A.n_touched = n_touched_;
     A.n_levels = n_levels_;
@@ -977,14 +790,83 @@ void Projector::apply_fused(float* v, const float* w, const double* shift_num, d
     A.rhs = d_rhs_;
     A.y = d_y_;
     A.sol = d_sol_;
-    void* args[] = {(void*)&A, (void*)&v, (void*)&w, (void*)&shift_num, (void*)&shift_den};
-    SHM3D_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_proj_fused, dim3(coop_blocks_), dim3(256), args, 0, s));
+    return A;
+}
+
+void Projector::gather(const float* v, const float* w, const double* shift_num, double shift_den,
+                       cudaStream_t s) const {
+    if (!m_) return;
+    k_proj_gather<<<(m_ + 127) / 128, 128, 0, s>>>(dev_view(), v, w, shift_num, shift_den);
+    SHM3D_LAUNCHED();
+    if (reduce_hook_) reduce_hook_(d_rhs_, m_, s);
+}
+
+void Projector::solve(cudaStream_t s) const {
+    if (!m_) return;
+    const ProjDev A = dev_view();
+    const int H = (int)fwd_levels_.size();
+    for (int h = 0; h < H; h++) {
+        const LevelBatch& lb = fwd_levels_[h];
+        if (!lb.n_rows) continue;
+        k_proj_fwd<<<(lb.n_rows * 32 + 255) / 256, 256, 0, s>>>(A, lb.n_rows, lb.row_node, lb.row_local);
+        SHM3D_LAUNCHED();
+    }
+    for (int h = H - 1; h >= 0; h--) {
+        const LevelBatch& lb = fwd_levels_[h];
+        const int nr = lb.n_nodes;
+        if (!nr) continue;
+        k_proj_bwd<<<(nr * 32 + 255) / 256, 256, 0, s>>>(A, nr, d_rowmaps_ + bwd_off_[4 * h + 2],
+                                                          d_rowmaps_ + bwd_off_[4 * h + 3]);
+        SHM3D_LAUNCHED();
+    }
+    SHM3D_CUDA_CHECK(cudaGetLastError());
+}
+
+void Projector::scatter_sub(float* v, cudaStream_t s) const {
+    if (!m_ || !n_touched_) return;
+    k_proj_scatter<<<(n_touched_ + 127) / 128, 128, 0, s>>>(dev_view(), v);
     SHM3D_LAUNCHED();
 }
 
+void Projector::record_apply(std::vector<TailOp>& ops, float* v, const float* w, bool shifted) const {
+    if (!m_) return;
+    TailOp op;
+    memset(&op, 0, sizeof(op));
+    op.proj = d_self_;
+    op.code = kTGather;
+    op.a = v;
+    op.b = w;
+    op.h = shifted ? 1 : 0;
+    ops.push_back(op);
+    op.a = op.b = nullptr;
+    const int H = (int)fwd_levels_.size();
+    for (int h = 0; h < H; h++) {
+        if (!fwd_levels_[h].n_rows) continue;
+        op.code = kTFwd;
+        op.h = h;
+        ops.push_back(op);
+    }
+    for (int h = H - 1; h >= 0; h--) {
+        if (!fwd_levels_[h].n_nodes) continue;
+        op.code = kTBwd;
+        op.h = h;
+        ops.push_back(op);
+    }
+    if (n_touched_) {
+        op.code = kTScatter;
+        op.h = 0;
+        op.o = v;
+        ops.push_back(op);
+    }
+}
+
+// Small systems (coarse multigrid levels): the whole application is one launch of the cluster program (mg_tail.cuh),
+// whose phases are separated by hardware cluster barriers instead of kernel boundaries.
+bool Projector::cluster_path() const { return cluster_prog_ != nullptr && !reduce_hook_; }
+
 void Projector::apply(float* v, cudaStream_t s) const {
     if (!m_) return;
-    if (coop_blocks_ && !reduce_hook_) return apply_fused(v, nullptr, nullptr, 1.0, s);
+    if (cluster_path()) return launch_cluster_program(cluster_prog_, cluster_prog_len_, v, nullptr, nullptr, 1.0, s);
     gather(v, nullptr, nullptr, 1.0, s);
     solve(s);
     scatter_sub(v, s);
@@ -992,7 +874,7 @@ void Projector::apply(float* v, cudaStream_t s) const {
 
 void Projector::apply_update(float* v, const float* w, cudaStream_t s) const {
     if (!m_) return;
-    if (coop_blocks_ && !reduce_hook_) return apply_fused(v, w, nullptr, 1.0, s);
+    if (cluster_path()) return launch_cluster_program(cluster_prog_, cluster_prog_len_, v, w, nullptr, 1.0, s);
     gather(v, w, nullptr, 1.0, s);
     solve(s);
     scatter_sub(v, s);
@@ -1000,7 +882,7 @@ void Projector::apply_update(float* v, const float* w, cudaStream_t s) const {
 
 void Projector::apply_shifted(float* v, const double* shift_num, double shift_den, cudaStream_t s) const {
     if (!m_) return;
-    if (coop_blocks_ && !reduce_hook_) return apply_fused(v, nullptr, shift_num, shift_den, s);
+    if (cluster_path()) return launch_cluster_program(cluster_prog_, cluster_prog_len_, v, nullptr, shift_num, shift_den, s);
     gather(v, nullptr, shift_num, shift_den, s);
     solve(s);
     scatter_sub(v, s);

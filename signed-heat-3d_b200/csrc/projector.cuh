@@ -96,6 +96,14 @@ class Projector {
     void solve(cudaStream_t s) const;                         // sol_ = (A D^-1 A^T)^-1 rhs_
     void scatter_sub(float* v, cudaStream_t s) const;         // v -= D^-1 A^T sol_
 
+    // Cluster programs (mg_tail.cuh).  Systems of up to kClusterMaxRows rows are applied by ONE launch (gather, the
+    // 2*height sweeps and the scatter separated by cluster barriers instead of kernel boundaries).
+    static constexpr int kClusterMaxRows = 32768;
+    ProjDev dev_view() const;
+    const ProjDev* dev_ptr() const { return d_self_; }
+    // appends the ops of one application  v <- v - D^-1 A^T (A D^-1 A^T)^-1 A (v - w)  (w may be null) to a program
+    void record_apply(std::vector<TailOp>& ops, float* v, const float* w, bool shifted) const;
+
   private:
     struct LevelBatch {
         int n_rows = 0;          // total matrix rows handled by this launch
@@ -136,10 +144,12 @@ class Projector {
     mutable double* d_sol_ = nullptr;
     std::vector<int> perm_;  // row -> permuted index
     std::vector<size_t> bwd_off_;
-    ProjLevelInfo* d_levels_ = nullptr;  // [tree height] for the fused single-launch path
+    ProjLevelInfo* d_levels_ = nullptr;  // [tree height] row maps per height, for the cluster programs
     int n_levels_ = 0;
-    int coop_blocks_ = 0;                // co-resident grid size of k_proj_fused (0: unavailable)
-    void apply_fused(float* v, const float* w, const double* shift_num, double shift_den, cudaStream_t s) const;
+    ProjDev* d_self_ = nullptr;          // dev_view() in device memory (what the ops of a cluster program point to)
+    TailOp* cluster_prog_ = nullptr;     // one whole application as a cluster program (m <= kClusterMaxRows), else null
+    int cluster_prog_len_ = 0;
+    bool cluster_path() const;
 
   public:
     // multi-GPU: called on the gathered partial sums A v (m doubles on device) before the solve (allreduce)

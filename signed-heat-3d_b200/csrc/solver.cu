@@ -77,6 +77,9 @@ struct shm3d_ctx {
     DevBuf<float4> d_qpts;
     DevBuf<float> d_qY;
     std::vector<MGLevel> levels;
+    DevBuf<TailOp> tail_prog;          // the V-cycle below ~64^3 as one cluster program (mg_tail.cuh)
+    cudaGraphExec_t pcg_graph[2] = {nullptr, nullptr};  // one PCG iteration per buffer parity, re-used across solves
+    double* d_rho_ring = nullptr;      // device alias of h_rho (mapped pinned memory)
     std::unique_ptr<IsoSurface> iso;  // row N3, created on first use
 };
 
@@ -84,20 +87,26 @@ namespace shm3d {
 
 constexpr int kRhoRing = 64;
 constexpr size_t kReplicateBelow = (size_t)128 * 128 * 128;
-enum Sc { kRho = 0, kPQ, kSumR, kRZ, kSumZ, kRhoNew, kRho0, kShiftNum, kShiftDen, kTmp, kNumSc = 16 };
+enum Sc { kRho = 0, kPQ, kSumR, kRZ, kSumZ, kRhoNew, kRho0, kShiftNum, kShiftDen, kTmp, kIter, kNumSc = 16 };
 
 // ------------------------------------------------------------------------------------------------
 // small device kernels that belong to the orchestration
 // ------------------------------------------------------------------------------------------------
-__global__ void k_scalars_after_dot(double* sc, double n_global) {
-    // rho_new = r.g = r.z - mean(z) * sum(r)   (r is in range(P), so r.(A^T lam) = 0)
-    double mean_z = sc[kSumZ] / n_global;
-    sc[kRhoNew] = sc[kRZ] - mean_z * sc[kSumR];
-}
-__global__ void k_scalars_commit(double* sc, int first) {
-    if (first) sc[kRho0] = sc[kRhoNew];
-    sc[kTmp] = sc[kRho];  // previous rho (beta denominator)
-    sc[kRho] = sc[kRhoNew];
+// After the r.z / sum z reduction of iteration it = sc[kIter]:  rho_new = r.g = r.z - mean(z) * sum(r)  (r is in
+// range(P), so r.(A^T lam) = 0); previous rho -> kTmp (beta denominator; +inf on the first iteration: beta = 0), and
+// rho goes to slot it % kRhoRing of the host-mapped ring for the lagged convergence check.  The iteration counter lives
+// on the device so that the same captured graph serves every iteration.
+__global__ void k_scalars(double* sc, double n_global, double* rho_ring) {
+    const double mean_z = sc[kSumZ] / n_global;
+    const double rho_new = sc[kRZ] - mean_z * sc[kSumR];
+    const long long it = (long long)sc[kIter];
+    sc[kRhoNew] = rho_new;
+    if (it == 0) sc[kRho0] = rho_new;
+    sc[kTmp] = it == 0 ? (double)INFINITY : sc[kRho];
+    sc[kRho] = rho_new;
+    sc[kIter] = (double)(it + 1);
+    rho_ring[it % kRhoRing] = rho_new;
+    __threadfence_system();
 }
 
 // weighted source average of the trilinear interpolant (src/signed_heat_grid_solver.cpp:405-431, :466-496)
@@ -390,6 +399,8 @@ struct Solver {
         prof.on = (prm->flags & SHM3D_FLAG_PROFILE) != 0;
         constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
         set_march_config(!(prm->flags & SHM3D_FLAG_NO_TMA), c->sm_count);
+        use_tail = !(prm->flags & SHM3D_FLAG_NO_CLUSTER_TAIL);
+        use_graph = !(prm->flags & SHM3D_FLAG_NO_GRAPH);
         cmg_from = prm->mg_constrained_from == 0 ? 2 : std::max(0, prm->mg_constrained_from);
         if (const char* e = getenv("SHM3D_CMG_FROM")) cmg_from = atoi(e);
         if (const char* e = getenv("SHM3D_NU_COARSE")) nu_coarse = atoi(e);
@@ -667,6 +678,10 @@ struct Solver {
     void vcycle(int l, const float* b, const double* sum_b, double n_global, double* dot_acc = nullptr) {
         std::vector<MGLevel>& lv = c->levels;
         MGLevel& Lv = lv[l];
+        if (l == tail_level) {  // everything from here down and back up: one launch (b == Lv.b, result in Lv.x)
+            launch_cluster_program(c->tail_prog.p, tail_len, nullptr, nullptr, nullptr, 1.0, s);
+            return;
+        }
         if (l + 1 == (int)lv.size()) {
             launch_mg_coarse_solve((int)Lv.L.n(), c->d_pinv.p, b, Lv.x.ip(), s);
             return;
@@ -715,6 +730,107 @@ struct Solver {
                          /*exchange=*/k + 1 < nul);
     }
 
+    // ---------------------------------------------------------------- V-cycle tail as one cluster program
+    // From the first level with <= 64^3 nodes down, every operation of the V-cycle -- sweeps, transfers, the dense coarsest
+    // solve and each tree level of the projected smoothers' multifrontal sweeps -- is a launch-latency-bound kernel of a
+    // few microseconds.  record_tail() restates vcycle() for those levels as a program of TailOp (mg_tail.cuh) that one
+    // thread-block cluster executes in a single launch.  Recorded once per solve, after build_levels().
+    bool use_tail = true, use_graph = true;
+    int tail_level = -1, tail_len = 0;
+    std::vector<TailOp> tail_host;
+
+    void record_tail() {
+        tail_level = -1;
+        tail_len = 0;
+        std::vector<MGLevel>& lv = c->levels;
+        const int nl = (int)lv.size();
+        if (!use_tail || !use_mg || nl < 3) return;
+        int lt = -1;
+        for (int l = 1; l + 1 < nl && lt < 0; l++)
+            if ((size_t)lv[l].L.nx * lv[l].L.ny * lv[l].L.nz <= (size_t)64 * 64 * 64 && (c->world == 1 || lv[l].replicated)) lt = l;
+        if (lt < 0) return;
+        for (int l = lt; l < nl; l++) {  // the row bodies need nx % 4 == 0 and factor-2 transfers
+            if (lv[l].L.nx % 4 || lv[l].L.nzl() != lv[l].L.nz) return;
+            if (l + 1 < nl && lv[l].L.nx != 2 * lv[l + 1].L.nx) return;
+            if (level_projected(l) && (lv[l].proj->m() > Projector::kClusterMaxRows || lv[l].proj->reduce_hook_)) return;
+        }
+        std::vector<TailOp>& ops = tail_host;  // (member: stays alive until the upload has run)
+        ops.clear();
+        std::vector<float*> X(nl), T(nl);
+        for (int l = 0; l < nl; l++) {
+            X[l] = lv[l].x.ip();
+            T[l] = lv[l].tmp.ip();
+        }
+        auto mk = [](int code, const LevelDims& L) {
+            TailOp op;
+            memset(&op, 0, sizeof(op));
+            op.code = code;
+            op.L = L;
+            op.Lc = L;
+            return op;
+        };
+        std::function<void(int)> rec = [&](int l) {
+            MGLevel& Lv = lv[l];
+            float* rhs = Lv.b.ip();
+            if (l + 1 == nl) {
+                TailOp op = mk(kTCoarse, Lv.L);
+                op.h = (int)Lv.L.n();
+                op.a = c->d_pinv.p;
+                op.b = rhs;
+                op.o = X[l];
+                ops.push_back(op);
+                return;
+            }
+            const bool proj = level_projected(l);
+            const int nul = (l >= cmg_from && nu_coarse > 0) ? nu_coarse : nu;
+            auto sweep = [&](float om) {  // smooth_sweep(): T = X + om D^-1 (b - K X), projected update, swap
+                TailOp op = mk(kTSmooth, Lv.L);
+                op.omega = om;
+                op.a = rhs;
+                op.b = X[l];
+                op.o = T[l];
+                ops.push_back(op);
+                if (proj) Lv.proj->record_apply(ops, T[l], X[l], false);
+                std::swap(X[l], T[l]);
+            };
+            TailOp op = mk(kTSmooth0, Lv.L);
+            op.omega = sweep_omega(0, nul);
+            op.a = rhs;
+            op.o = X[l];
+            ops.push_back(op);
+            if (proj) Lv.proj->record_apply(ops, X[l], nullptr, false);
+            for (int k = 1; k < nul; k++) sweep(sweep_omega(k, nul));
+            op = mk(kTResidual, Lv.L);
+            op.a = rhs;
+            op.b = X[l];
+            op.o = Lv.r.ip();
+            ops.push_back(op);
+            op = mk(kTRestrict, Lv.L);
+            op.Lc = lv[l + 1].L;
+            op.a = Lv.r.ip();
+            op.o = lv[l + 1].b.ip();
+            ops.push_back(op);
+            rec(l + 1);
+            op = mk(kTProlong, Lv.L);
+            op.Lc = lv[l + 1].L;
+            op.a = X[l + 1];
+            op.o = X[l];
+            ops.push_back(op);
+            for (int k = 0; k < nul; k++) sweep(sweep_omega(nul - 1 - k, nul));
+        };
+        rec(lt);
+        if (X[lt] != lv[lt].x.ip()) {  // an odd number of sweeps: the parent level reads lv[lt].x
+            TailOp op = mk(kTCopy, lv[lt].L);
+            op.a = X[lt];
+            op.o = lv[lt].x.ip();
+            ops.push_back(op);
+        }
+        c->tail_prog.upload(ops, s);
+        tail_level = lt;
+        tail_len = (int)ops.size();
+        st.tail_ops = tail_len;
+    }
+
     // ---------------------------------------------------------------- constrained PCG
     // On entry c->vr holds b' = cell^2 D^T Y.  On exit c->vx holds phi (unshifted).
     //
@@ -740,26 +856,32 @@ struct Solver {
         const bool verbose = (p->flags & SHM3D_FLAG_VERBOSE) != 0;
         const int kCheck = verbose ? 1 : 4;  // (the event profiler is asynchronous: it does not need per-iteration syncs)
         const bool fuse_dot = use_mg && !level_projected(0) && lv.size() > 1 && nu >= 1;
-        if (!c->h_rho) SHM3D_CUDA_CHECK(cudaHostAlloc((void**)&c->h_rho, kRhoRing * sizeof(double), cudaHostAllocDefault));
+        if (!c->h_rho) {
+            SHM3D_CUDA_CHECK(cudaHostAlloc((void**)&c->h_rho, kRhoRing * sizeof(double), cudaHostAllocMapped));
+            SHM3D_CUDA_CHECK(cudaHostGetDevicePointer((void**)&c->d_rho_ring, c->h_rho, 0));
+        }
         Timer t(s);
         t.start();
         SHM3D_CUDA_CHECK(cudaMemsetAsync(sc, 0, kNumSc * sizeof(double), s));
         SHM3D_CUDA_CHECK(cudaMemsetAsync(x, 0, n * sizeof(float), s));
+        // beta = rho / rho_old is 0 on the first iteration (rho_old = +inf, k_scalars): the old p must be finite there
+        SHM3D_CUDA_CHECK(cudaMemsetAsync(pbuf[0] - L0.plane(), 0, (n + 2 * L0.plane()) * sizeof(float), s));
         P.apply(r, s);  // r~ = P b
         launch_vec_sum(r, n, sc + kSumR, s);
         if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
-        double rho0 = 0, rho = 0;
-        int it = 0, bad = 0, checked = 0;
-        double rel = 1.0;
-        bool stop = false;
-        for (;; it++) {
-            // z = V(r - mean r)
+
+        // One iteration = part A (z = V(r - mean r), r.z, g = P (z - mean z), rho) and part B (p, q = K p, p.q, Pi q, x/r
+        // update).  The loop runs A(0), then [B(it), A(it+1)] per iteration, so the convergence check sits between an A
+        // and the following B exactly as in the textbook order.  All scalars (rho, beta, alpha, the iteration counter)
+        // live on the device and buffers alternate with period 2, so [B, A] is captured ONCE per parity into a CUDA graph
+        // and replayed: ~90 launches per iteration cost one graph launch on the host and back-to-back nodes on the GPU.
+        auto part_a = [&](bool profile) {
             float* z = lv[0].x.ip();
             if (use_mg) {
                 if (c->dist) c->dist->exchange_halo(r, L0, s);
-                prof.begin(s, kProfVcycle);
+                if (profile) prof.begin(s, kProfVcycle);
                 vcycle(0, r, sc + kSumR, Ng, fuse_dot ? sc + kRZ : nullptr);
-                prof.end(s);
+                if (profile) prof.end(s);
                 z = lv[0].x.ip();  // (the sweeps swap x and tmp)
                 if (!fuse_dot) launch_dot_rz(L0, r, z, sc + kRZ, s);  // writes kRZ, kSumZ
             } else {
@@ -768,14 +890,50 @@ struct Solver {
             }
             if (c->dist) c->dist->allreduce(sc + kRZ, 2, s);
             // g = P (z - mean z): z <- z - A^T (A A^T)^-1 A (z - mean z); the mean itself is removed in the p update
-            prof.begin(s, kProfProjector);
+            if (profile) prof.begin(s, kProfProjector);
             P.apply_shifted(z, sc + kSumZ, Ng, s);
-            prof.end(s);
-            k_scalars_after_dot<<<1, 1, 0, s>>>(sc, Ng);
+            if (profile) prof.end(s);
+            k_scalars<<<1, 1, 0, s>>>(sc, Ng, c->d_rho_ring);
             SHM3D_LAUNCHED();
-            k_scalars_commit<<<1, 1, 0, s>>>(sc, it == 0);
-            SHM3D_LAUNCHED();
-            SHM3D_CUDA_CHECK(cudaMemcpyAsync(c->h_rho + (it % kRhoRing), sc + kRho, sizeof(double), cudaMemcpyDeviceToHost, s));
+        };
+        auto part_b = [&](int it, bool profile) {
+            float* z = lv[0].x.ip();
+            if (c->dist) c->dist->exchange_halo(z, L0, s);
+            // p = (z - mean z) + beta p ; q = K p ; p.q   (one pass; p ping-pongs between two buffers)
+            float* pn = pbuf[(it + 1) & 1];
+            const float* po = pbuf[it & 1];
+            if (profile) prof.begin(s, kProfStencil);
+            launch_update_p_stencil(L0, pn, po, z, q, sc + kSumZ, Ng, sc + kRho, sc + kTmp, 0, sc + kPQ, s);
+            if (profile) prof.end(s);
+            if (c->dist) {
+                // the ghost planes of the new p follow from the ghost planes of z and the old p: no extra exchange
+                LevelDims G1{L0.nx, L0.ny, 1, 0, 1};
+                const size_t pl = L0.plane();
+                if (L0.k0 > 0) launch_update_p(G1, pn - pl, po - pl, z - pl, sc + kSumZ, Ng, sc + kRho, sc + kTmp, 0, s);
+                if (L0.k1 < L0.nz) launch_update_p(G1, pn + n, po + n, z + n, sc + kSumZ, Ng, sc + kRho, sc + kTmp, 0, s);
+                c->dist->allreduce(sc + kPQ, 1, s);
+            }
+            // alpha = rho / p.q ; x += alpha p ; r -= alpha P q
+            if (profile) prof.begin(s, kProfProjector);
+            P.apply(q, s);
+            if (profile) prof.end(s);
+            if (profile) prof.begin(s, kProfUpdate);
+            launch_update_xr(L0, x, r, pn, q, sc + kRho, sc + kPQ, sc + kSumR, s);
+            if (profile) prof.end(s);
+            if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
+        };
+        // profiling (bench.py's per-kernel roofline numbers): the first iterations run eagerly with CUDA events around the
+        // kernels of interest; the rest of the solve replays the graphs like an unprofiled one
+        const int n_eager = prof.on ? 6 : 1;  // (the first pass also runs every kernel's one-time set-up outside a capture)
+        bool captured[2] = {false, false};
+        int64_t graph_nodes[2] = {0, 0};
+
+        double rho0 = 0, rho = 0;
+        int it = 0, bad = 0, checked = 0;
+        double rel = 1.0;
+        bool stop = false;
+        part_a(prof.on);  // A(0)
+        for (;;) {
             if ((it + 1) % kCheck == 0 || it == 0 || it >= maxit) {
                 SHM3D_CUDA_CHECK(cudaStreamSynchronize(s));
                 for (; checked <= it; checked++) {
@@ -792,29 +950,47 @@ struct Solver {
                 }
                 if (stop || it >= maxit) break;
             }
-            if (c->dist) c->dist->exchange_halo(z, L0, s);
-            // p = (z - mean z) + beta p ; q = K p ; p.q   (one pass; p ping-pongs between two buffers)
-            float* pn = pbuf[(it + 1) & 1];
-            const float* po = pbuf[it & 1];
-            prof.begin(s, kProfStencil);
-            launch_update_p_stencil(L0, pn, po, z, q, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, sc + kPQ, s);
-            prof.end(s);
-            if (c->dist) {
-                // the ghost planes of the new p follow from the ghost planes of z and the old p: no extra exchange
-                LevelDims G1{L0.nx, L0.ny, 1, 0, 1};
-                const size_t pl = L0.plane();
-                if (L0.k0 > 0) launch_update_p(G1, pn - pl, po - pl, z - pl, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
-                if (L0.k1 < L0.nz) launch_update_p(G1, pn + n, po + n, z + n, sc + kSumZ, Ng, sc + kRho, sc + kTmp, it == 0, s);
-                c->dist->allreduce(sc + kPQ, 1, s);
+            const int next = it + 1;
+            if (!use_graph || next <= n_eager) {
+                part_b(it, prof.on);
+                part_a(prof.on);
+            } else {
+                const int par = next & 1;
+                if (!captured[par]) {
+                    const int64_t l0 = g_kernel_launches;
+                    cudaGraph_t g = nullptr;
+                    SHM3D_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+                    try {
+                        part_b(it, false);
+                        part_a(false);
+                    } catch (...) {
+                        cudaStreamEndCapture(s, &g);
+                        if (g) cudaGraphDestroy(g);
+                        throw;
+                    }
+                    SHM3D_CUDA_CHECK(cudaStreamEndCapture(s, &g));
+                    graph_nodes[par] = g_kernel_launches - l0;
+                    g_kernel_launches = l0;  // recorded, not launched: counted per replay below
+                    // same topology as the previous solve on this context -> update the executable graph in place
+                    bool ok = false;
+                    if (c->pcg_graph[par]) {
+                        cudaGraphExecUpdateResultInfo info;
+                        ok = cudaGraphExecUpdate(c->pcg_graph[par], g, &info) == cudaSuccess;
+                        if (!ok) {
+                            cudaGetLastError();
+                            cudaGraphExecDestroy(c->pcg_graph[par]);
+                            c->pcg_graph[par] = nullptr;
+                        }
+                    }
+                    if (!ok) SHM3D_CUDA_CHECK(cudaGraphInstantiate(&c->pcg_graph[par], g, 0));
+                    cudaGraphDestroy(g);
+                    captured[par] = true;
+                }
+                SHM3D_CUDA_CHECK(cudaGraphLaunch(c->pcg_graph[par], s));
+                g_kernel_launches += graph_nodes[par];
+                st.graph_replays++;
             }
-            // alpha = rho / p.q ; x += alpha p ; r -= alpha P q
-            prof.begin(s, kProfProjector);
-            P.apply(q, s);
-            prof.end(s);
-            prof.begin(s, kProfUpdate);
-            launch_update_xr(L0, x, r, pn, q, sc + kRho, sc + kPQ, sc + kSumR, s);
-            prof.end(s);
-            if (c->dist) c->dist->allreduce(sc + kSumR, 1, s);
+            it = next;
         }
         // x = sum alpha_k p_k left null(A) only by fp32 rounding (|A x| ~ 1e-4 after ~100 iterations at 512^3):
         // one last projection restores the zero level set at the pinned sources to rounding
@@ -828,6 +1004,7 @@ struct Solver {
             st.ms_pcg_stencil = ms[kProfStencil];
             st.pcg_stencil_launches = cnt[kProfStencil];
             st.ms_pcg_vcycle = ms[kProfVcycle];
+            st.pcg_vcycles = cnt[kProfVcycle];
             st.ms_pcg_projector = ms[kProfProjector];
             st.pcg_projector_applies = cnt[kProfProjector];
             st.ms_pcg_update = ms[kProfUpdate];
@@ -1038,6 +1215,7 @@ static int solve_impl(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const do
         S.alloc_pcg_vectors();
         S.run_step12();       // asynchronous on the GPU ...
         S.build_levels();     // ... while the host builds and factorises the constraint systems
+        S.record_tail();
         S.finish_step12_stats();
         S.run_rhs(ctx->vr.ip());
         S.run_pcg();
@@ -1141,6 +1319,7 @@ int shm3d_step3(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double* 
     S.prepare_sources(M, pos, nullptr, area, false);
     S.alloc_pcg_vectors();
     S.build_levels();
+    S.record_tail();
     SHM3D_CUDA_CHECK(cudaMemcpyAsync(ctx->vr.ip(), b, S.L0.n() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     S.run_pcg();
     S.run_shift_and_output(phi_out, nullptr);

@@ -20,6 +20,8 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libshm3d_grid.so")
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_FACTORIZATION, ERR_NO_CONVERGENCE, ERR_NCCL = range(7)
 FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_PROFILE = 1, 2, 4, 8, 16, 32
 FLAG_NO_TMA = 128         # diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones
+FLAG_NO_CLUSTER_TAIL = 256  # diagnostics: no single-launch cluster programs (V-cycle tail, small projectors)
+FLAG_NO_GRAPH = 512       # diagnostics: PCG iterations launched kernel by kernel instead of CUDA-graph replays
 FLAG_FP64_UNDERFLOW = 64  # reproduce the reference's fp64 underflow in X.norm() at far nodes (include/shm3d_grid.h)
 
 
@@ -41,7 +43,8 @@ class Stats(C.Structure):
                 ("n_clusters", C.c_int32), ("m_constraints", C.c_int32), ("cg_iters", C.c_int32),
                 ("cg_rel_residual", C.c_double), ("shift", C.c_double), ("kernel_launches", C.c_int64),
                 ("ms_pcg_stencil", C.c_double), ("pcg_stencil_launches", C.c_int64), ("ms_pcg_vcycle", C.c_double),
-                ("ms_pcg_projector", C.c_double), ("pcg_projector_applies", C.c_int64), ("ms_pcg_update", C.c_double)]
+                ("ms_pcg_projector", C.c_double), ("pcg_projector_applies", C.c_int64), ("ms_pcg_update", C.c_double),
+                ("pcg_vcycles", C.c_int64), ("tail_ops", C.c_int32), ("graph_replays", C.c_int32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
