@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes the C compiler produces for the two ABI structs (natural alignment)
     assert ctypes.sizeof(shm3d.Params) == 96
-    assert ctypes.sizeof(shm3d.Stats) == 168
+    assert ctypes.sizeof(shm3d.Stats) == 184
 
 
 def test_header_is_plain_c_and_links(tmp_path):
