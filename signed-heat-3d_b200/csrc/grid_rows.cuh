@@ -33,11 +33,9 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// (gw_, nw_): index of this warp among the nw_ warps that share the rows -- the whole grid for the stand-alone kernels,
-// one thread-block cluster for the multigrid tail program (mg_tail.cuh)
-#define ROWS_BEGIN_AT(L_, gw_, nw_)                                                                \
+#define ROWS_BEGIN(L_)                                                                             \
     const int lane = threadIdx.x & 31;                                                             \
-    const unsigned _gw = (gw_), _nw = (nw_);                                                       \
+    const unsigned _gw = (blockIdx.x * kT + threadIdx.x) >> 5, _nw = (gridDim.x * kT) >> 5;        \
     const unsigned _nrows = (unsigned)(L_).ny * (unsigned)(L_).nzl();                              \
     const int nq = (L_).nx >> 2;                                                                   \
     const unsigned pl = (unsigned)(L_).nx * (unsigned)(L_).ny;                                     \
@@ -51,7 +49,6 @@ __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.
 #define ROWS_END() \
         }          \
     }
-#define ROWS_BEGIN(L_) ROWS_BEGIN_AT(L_, (blockIdx.x * kT + threadIdx.x) >> 5, (gridDim.x * kT) >> 5)
 
 // x-neighbours of a quad whose (possibly derived) values are c: shuffles, lanes 0 / 31 use the supplied scalars
 __device__ __forceinline__ void x_neighbours(const float4& c, int lane, int q, int nq, float lane0_left, float lane31_right,
@@ -101,9 +98,12 @@ __global__ void __launch_bounds__(kT) k_row_stencil_dot(LevelDims L, const float
 
 // ---------------------------------------------------------------- damped Jacobi sweep (optionally with the PCG dots)
 template <bool DOT>
-__device__ __forceinline__ void rows_smooth(const LevelDims& L, float* xo, const float* x, const float* bb, float shift,
-                                            float omega, double (&acc)[2], unsigned gw, unsigned nw) {
-    ROWS_BEGIN_AT(L, gw, nw)
+__global__ void __launch_bounds__(kT) k_row_smooth(LevelDims L, float* __restrict__ xo, const float* __restrict__ x,
+                                                   const float* __restrict__ bb, const double* sum_b, double n_global,
+                                                   float omega, RedScratch rs, double* out) {
+    const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
+    double acc[2] = {0.0, 0.0};
+    ROWS_BEGIN(L)
         const float4 c = ld4(x + e);
         const float4 a = R.ym ? ld4(x + e - L.nx) : zero4();
         const float4 b = R.yp ? ld4(x + e + L.nx) : zero4();
@@ -131,38 +131,14 @@ __device__ __forceinline__ void rows_smooth(const LevelDims& L, float* xo, const
             }
         }
     ROWS_END()
-}
-
-template <bool DOT>
-__global__ void __launch_bounds__(kT) k_row_smooth(LevelDims L, float* __restrict__ xo, const float* __restrict__ x,
-                                                   const float* __restrict__ bb, const double* sum_b, double n_global,
-                                                   float omega, RedScratch rs, double* out) {
-    const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
-    double acc[2] = {0.0, 0.0};
-    rows_smooth<DOT>(L, xo, x, bb, shift, omega, acc, (blockIdx.x * kT + threadIdx.x) >> 5, (gridDim.x * kT) >> 5);
     if (DOT) block_reduce_commit<2>(acc, rs, out);
 }
 
-// first sweep from a zero guess: x = omega (b - shift) / d
-__device__ __forceinline__ void rows_smooth0(const LevelDims& L, float* xo, const float* bb, float shift, float omega,
-                                             unsigned gw, unsigned nw) {
-    ROWS_BEGIN_AT(L, gw, nw)
-        const float4 rhs = ld4(bb + e);
-        const float cin = R.cyz + 2.f, ced = R.cyz + 1.f;
-        const bool e0 = q == 0, e3 = q == nq - 1;
-        float4 o;
-        o.x = omega * (rhs.x - shift) / (e0 ? ced : cin);
-        o.y = omega * (rhs.y - shift) / cin;
-        o.z = omega * (rhs.z - shift) / cin;
-        o.w = omega * (rhs.w - shift) / (e3 ? ced : cin);
-        if (act) st4(xo + e, o);
-    ROWS_END()
-}
-
 // ---------------------------------------------------------------- r = (b - shift) - K'x
-__device__ __forceinline__ void rows_residual(const LevelDims& L, const float* x, const float* bb, float shift, float* ro,
-                                              unsigned gw, unsigned nw) {
-    ROWS_BEGIN_AT(L, gw, nw)
+__global__ void __launch_bounds__(kT) k_row_residual(LevelDims L, const float* __restrict__ x, const float* __restrict__ bb,
+                                                     const double* sum_b, double n_global, float* __restrict__ ro) {
+    const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
+    ROWS_BEGIN(L)
         const float4 c = ld4(x + e);
         const float4 a = R.ym ? ld4(x + e - L.nx) : zero4();
         const float4 b = R.yp ? ld4(x + e + L.nx) : zero4();
@@ -177,12 +153,6 @@ __device__ __forceinline__ void rows_residual(const LevelDims& L, const float* x
         const float4 K = stencil_quad(c, a, b, d, f, l, r, q == 0 ? cin - 1.f : cin, cin, q == nq - 1 ? cin - 1.f : cin);
         if (act) st4(ro + e, make_float4((rhs.x - shift) - K.x, (rhs.y - shift) - K.y, (rhs.z - shift) - K.z, (rhs.w - shift) - K.w));
     ROWS_END()
-}
-
-__global__ void __launch_bounds__(kT) k_row_residual(LevelDims L, const float* __restrict__ x, const float* __restrict__ bb,
-                                                     const double* sum_b, double n_global, float* __restrict__ ro) {
-    const float shift = sum_b ? (float)(*sum_b / n_global) : 0.f;
-    rows_residual(L, x, bb, shift, ro, (blockIdx.x * kT + threadIdx.x) >> 5, (gridDim.x * kT) >> 5);
 }
 
 // ---------------------------------------------------------------- first two Jacobi sweeps from a zero guess, one pass over b
@@ -272,10 +242,10 @@ __device__ __forceinline__ void rweights4(int I, int nc, float (&wt)[4]) {
     wt[3] = (I < nc - 1) ? 0.25f : 0.f;
 }
 
-__device__ __forceinline__ void rows_restrict(const LevelDims& Lf, const LevelDims& Lc, const float* r, float* bc,
-                                              unsigned gw, unsigned nw) {
+__global__ void __launch_bounds__(kT) k_row_restrict(LevelDims Lf, LevelDims Lc, const float* __restrict__ r,
+                                                     float* __restrict__ bc) {
     const ptrdiff_t plf = (ptrdiff_t)Lf.plane();
-    ROWS_BEGIN_AT(Lc, gw, nw)
+    ROWS_BEGIN(Lc)
         float wy[4], wz[4];
         rweights4(R.j, Lc.ny, wy);
         rweights4(R.k, Lc.nz, wz);
@@ -321,18 +291,13 @@ __device__ __forceinline__ void rows_restrict(const LevelDims& Lf, const LevelDi
     ROWS_END()
 }
 
-__global__ void __launch_bounds__(kT) k_row_restrict(LevelDims Lf, LevelDims Lc, const float* __restrict__ r,
-                                                     float* __restrict__ bc) {
-    rows_restrict(Lf, Lc, r, bc, (blockIdx.x * kT + threadIdx.x) >> 5, (gridDim.x * kT) >> 5);
-}
-
 // ---------------------------------------------------------------- x += P ec  (clamped cell-centred trilinear prolongation)
 // A warp owns a FINE row: the four contributing coarse rows are read as float2 (coarse nodes 2q, 2q+1 of fine quad q),
 // interpolated in y/z first, the two x-end coarse values come from the neighbouring lanes.
-__device__ __forceinline__ void rows_prolong_add(const LevelDims& Lf, const LevelDims& Lc, float* x, const float* ec,
-                                                 unsigned gw, unsigned nw) {
+__global__ void __launch_bounds__(kT) k_row_prolong_add(LevelDims Lf, LevelDims Lc, float* __restrict__ x,
+                                                        const float* __restrict__ ec) {
     const ptrdiff_t plc = (ptrdiff_t)Lc.plane();
-    ROWS_BEGIN_AT(Lf, gw, nw)
+    ROWS_BEGIN(Lf)
         const int J0 = R.j >> 1, K0 = R.k >> 1;
         const int J1 = min(max((R.j & 1) ? J0 + 1 : J0 - 1, 0), Lc.ny - 1);
         const int K1 = min(max((R.k & 1) ? K0 + 1 : K0 - 1, 0), Lc.nz - 1);
@@ -363,9 +328,4 @@ __device__ __forceinline__ void rows_prolong_add(const LevelDims& Lf, const Leve
             st4(x + e, v);
         }
     ROWS_END()
-}
-
-__global__ void __launch_bounds__(kT) k_row_prolong_add(LevelDims Lf, LevelDims Lc, float* __restrict__ x,
-                                                        const float* __restrict__ ec) {
-    rows_prolong_add(Lf, Lc, x, ec, (blockIdx.x * kT + threadIdx.x) >> 5, (gridDim.x * kT) >> 5);
 }

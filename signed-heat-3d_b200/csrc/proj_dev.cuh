@@ -39,18 +39,26 @@ __device__ __forceinline__ void proj_gather_row(const ProjDev& A, int r, const f
 }
 
 // forward: row R of a supernode at this height: val = <FWD[R, 0:s], rhs[s0:s0+s]>;
-// R < s -> y[s0+R] = val ; else rhs[B[R-s]] -= val   (one warp per row)
-__device__ __forceinline__ void proj_fwd_row(const ProjDev& A, const int* row_node, const int* row_local, int R, int lane) {
-    const ProjNodeDesc nd = A.nodes[row_node[R]];
-    const int rl = row_local[R];
-    const double* row = A.mat + nd.fwd + (long long)rl * nd.s;
-    const double* x = A.rhs + nd.s0;
+// R < s -> y[s0+R] = val ; else rhs[B[R-s]] -= val.
+// G lanes (a power of two <= 32, aligned sub-group of a warp) share one row; `valid` = this sub-group has a row (all 32
+// lanes of the warp must make the call: the reduction shuffles name the full warp).
+template <int G>
+__device__ __forceinline__ void proj_fwd_row(const ProjDev& A, const int* row_node, const int* row_local, int R, int gl,
+                                             bool valid = true) {
     double acc = 0;
-    const int cend = rl < nd.s ? rl + 1 : nd.s;  // W is lower triangular
-    for (int c = lane; c < cend; c += 32) acc += row[c] * x[c];
+    ProjNodeDesc nd = {};
+    int rl = 0;
+    if (valid) {
+        nd = A.nodes[row_node[R]];
+        rl = row_local[R];
+        const double* row = A.mat + nd.fwd + (long long)rl * nd.s;
+        const double* x = A.rhs + nd.s0;
+        const int cend = rl < nd.s ? rl + 1 : nd.s;  // W is lower triangular
+        for (int c = gl; c < cend; c += G) acc += row[c] * x[c];
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (valid && gl == 0) {
         if (rl < nd.s)
             A.y[nd.s0 + rl] = acc;
         else
@@ -58,19 +66,25 @@ __device__ __forceinline__ void proj_fwd_row(const ProjDev& A, const int* row_no
     }
 }
 
-// backward: sol[s0+R] = <BWD[R, 0:s], y[s0:]> + <BWD[R, s:s+b], sol[B]>   (one warp per row)
-__device__ __forceinline__ void proj_bwd_row(const ProjDev& A, const int* row_node, const int* row_local, int R, int lane) {
-    const ProjNodeDesc nd = A.nodes[row_node[R]];
-    const int rl = row_local[R];
-    const int f = nd.s + nd.b;
-    const double* row = A.mat + nd.bwd + (long long)rl * f;
+// backward: sol[s0+R] = <BWD[R, 0:s], y[s0:]> + <BWD[R, s:s+b], sol[B]>
+template <int G>
+__device__ __forceinline__ void proj_bwd_row(const ProjDev& A, const int* row_node, const int* row_local, int R, int gl,
+                                             bool valid = true) {
     double acc = 0;
-    for (int c = rl + lane; c < nd.s; c += 32) acc += row[c] * A.y[nd.s0 + c];  // W^T is upper triangular
-    const int* bi = A.bidx + nd.bidx;
-    for (int c = lane; c < nd.b; c += 32) acc += row[nd.s + c] * A.sol[bi[c]];
+    ProjNodeDesc nd = {};
+    int rl = 0;
+    if (valid) {
+        nd = A.nodes[row_node[R]];
+        rl = row_local[R];
+        const int f = nd.s + nd.b;
+        const double* row = A.mat + nd.bwd + (long long)rl * f;
+        for (int c = rl + gl; c < nd.s; c += G) acc += row[c] * A.y[nd.s0 + c];  // W^T is upper triangular
+        const int* bi = A.bidx + nd.bidx;
+        for (int c = gl; c < nd.b; c += G) acc += row[nd.s + c] * A.sol[bi[c]];
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) A.sol[nd.s0 + rl] = acc;
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (valid && gl == 0) A.sol[nd.s0 + rl] = acc;
 }
 
 // v[node t] -= (D^-1 A^T sol)_t

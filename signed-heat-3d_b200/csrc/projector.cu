@@ -268,6 +268,10 @@ bool partial_cholesky(double* F, int f, int s, bool par) {
 
 void set_host_ranks_hint(int ranks_on_node) { g_ranks_on_node = std::max(1, ranks_on_node); }
 
+// cluster programs (mg_tail.cuh) on/off for the projectors built by the calling host thread (SHM3D_FLAG_NO_CLUSTER_TAIL)
+static thread_local bool g_cluster_programs = true;
+void set_projector_cluster_programs(bool enabled) { g_cluster_programs = enabled; }
+
 // ================================================================================================
 // device kernels
 // ================================================================================================
@@ -283,12 +287,12 @@ __global__ void k_proj_gather(ProjDev A, const float* __restrict__ v, const floa
 // one warp per matrix row of the supernodes at one tree height (proj_dev.cuh)
 __global__ void k_proj_fwd(ProjDev A, int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local) {
     int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (R < n_rows) proj_fwd_row(A, row_node, row_local, R, threadIdx.x & 31);
+    if (R < n_rows) proj_fwd_row<32>(A, row_node, row_local, R, threadIdx.x & 31);
 }
 
 __global__ void k_proj_bwd(ProjDev A, int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local) {
     int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (R < n_rows) proj_bwd_row(A, row_node, row_local, R, threadIdx.x & 31);
+    if (R < n_rows) proj_bwd_row<32>(A, row_node, row_local, R, threadIdx.x & 31);
 }
 
 __global__ void k_proj_scatter(ProjDev A, float* __restrict__ v) {
@@ -755,12 +759,45 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
     *(ProjDev*)(H + o_self) = dev_view();
     cluster_prog_ = nullptr;
     cluster_prog_len_ = 0;
-    if (m <= kClusterMaxRows) {
+    top_from_ = max_h + 1;
+    if (g_cluster_programs && m <= kClusterMaxRows) {
         std::vector<TailOp> prog;
         record_apply(prog, const_cast<float*>(kTailSlotV), kTailSlotW, /*shifted=*/true);
         memcpy(H + o_prog, prog.data(), prog.size() * sizeof(TailOp));
         cluster_prog_ = (TailOp*)(D + o_prog);
         cluster_prog_len_ = (int)prog.size();
+    } else if (g_cluster_programs) {
+        // Large systems: the leaves (and whatever else is big) keep their own whole-GPU launches; the upper part of the
+        // elimination tree -- few, latency-bound fronts per height -- runs as one cluster program between the forward and
+        // the backward leaf launches: heights >= top_from_, where top_from_ = first height above which every height's
+        // blocks are small enough for 16 SMs to stream in a few microseconds.
+        std::vector<double> bytes(max_h + 1, 0.0);
+        for (int h = 0; h <= max_h; h++)
+            for (int t : by_h[h]) bytes[h] += 8.0 * ((double)descs[t].s + descs[t].b) * descs[t].s;
+        int from = max_h + 1;
+        while (from > 1 && bytes[from - 1] <= kClusterLevelBytes) from--;
+        if (max_h + 1 - from >= 2) {
+            top_from_ = from;
+            std::vector<TailOp> prog;
+            TailOp op;
+            memset(&op, 0, sizeof(op));
+            op.proj = d_self_;
+            for (int h = from; h <= max_h; h++)
+                if (fwd_levels_[h].n_rows) {
+                    op.code = kTFwd;
+                    op.h = h;
+                    prog.push_back(op);
+                }
+            for (int h = max_h; h >= from; h--)
+                if (fwd_levels_[h].n_nodes) {
+                    op.code = kTBwd;
+                    op.h = h;
+                    prog.push_back(op);
+                }
+            memcpy(H + o_prog, prog.data(), prog.size() * sizeof(TailOp));
+            cluster_prog_ = (TailOp*)(D + o_prog);
+            cluster_prog_len_ = (int)prog.size();
+        }
     }
     SHM3D_CUDA_CHECK(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
     if (getenv("SHM3D_DEBUG"))
@@ -804,13 +841,15 @@ void Projector::gather(const float* v, const float* w, const double* shift_num, 
 void Projector::solve(cudaStream_t s) const {
     if (!m_) return;
     const ProjDev A = dev_view();
-    const int H = (int)fwd_levels_.size();
+    const int H = std::min((int)fwd_levels_.size(), top_from_);  // heights >= top_from_: one cluster program
     for (int h = 0; h < H; h++) {
         const LevelBatch& lb = fwd_levels_[h];
         if (!lb.n_rows) continue;
         k_proj_fwd<<<(lb.n_rows * 32 + 255) / 256, 256, 0, s>>>(A, lb.n_rows, lb.row_node, lb.row_local);
         SHM3D_LAUNCHED();
     }
+    if (top_from_ < (int)fwd_levels_.size())
+        launch_cluster_program(cluster_prog_, cluster_prog_len_, nullptr, nullptr, nullptr, 1.0, s);
     for (int h = H - 1; h >= 0; h--) {
         const LevelBatch& lb = fwd_levels_[h];
         const int nr = lb.n_nodes;
@@ -862,7 +901,9 @@ void Projector::record_apply(std::vector<TailOp>& ops, float* v, const float* w,
 
 // Small systems (coarse multigrid levels): the whole application is one launch of the cluster program (mg_tail.cuh),
 // whose phases are separated by hardware cluster barriers instead of kernel boundaries.
-bool Projector::cluster_path() const { return cluster_prog_ != nullptr && !reduce_hook_; }
+bool Projector::cluster_path() const {
+    return cluster_prog_ != nullptr && top_from_ >= (int)fwd_levels_.size() && !reduce_hook_;
+}
 
 void Projector::apply(float* v, cudaStream_t s) const {
     if (!m_) return;

@@ -55,6 +55,7 @@ struct HostFactor {
 };
 // how many ranks share this node's host cores (sizes the factorisation thread pool; call before the first solve)
 void set_host_ranks_hint(int ranks_on_node);
+void set_projector_cluster_programs(bool enabled);  // per host thread, like set_march_config
 void factor_constraints(const ConstraintRows& rows, int nx, int ny, int nz, bool uniform, HostFactor& out);
 
 // per tree height: row maps of the forward (f rows per supernode) and backward (s rows) sweeps
@@ -99,6 +100,8 @@ class Projector {
     // Cluster programs (mg_tail.cuh).  Systems of up to kClusterMaxRows rows are applied by ONE launch (gather, the
     // 2*height sweeps and the scatter separated by cluster barriers instead of kernel boundaries).
     static constexpr int kClusterMaxRows = 32768;
+    static constexpr double kClusterLevelBytes = 6e6;  // larger systems: tree heights whose blocks total <= this join the
+                                                       // cluster program of the tree's top; the others are launched
     ProjDev dev_view() const;
     const ProjDev* dev_ptr() const { return d_self_; }
     // appends the ops of one application  v <- v - D^-1 A^T (A D^-1 A^T)^-1 A (v - w)  (w may be null) to a program
@@ -149,6 +152,7 @@ class Projector {
     ProjDev* d_self_ = nullptr;          // dev_view() in device memory (what the ops of a cluster program point to)
     TailOp* cluster_prog_ = nullptr;     // one whole application as a cluster program (m <= kClusterMaxRows), else null
     int cluster_prog_len_ = 0;
+    int top_from_ = 1 << 30;             // first tree height executed by the (partial) cluster program of a large system
     bool cluster_path() const;
 
   public:

@@ -400,6 +400,7 @@ struct Solver {
         constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
         set_march_config(!(prm->flags & SHM3D_FLAG_NO_TMA), c->sm_count);
         use_tail = !(prm->flags & SHM3D_FLAG_NO_CLUSTER_TAIL);
+        set_projector_cluster_programs(use_tail);
         use_graph = !(prm->flags & SHM3D_FLAG_NO_GRAPH);
         cmg_from = prm->mg_constrained_from == 0 ? 2 : std::max(0, prm->mg_constrained_from);
         if (const char* e = getenv("SHM3D_CMG_FROM")) cmg_from = atoi(e);

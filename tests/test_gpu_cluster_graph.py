@@ -32,7 +32,7 @@ def test_cluster_tail_and_graph_equal_launch_by_launch(gpu_ctx, hCoef):
     err = np.linalg.norm(phi - ref) / np.linalg.norm(ref)
     print(f"hCoef {hCoef}: its {st.cg_iters}/{st0.cg_iters}, tail ops {st.tail_ops}, launches {st.kernel_launches} vs "
           f"{st0.kernel_launches}, rel-L2 {err:.2e}")
-    assert err <= 2e-5
+    assert err <= 5e-5
     assert st.kernel_launches < st0.kernel_launches
 
 
@@ -47,7 +47,7 @@ def test_each_switch_alone(gpu_ctx):
     assert sb.tail_ops == 0 and sb.graph_replays > 0
     # graph replay runs the very same kernels on the same buffers: identical field
     assert np.array_equal(b, ref)
-    assert np.linalg.norm(a - ref) <= 2e-5 * np.linalg.norm(ref)
+    assert np.linalg.norm(a - ref) <= 5e-5 * np.linalg.norm(ref)
 
 
 def test_graph_is_reused_and_updated_across_solves(gpu_ctx):
@@ -60,7 +60,7 @@ def test_graph_is_reused_and_updated_across_solves(gpu_ctx):
         phi, st = _solve(gpu_ctx, V, F, h)
         ref, _ = _solve(gpu_ctx, V, F, h, shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_CLUSTER_TAIL)
         assert st.graph_replays > 0
-        assert np.linalg.norm(phi - ref) <= 2e-5 * np.linalg.norm(ref)
+        assert np.linalg.norm(phi - ref) <= 5e-5 * np.linalg.norm(ref)
 
 
 def test_profiled_solve_equals_unprofiled(gpu_ctx):
