@@ -64,8 +64,10 @@ extern "C" {
                                         * adapter and the class mirrors (a drop-in returns what the reference returns); a
                                         * caller filling shm3d_params by hand opts in. */
 #define SHM3D_FLAG_NO_TMA 128u          /* diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones */
-#define SHM3D_FLAG_NO_CLUSTER_TAIL 256u /* diagnostics: every multigrid level / projector tree level as its own launch instead of
-                                          the single-launch cluster programs (csrc/mg_tail.cuh) */
+#define SHM3D_FLAG_NO_CLUSTER_TAIL 256u /* diagnostics: every operation of the coarsest multigrid levels as its own launch instead
+                                          of the single-launch program (csrc/mg_tail.cuh) */
+#define SHM3D_FLAG_NO_PDL 1024u         /* diagnostics: the projector's sweep kernels launched fully serialised instead of with
+                                          programmatic dependent launch */
 #define SHM3D_FLAG_NO_GRAPH 512u        /* diagnostics: launch every PCG iteration kernel by kernel instead of replaying the
                                           captured CUDA graph */
 #define SHM3D_FLAG_PLAIN_MG 16u        /* unconstrained Poisson V-cycle as preconditioner, projector on the fine level only */

@@ -787,14 +787,19 @@ void launch_fast_integrate_z(const LevelDims& L, float cell, const float* Y, siz
     k_fast_z<<<(unsigned)((L.plane() + kT - 1) / kT), kT, 0, s>>>(L, cell, Y, cs, phi);
     POST();
 }
-void launch_cluster_program(const TailOp* d_ops, int n_ops, float* v, const float* w, const double* shift_num,
+void launch_cluster_program(const TailOp* d_ops, int n_ops, int ctas, float* v, const float* w, const double* shift_num,
                             double shift_den, cudaStream_t s) {
     if (n_ops <= 0) return;
-    const int cs = tail_cluster_size();
+    if (ctas <= 1) {
+        k_cluster_program<<<1, kTailThreads, 0, s>>>(d_ops, n_ops, v, w, shift_num, shift_den);
+        POST();
+        return;
+    }
+    const int cs = tail_cluster_size(ctas);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs);
     cfg.blockDim = dim3(kTailThreads);
-    cfg.dynamicSmemBytes = kTailSmemBytes;
+    cfg.dynamicSmemBytes = cs > 1 ? kTailSmemBytes : 0;
     cfg.stream = s;
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeClusterDimension;

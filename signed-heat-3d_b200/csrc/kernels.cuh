@@ -111,8 +111,8 @@ void launch_mg_prolong_add(const LevelDims& Lf, const LevelDims& Lc, float* x_pa
 void launch_mg_coarse_solve(int n3, const float* pinv, const float* b, float* x, cudaStream_t s);
 
 // ---------------------------------------------------------------- cluster programs (mg_tail.cuh)
-// A sequence of latency-bound multigrid / projector operations executed by ONE launch of one thread-block cluster,
-// with the hardware cluster barrier between consecutive ops.  Vector operands are interior pointers of padded level
+// A sequence of latency-bound multigrid / projector operations executed by ONE launch (one CTA, or one thread-block
+// cluster), with a CTA / cluster barrier between consecutive ops.  Vector operands are interior pointers of padded level
 // vectors; kTailSlotV / kTailSlotW stand for the v / w arguments of the launch.
 struct ProjDev;  // proj_dev.cuh
 enum TailCode : int {
@@ -141,7 +141,8 @@ struct TailOp {
 };
 #define kTailSlotV (reinterpret_cast<const float*>(uintptr_t(8)))
 #define kTailSlotW (reinterpret_cast<const float*>(uintptr_t(16)))
-void launch_cluster_program(const TailOp* d_ops, int n_ops, float* v, const float* w, const double* shift_num,
+// ctas = 1: one CTA, __syncthreads() between ops (what the solver uses); > 1: a thread-block cluster of up to 16 CTAs
+void launch_cluster_program(const TailOp* d_ops, int n_ops, int ctas, float* v, const float* w, const double* shift_num,
                             double shift_den, cudaStream_t s);
 
 }  // namespace shm3d

@@ -1,20 +1,22 @@
 // mg_tail.cuh -- the latency-bound tail of a V-cycle as ONE launch.  Included by grid_ops.cu inside its anonymous
-// namespace (after grid_rows.cuh, whose row bodies it reuses).
+// namespace (after the element-indexed kernels, whose helpers it reuses).
 //
-// Below ~64^3 every multigrid operation (and every level of the constraint projector's elimination tree) is a kernel of
-// a few microseconds whose cost is the launch itself: at 512^3 the projected levels 128^3 .. 8^3 were ~210 launches and
-// 1.3 ms of a 4.7 ms PCG iteration (profiles/r02_launches_sphere512_tma_first3000.csv).  Here such a sequence is a
-// PROGRAM -- an array of TailOp in device memory, recorded once per solve by the host -- interpreted by one thread-block
-// cluster (up to 16 CTAs on one GPC): every op is spread over all warps of the cluster, ops are separated by the
-// hardware cluster barrier (barrier.cluster arrive.release / wait.acquire: ~0.2 us, and ptxas emits the L1 invalidate
-// with it, so plain loads see what other CTAs of the cluster wrote in the previous op) instead of a kernel boundary
-// (~5 us).  Two kinds of program: the whole V-cycle from the first level with <= 64^3 nodes down to the dense coarsest
-// solve and back up (Solver::record_tail), and one application of a small projector (Projector::build).
+// Below ~32^3 every multigrid operation (and every level of the constraint projector's elimination tree) is a kernel of
+// a few microseconds whose cost is the launch boundary itself (~3.4 us per node even inside a CUDA graph): at 512^3 the
+// projected levels 32^3 .. 4^3 are ~90 launches per V-cycle.  Here that sequence is a PROGRAM -- an array of TailOp in
+// device memory, recorded once per solve by the host (Solver::record_tail) -- interpreted by ONE CTA of 1024 threads:
+// ops are separated by __syncthreads() (tens of cycles; the level's vectors and factor blocks stay in this SM's L1 / L2)
+// instead of a kernel boundary.
+// Measured on B200 (profiles/experiments/r02_pcg_probe_cluster16_vs_graph.jsonl): the first version ran the levels
+// <= 64^3 on a 16-CTA thread-block cluster with the hardware cluster barrier between ops; every barrier carries a
+// GPU-scope MEMBAR plus an L1 invalidate (SASS: MEMBAR.ALL.GPU, UCGABAR_ARV/WAIT, CCTL.IVALL), ~6 us per op all told --
+// slower than graph-replayed launches (4.78 vs 4.07 ms per PCG iteration).  The kernel still accepts a multi-CTA cluster
+// (launch_cluster_program's `ctas`), but the solver uses one CTA.
 #pragma once
 // (grid_ops.cu includes <cooperative_groups.h> at file scope before this header)
 
 constexpr int kTailThreads = 1024;          // 32 warps per CTA, <= 64 registers per thread
-constexpr int kTailSmemBytes = 120 * 1024;  // unused; asks for one CTA per SM so the cluster spreads over 16 SMs
+constexpr int kTailSmemBytes = 120 * 1024;  // multi-CTA launches only: unused, asks for one CTA per SM
 
 __device__ __forceinline__ const float* tail_in(const float* p, const float* v, const float* w) {
     return p == kTailSlotV ? v : (p == kTailSlotW ? w : p);
@@ -144,9 +146,11 @@ __global__ void __launch_bounds__(kTailThreads, 1)
                       double shift_den) {
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
+    const bool single = gridDim.x == 1;  // one CTA: ops are separated by __syncthreads()
     const unsigned wpb = kTailThreads / 32;
-    const unsigned gw = cl.block_rank() * wpb + (threadIdx.x >> 5), nw = cl.num_blocks() * wpb;
-    const unsigned gt = cl.block_rank() * kTailThreads + threadIdx.x, nt = cl.num_blocks() * kTailThreads;
+    const unsigned rank = single ? 0u : cl.block_rank(), nblk = single ? 1u : cl.num_blocks();
+    const unsigned gw = rank * wpb + (threadIdx.x >> 5), nw = nblk * wpb;
+    const unsigned gt = rank * kTailThreads + threadIdx.x, nt = nblk * kTailThreads;
     const int lane = threadIdx.x & 31;
     for (int i = 0; i < n_ops; i++) {
         const TailOp op = ops[i];
@@ -214,20 +218,17 @@ __global__ void __launch_bounds__(kTailThreads, 1)
             default:
                 break;
         }
-        cl.sync();
+        if (single) __syncthreads();
+        else cl.sync();
     }
 }
 
-// cluster size this device can co-schedule for the program kernel (16 = one GPC's worth, non-portable; else 8)
-inline int tail_cluster_size() {
-    static thread_local int cached[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+// largest cluster (<= want) this device can co-schedule for the program kernel (16 needs the non-portable opt-in)
+inline int tail_cluster_size(int want) {
     SHM3D_CUDA_CHECK(cudaFuncSetAttribute(k_cluster_program, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
     SHM3D_CUDA_CHECK(cudaFuncSetAttribute(k_cluster_program, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    int best = 0;
-    for (int cs : {16, 8, 4, 2, 1}) {
+    for (int cs : {16, 8, 4, 2}) {
+        if (cs > want) continue;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs);
         cfg.blockDim = dim3(kTailThreads);
@@ -239,13 +240,8 @@ inline int tail_cluster_size() {
         cfg.attrs = &at;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, k_cluster_program, &cfg) == cudaSuccess && n >= 1) {
-            best = cs;
-            break;
-        }
+        if (cudaOccupancyMaxActiveClusters(&n, k_cluster_program, &cfg) == cudaSuccess && n >= 1) return cs;
         cudaGetLastError();
     }
-    if (!best) throw Error(SHM3D_ERR_CUDA, "thread-block clusters are not available on this device");
-    if (dev >= 0 && dev < 64) cached[dev] = best;
-    return best;
+    return 1;
 }

@@ -268,39 +268,69 @@ bool partial_cholesky(double* F, int f, int s, bool par) {
 
 void set_host_ranks_hint(int ranks_on_node) { g_ranks_on_node = std::max(1, ranks_on_node); }
 
-// cluster programs (mg_tail.cuh) on/off for the projectors built by the calling host thread (SHM3D_FLAG_NO_CLUSTER_TAIL)
-static thread_local bool g_cluster_programs = true;
-void set_projector_cluster_programs(bool enabled) { g_cluster_programs = enabled; }
+// programmatic dependent launch of the sweep kernels on/off for the calling host thread (SHM3D_FLAG_NO_PDL)
+void set_projector_chained_launches(bool enabled);
 
 // ================================================================================================
 // device kernels
 // ================================================================================================
 namespace {
 
-__global__ void k_proj_gather(ProjDev A, const float* __restrict__ v, const float* __restrict__ w, const double* shift_num,
-                              double shift_den) {
+// The four kernels form a chain of ~2*height + 2 dependent launches of a few microseconds each.  They are launched with
+// programmatic dependent launch (launch_chained below): every kernel lets its successor's CTAs be scheduled right away
+// (griddepcontrol.launch_dependents) and then waits for its predecessor's writes (griddepcontrol.wait) before touching
+// memory, so the launch latency of step k+1 hides behind step k instead of adding to it.
+__device__ __forceinline__ void chain_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+__global__ void k_proj_gather(ProjDev A, const float* v, const float* w, const double* shift_num, double shift_den) {
+    chain_prologue();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.m) return;
     proj_gather_row(A, r, v, w, shift_num ? *shift_num / shift_den : 0.0);
 }
 
 // one warp per matrix row of the supernodes at one tree height (proj_dev.cuh)
-__global__ void k_proj_fwd(ProjDev A, int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local) {
+__global__ void k_proj_fwd(ProjDev A, int n_rows, const int* row_node, const int* row_local) {
+    chain_prologue();
     int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (R < n_rows) proj_fwd_row<32>(A, row_node, row_local, R, threadIdx.x & 31);
 }
 
-__global__ void k_proj_bwd(ProjDev A, int n_rows, const int* __restrict__ row_node, const int* __restrict__ row_local) {
+__global__ void k_proj_bwd(ProjDev A, int n_rows, const int* row_node, const int* row_local) {
+    chain_prologue();
     int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (R < n_rows) proj_bwd_row<32>(A, row_node, row_local, R, threadIdx.x & 31);
 }
 
-__global__ void k_proj_scatter(ProjDev A, float* __restrict__ v) {
+__global__ void k_proj_scatter(ProjDev A, float* v) {
+    chain_prologue();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < A.n_touched) proj_scatter_node(A, t, v);
 }
 
+// launch with the programmatic-stream-serialization attribute (the kernel must start with chain_prologue())
+static thread_local bool g_chained_launches = true;
+template <typename... KArgs, typename... Args>
+void launch_chained(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = g_chained_launches ? 1 : 0;
+    SHM3D_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+    SHM3D_LAUNCHED();
+}
+
 }  // namespace
+
+void set_projector_chained_launches(bool enabled) { g_chained_launches = enabled; }
 
 // ================================================================================================
 // Projector
@@ -369,7 +399,9 @@ void factor_constraints(const ConstraintRows& rows, int nx_, int ny_, int nz_, b
     nd.cell = rows.cell.data();
     // leaves of ~128 rows: two fewer tree levels (= 4 fewer launches per application) than with 40, for +8 % host time
     nd.leaf = 128;
+#ifdef SHM3D_TUNING_KNOBS
     if (const char* e = getenv("SHM3D_ND_LEAF")) nd.leaf = std::max(8, atoi(e));
+#endif
     nd.order.reserve(m);
     {
         std::vector<int> all(m);
@@ -662,7 +694,7 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
                  o_trow = B.take<int>(ent.size()), o_tw = B.take<double>(ent.size()),
                  o_nodes = B.take<ProjNodeDesc>(descs.size()), o_bidx = B.take<int>(hf.bidx.size()),
                  o_rowmaps = B.take<int>(n_rowmaps), o_levels = B.take<ProjLevelInfo>(max_h + 1),
-                 o_self = B.take<ProjDev>(1), o_prog = B.take<TailOp>(2 * (size_t)(max_h + 1) + 2);
+                 o_self = B.take<ProjDev>(1);
     const size_t upload_bytes = B.off;
     const size_t o_rhs = B.take<double>(m), o_y = B.take<double>(m), o_sol = B.take<double>(m);
     if (upload_bytes > h_arena_cap_) {
@@ -757,48 +789,6 @@ void Projector::build(const ConstraintRows& rows, const LevelDims& L, bool unifo
     d_sol_ = (double*)(D + o_sol);
     d_self_ = (ProjDev*)(D + o_self);
     *(ProjDev*)(H + o_self) = dev_view();
-    cluster_prog_ = nullptr;
-    cluster_prog_len_ = 0;
-    top_from_ = max_h + 1;
-    if (g_cluster_programs && m <= kClusterMaxRows) {
-        std::vector<TailOp> prog;
-        record_apply(prog, const_cast<float*>(kTailSlotV), kTailSlotW, /*shifted=*/true);
-        memcpy(H + o_prog, prog.data(), prog.size() * sizeof(TailOp));
-        cluster_prog_ = (TailOp*)(D + o_prog);
-        cluster_prog_len_ = (int)prog.size();
-    } else if (g_cluster_programs) {
-        // Large systems: the leaves (and whatever else is big) keep their own whole-GPU launches; the upper part of the
-        // elimination tree -- few, latency-bound fronts per height -- runs as one cluster program between the forward and
-        // the backward leaf launches: heights >= top_from_, where top_from_ = first height above which every height's
-        // blocks are small enough for 16 SMs to stream in a few microseconds.
-        std::vector<double> bytes(max_h + 1, 0.0);
-        for (int h = 0; h <= max_h; h++)
-            for (int t : by_h[h]) bytes[h] += 8.0 * ((double)descs[t].s + descs[t].b) * descs[t].s;
-        int from = max_h + 1;
-        while (from > 1 && bytes[from - 1] <= kClusterLevelBytes) from--;
-        if (max_h + 1 - from >= 2) {
-            top_from_ = from;
-            std::vector<TailOp> prog;
-            TailOp op;
-            memset(&op, 0, sizeof(op));
-            op.proj = d_self_;
-            for (int h = from; h <= max_h; h++)
-                if (fwd_levels_[h].n_rows) {
-                    op.code = kTFwd;
-                    op.h = h;
-                    prog.push_back(op);
-                }
-            for (int h = max_h; h >= from; h--)
-                if (fwd_levels_[h].n_nodes) {
-                    op.code = kTBwd;
-                    op.h = h;
-                    prog.push_back(op);
-                }
-            memcpy(H + o_prog, prog.data(), prog.size() * sizeof(TailOp));
-            cluster_prog_ = (TailOp*)(D + o_prog);
-            cluster_prog_len_ = (int)prog.size();
-        }
-    }
     SHM3D_CUDA_CHECK(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
     if (getenv("SHM3D_DEBUG"))
         fprintf(stderr, "[shm3d] projector m=%d: factor %.1f ms, maps+upload issue %.1f ms\n", m, (tb1 - tb0) * 1e3,
@@ -833,38 +823,32 @@ ProjDev Projector::dev_view() const {
 void Projector::gather(const float* v, const float* w, const double* shift_num, double shift_den,
                        cudaStream_t s) const {
     if (!m_) return;
-    k_proj_gather<<<(m_ + 127) / 128, 128, 0, s>>>(dev_view(), v, w, shift_num, shift_den);
-    SHM3D_LAUNCHED();
+    launch_chained(k_proj_gather, (m_ + 127) / 128, 128, s, dev_view(), v, w, shift_num, shift_den);
     if (reduce_hook_) reduce_hook_(d_rhs_, m_, s);
 }
 
 void Projector::solve(cudaStream_t s) const {
     if (!m_) return;
     const ProjDev A = dev_view();
-    const int H = std::min((int)fwd_levels_.size(), top_from_);  // heights >= top_from_: one cluster program
+    const int H = (int)fwd_levels_.size();
     for (int h = 0; h < H; h++) {
         const LevelBatch& lb = fwd_levels_[h];
         if (!lb.n_rows) continue;
-        k_proj_fwd<<<(lb.n_rows * 32 + 255) / 256, 256, 0, s>>>(A, lb.n_rows, lb.row_node, lb.row_local);
-        SHM3D_LAUNCHED();
+        launch_chained(k_proj_fwd, (lb.n_rows * 32 + 255) / 256, 256, s, A, lb.n_rows, (const int*)lb.row_node,
+                       (const int*)lb.row_local);
     }
-    if (top_from_ < (int)fwd_levels_.size())
-        launch_cluster_program(cluster_prog_, cluster_prog_len_, nullptr, nullptr, nullptr, 1.0, s);
     for (int h = H - 1; h >= 0; h--) {
         const LevelBatch& lb = fwd_levels_[h];
         const int nr = lb.n_nodes;
         if (!nr) continue;
-        k_proj_bwd<<<(nr * 32 + 255) / 256, 256, 0, s>>>(A, nr, d_rowmaps_ + bwd_off_[4 * h + 2],
-                                                          d_rowmaps_ + bwd_off_[4 * h + 3]);
-        SHM3D_LAUNCHED();
+        launch_chained(k_proj_bwd, (nr * 32 + 255) / 256, 256, s, A, nr, (const int*)(d_rowmaps_ + bwd_off_[4 * h + 2]),
+                       (const int*)(d_rowmaps_ + bwd_off_[4 * h + 3]));
     }
-    SHM3D_CUDA_CHECK(cudaGetLastError());
 }
 
 void Projector::scatter_sub(float* v, cudaStream_t s) const {
     if (!m_ || !n_touched_) return;
-    k_proj_scatter<<<(n_touched_ + 127) / 128, 128, 0, s>>>(dev_view(), v);
-    SHM3D_LAUNCHED();
+    launch_chained(k_proj_scatter, (n_touched_ + 127) / 128, 128, s, dev_view(), v);
 }
 
 void Projector::record_apply(std::vector<TailOp>& ops, float* v, const float* w, bool shifted) const {
@@ -899,15 +883,8 @@ void Projector::record_apply(std::vector<TailOp>& ops, float* v, const float* w,
     }
 }
 
-// Small systems (coarse multigrid levels): the whole application is one launch of the cluster program (mg_tail.cuh),
-// whose phases are separated by hardware cluster barriers instead of kernel boundaries.
-bool Projector::cluster_path() const {
-    return cluster_prog_ != nullptr && top_from_ >= (int)fwd_levels_.size() && !reduce_hook_;
-}
-
 void Projector::apply(float* v, cudaStream_t s) const {
     if (!m_) return;
-    if (cluster_path()) return launch_cluster_program(cluster_prog_, cluster_prog_len_, v, nullptr, nullptr, 1.0, s);
     gather(v, nullptr, nullptr, 1.0, s);
     solve(s);
     scatter_sub(v, s);
@@ -915,7 +892,6 @@ void Projector::apply(float* v, cudaStream_t s) const {
 
 void Projector::apply_update(float* v, const float* w, cudaStream_t s) const {
     if (!m_) return;
-    if (cluster_path()) return launch_cluster_program(cluster_prog_, cluster_prog_len_, v, w, nullptr, 1.0, s);
     gather(v, w, nullptr, 1.0, s);
     solve(s);
     scatter_sub(v, s);
@@ -923,7 +899,6 @@ void Projector::apply_update(float* v, const float* w, cudaStream_t s) const {
 
 void Projector::apply_shifted(float* v, const double* shift_num, double shift_den, cudaStream_t s) const {
     if (!m_) return;
-    if (cluster_path()) return launch_cluster_program(cluster_prog_, cluster_prog_len_, v, nullptr, shift_num, shift_den, s);
     gather(v, nullptr, shift_num, shift_den, s);
     solve(s);
     scatter_sub(v, s);

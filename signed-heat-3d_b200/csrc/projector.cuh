@@ -55,7 +55,7 @@ struct HostFactor {
 };
 // how many ranks share this node's host cores (sizes the factorisation thread pool; call before the first solve)
 void set_host_ranks_hint(int ranks_on_node);
-void set_projector_cluster_programs(bool enabled);  // per host thread, like set_march_config
+void set_projector_chained_launches(bool enabled);  // per host thread, like set_march_config
 void factor_constraints(const ConstraintRows& rows, int nx, int ny, int nz, bool uniform, HostFactor& out);
 
 // per tree height: row maps of the forward (f rows per supernode) and backward (s rows) sweeps
@@ -97,11 +97,8 @@ class Projector {
     void solve(cudaStream_t s) const;                         // sol_ = (A D^-1 A^T)^-1 rhs_
     void scatter_sub(float* v, cudaStream_t s) const;         // v -= D^-1 A^T sol_
 
-    // Cluster programs (mg_tail.cuh).  Systems of up to kClusterMaxRows rows are applied by ONE launch (gather, the
-    // 2*height sweeps and the scatter separated by cluster barriers instead of kernel boundaries).
-    static constexpr int kClusterMaxRows = 32768;
-    static constexpr double kClusterLevelBytes = 6e6;  // larger systems: tree heights whose blocks total <= this join the
-                                                       // cluster program of the tree's top; the others are launched
+    // Cluster programs (mg_tail.cuh): the V-cycle tail runs whole projector applications as ops of one launch.
+    static constexpr int kClusterMaxRows = 4096;  // largest system a single-CTA tail program takes on
     ProjDev dev_view() const;
     const ProjDev* dev_ptr() const { return d_self_; }
     // appends the ops of one application  v <- v - D^-1 A^T (A D^-1 A^T)^-1 A (v - w)  (w may be null) to a program
@@ -150,10 +147,6 @@ class Projector {
     ProjLevelInfo* d_levels_ = nullptr;  // [tree height] row maps per height, for the cluster programs
     int n_levels_ = 0;
     ProjDev* d_self_ = nullptr;          // dev_view() in device memory (what the ops of a cluster program point to)
-    TailOp* cluster_prog_ = nullptr;     // one whole application as a cluster program (m <= kClusterMaxRows), else null
-    int cluster_prog_len_ = 0;
-    int top_from_ = 1 << 30;             // first tree height executed by the (partial) cluster program of a large system
-    bool cluster_path() const;
 
   public:
     // multi-GPU: called on the gathered partial sums A v (m doubles on device) before the solve (allreduce)

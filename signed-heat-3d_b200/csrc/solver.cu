@@ -400,13 +400,19 @@ struct Solver {
         constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
         set_march_config(!(prm->flags & SHM3D_FLAG_NO_TMA), c->sm_count);
         use_tail = !(prm->flags & SHM3D_FLAG_NO_CLUSTER_TAIL);
-        set_projector_cluster_programs(use_tail);
+        set_projector_chained_launches(!(prm->flags & SHM3D_FLAG_NO_PDL));
+#ifdef SHM3D_TUNING_KNOBS
+        if (const char* e = getenv("SHM3D_TAIL_CTAS")) tail_ctas = atoi(e);
+        if (const char* e = getenv("SHM3D_TAIL_MAX_N")) tail_max_nodes = (size_t)atoi(e) * atoi(e) * atoi(e);
+#endif
         use_graph = !(prm->flags & SHM3D_FLAG_NO_GRAPH);
         cmg_from = prm->mg_constrained_from == 0 ? 2 : std::max(0, prm->mg_constrained_from);
+#ifdef SHM3D_TUNING_KNOBS  // experiment overrides: compiled out of the product library (csrc/build.sh -DSHM3D_TUNING_KNOBS)
         if (const char* e = getenv("SHM3D_CMG_FROM")) cmg_from = atoi(e);
         if (const char* e = getenv("SHM3D_NU_COARSE")) nu_coarse = atoi(e);
         if (const char* e = getenv("SHM3D_CHEBYSHEV")) chebyshev = atoi(e) != 0;
         if (const char* e = getenv("SHM3D_CHEB_A")) cheb_a = (float)atof(e);
+#endif
         if (c->sc.n < kNumSc) c->sc.alloc(kNumSc);
         if (c->counters.n < 4) c->counters.alloc(4);
         if (c->nonfinite.n < 1) c->nonfinite.alloc(1);
@@ -446,6 +452,16 @@ struct Solver {
             c->d_pos.upload(pos, 3 * M, s);
             c->d_area.upload(area, M, s);
         }
+        // every source must lie inside the node lattice: the shift (k_source_average) and the constraint rows index the
+        // eight corner nodes of its cell (the reference's own evaluateFunction / trilinearCoefficients, :405-464, assume it)
+        for (int64_t i = 0; i < M; i++)
+            for (int a = 0; a < 3; a++) {
+                const int na = a == 0 ? G.nx : (a == 1 ? G.ny : G.nz);
+                const double t = (pos[3 * i + a] - G.bmin[a]) / G.cell;
+                if (!(t >= 0.0) || !(t < (double)(na - 1)))  // (also rejects NaN)
+                    throw Error(SHM3D_ERR_INVALID_ARG, "source " + std::to_string(i) + " lies outside the grid (axis " +
+                                                           std::to_string(a) + "): the box must contain every source");
+            }
         st.ms_h2d += now_ms() - t0;
     }
 
@@ -602,7 +618,13 @@ struct Solver {
             }
             const LevelDims Lc = dims.back();
             if (dims.size() == 1 || (size_t)Lc.nx * Lc.ny * Lc.nz > 512 || (c->world > 1 && !repl.back())) {
-                // no usable hierarchy (odd sizes, uneven slabs) -> plain projected CG
+                // no usable hierarchy (odd sizes, uneven slabs) -> plain projected CG, which only small grids can afford
+                if (c->world > 1 && (size_t)L0.nx * L0.ny * L0.nz > (size_t)128 * 128 * 128)
+                    throw Error(SHM3D_ERR_INVALID_ARG,
+                                "slab-partitioned solve: nz = " + std::to_string(L0.nz) + " does not split into " +
+                                    std::to_string(c->world) + " z-slabs that coarsen cleanly (need nz divisible by "
+                                    "ranks * 2^levels); without the multigrid hierarchy the constrained CG would not "
+                                    "converge at this size -- use a rank count that divides nz / 8");
                 dims.resize(1);
                 geo.resize(1);
                 repl.resize(1);
@@ -680,7 +702,7 @@ struct Solver {
         std::vector<MGLevel>& lv = c->levels;
         MGLevel& Lv = lv[l];
         if (l == tail_level) {  // everything from here down and back up: one launch (b == Lv.b, result in Lv.x)
-            launch_cluster_program(c->tail_prog.p, tail_len, nullptr, nullptr, nullptr, 1.0, s);
+            launch_cluster_program(c->tail_prog.p, tail_len, tail_ctas, nullptr, nullptr, nullptr, 1.0, s);
             return;
         }
         if (l + 1 == (int)lv.size()) {
@@ -731,13 +753,15 @@ struct Solver {
                          /*exchange=*/k + 1 < nul);
     }
 
-    // ---------------------------------------------------------------- V-cycle tail as one cluster program
-    // From the first level with <= 64^3 nodes down, every operation of the V-cycle -- sweeps, transfers, the dense coarsest
+    // ---------------------------------------------------------------- V-cycle tail as one program launch
+    // From the first level with <= 32^3 nodes down, every operation of the V-cycle -- sweeps, transfers, the dense coarsest
     // solve and each tree level of the projected smoothers' multifrontal sweeps -- is a launch-latency-bound kernel of a
     // few microseconds.  record_tail() restates vcycle() for those levels as a program of TailOp (mg_tail.cuh) that one
-    // thread-block cluster executes in a single launch.  Recorded once per solve, after build_levels().
+    // CTA executes in a single launch.  Recorded once per solve, after build_levels().
     bool use_tail = true, use_graph = true;
     int tail_level = -1, tail_len = 0;
+    int tail_ctas = 1;                                 // one CTA (see mg_tail.cuh for the 16-CTA cluster measurement)
+    size_t tail_max_nodes = (size_t)32 * 32 * 32;      // first level the tail program takes over
     std::vector<TailOp> tail_host;
 
     void record_tail() {
@@ -748,7 +772,7 @@ struct Solver {
         if (!use_tail || !use_mg || nl < 3) return;
         int lt = -1;
         for (int l = 1; l + 1 < nl && lt < 0; l++)
-            if ((size_t)lv[l].L.nx * lv[l].L.ny * lv[l].L.nz <= (size_t)64 * 64 * 64 && (c->world == 1 || lv[l].replicated)) lt = l;
+            if ((size_t)lv[l].L.nx * lv[l].L.ny * lv[l].L.nz <= tail_max_nodes && (c->world == 1 || lv[l].replicated)) lt = l;
         if (lt < 0) return;
         for (int l = lt; l < nl; l++) {  // the row bodies need nx % 4 == 0 and factor-2 transfers
             if (lv[l].L.nx % 4 || lv[l].L.nzl() != lv[l].L.nz) return;

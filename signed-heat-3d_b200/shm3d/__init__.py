@@ -21,6 +21,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_FACTORIZATION, ERR_NO_CONVERGE
 FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_PROFILE = 1, 2, 4, 8, 16, 32
 FLAG_NO_TMA = 128         # diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones
 FLAG_NO_CLUSTER_TAIL = 256  # diagnostics: no single-launch cluster programs (V-cycle tail, small projectors)
+FLAG_NO_PDL = 1024        # diagnostics: projector sweep kernels without programmatic dependent launch
 FLAG_NO_GRAPH = 512       # diagnostics: PCG iterations launched kernel by kernel instead of CUDA-graph replays
 FLAG_FP64_UNDERFLOW = 64  # reproduce the reference's fp64 underflow in X.norm() at far nodes (include/shm3d_grid.h)
 
