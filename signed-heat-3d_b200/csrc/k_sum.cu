@@ -43,6 +43,34 @@ __device__ __forceinline__ float fast_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of work).  The two nodes a lane owns
+// (same x,y; z and z+2) travel as the low / high half of one 64-bit register; ptxas folds pack2(v, v) into the
+// instruction's scalar-broadcast operand form, so per-source constants need no extra moves.  Each half is computed by
+// the same IEEE operation (fma.rn / mul.rn / sub.rn) as the scalar form: results are bit-identical to it.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -241,24 +269,34 @@ k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict_
                 __syncwarp();
                 update_ref(px, py, pz0, bj, lam2, m0, cm0, X00, X01, X02);
                 update_ref(px, py, pz1, bj, lam2, m1, cm1, X10, X11, X12);
+                // the pair loop, both nodes of the lane at once in packed fp32 (low half: z0, high half: z1): per source
+                // 2 LDS.128 + 4 scalar (dx, dy, dx^2 + dy^2) + 9 packed + 4 MUFU = 19 issue slots for two pairs (the
+                // scalar form took 31: instruction issue was the co-limiter next to the MUFU pipe)
+                {
+                    const f32x2 pz = pack2(pz0, pz1), cm = pack2(cm0, cm1), nl = pack2(nlam2, nlam2);
+                    f32x2 Xx = pack2(X00, X10), Xy = pack2(X01, X11), Xz = pack2(X02, X12);
 #pragma unroll 4
-                for (int s = 0; s < rg.y; s++) {
-                    float4 p = s_src[w][0][s];
-                    float4 n = s_src[w][1][s];
-                    float dx = px - p.x, dy = py - p.y;
-                    float dxy2 = fmaf(dy, dy, dx * dx);
-                    float dz0 = pz0 - p.z, dz1 = pz1 - p.z;
-                    float r20 = fmaf(dz0, dz0, dxy2), r21 = fmaf(dz1, dz1, dxy2);
-                    float ri0 = fast_rsqrt(r20), ri1 = fast_rsqrt(r21);
-                    float r0 = r20 * ri0, r1 = r21 * ri1;
-                    float e0 = fast_ex2(fmaf(nlam2, r0, cm0)), e1 = fast_ex2(fmaf(nlam2, r1, cm1));
-                    float w0 = e0 * ri0, w1 = e1 * ri1;
-                    X00 = fmaf(w0, n.x, X00);
-                    X01 = fmaf(w0, n.y, X01);
-                    X02 = fmaf(w0, n.z, X02);
-                    X10 = fmaf(w1, n.x, X10);
-                    X11 = fmaf(w1, n.y, X11);
-                    X12 = fmaf(w1, n.z, X12);
+                    for (int s = 0; s < rg.y; s++) {
+                        const float4 p = s_src[w][0][s];
+                        const float4 n = s_src[w][1][s];
+                        const float dx = px - p.x, dy = py - p.y;
+                        const float dxy2 = fmaf(dy, dy, dx * dx);
+                        const f32x2 dz = sub2(pz, pack2(p.z, p.z));
+                        const f32x2 r2 = fma2(dz, dz, pack2(dxy2, dxy2));
+                        float r20, r21;
+                        unpack2(r2, r20, r21);
+                        const f32x2 ri = pack2(fast_rsqrt(r20), fast_rsqrt(r21));
+                        const f32x2 arg = fma2(nl, mul2(r2, ri), cm);
+                        float a0, a1;
+                        unpack2(arg, a0, a1);
+                        const f32x2 wgt = mul2(pack2(fast_ex2(a0), fast_ex2(a1)), ri);
+                        Xx = fma2(wgt, pack2(n.x, n.x), Xx);
+                        Xy = fma2(wgt, pack2(n.y, n.y), Xy);
+                        Xz = fma2(wgt, pack2(n.z, n.z), Xz);
+                    }
+                    unpack2(Xx, X00, X10);
+                    unpack2(Xy, X01, X11);
+                    unpack2(Xz, X02, X12);
                 }
                 npairs += 2ull * (unsigned)rg.y;
             }

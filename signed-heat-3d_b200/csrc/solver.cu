@@ -754,14 +754,14 @@ struct Solver {
     }
 
     // ---------------------------------------------------------------- V-cycle tail as one program launch
-    // From the first level with <= 32^3 nodes down, every operation of the V-cycle -- sweeps, transfers, the dense coarsest
+    // From the first level with <= 16^3 nodes down, every operation of the V-cycle -- sweeps, transfers, the dense coarsest
     // solve and each tree level of the projected smoothers' multifrontal sweeps -- is a launch-latency-bound kernel of a
     // few microseconds.  record_tail() restates vcycle() for those levels as a program of TailOp (mg_tail.cuh) that one
     // CTA executes in a single launch.  Recorded once per solve, after build_levels().
     bool use_tail = true, use_graph = true;
     int tail_level = -1, tail_len = 0;
     int tail_ctas = 1;                                 // one CTA (see mg_tail.cuh for the 16-CTA cluster measurement)
-    size_t tail_max_nodes = (size_t)32 * 32 * 32;      // first level the tail program takes over
+    size_t tail_max_nodes = (size_t)16 * 16 * 16;      // first level the tail program takes over (one quad per thread)
     std::vector<TailOp> tail_host;
 
     void record_tail() {
