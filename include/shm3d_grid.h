@@ -64,8 +64,8 @@ extern "C" {
                                         * adapter and the class mirrors (a drop-in returns what the reference returns); a
                                         * caller filling shm3d_params by hand opts in. */
 #define SHM3D_FLAG_NO_TMA 128u          /* diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones */
-#define SHM3D_FLAG_NO_CLUSTER_TAIL 256u /* diagnostics: every operation of the coarsest multigrid levels as its own launch instead
-                                          of the single-launch program (csrc/mg_tail.cuh) */
+#define SHM3D_FLAG_TAIL_PROGRAM 256u    /* experiment (off by default: measured 1 % slower than graph-replayed launches): the coarsest
+                                          multigrid levels (<= 16^3) as ONE launch of a recorded op program (csrc/mg_tail.cuh) */
 #define SHM3D_FLAG_NO_PDL 1024u         /* diagnostics: the projector's sweep kernels launched fully serialised instead of with
                                           programmatic dependent launch */
 #define SHM3D_FLAG_NO_GRAPH 512u        /* diagnostics: launch every PCG iteration kernel by kernel instead of replaying the
@@ -200,6 +200,11 @@ int shm3d_debug_tufted_weights(const double* P, int64_t nP, const int64_t* tris,
                                int64_t* n_flips_out, double* min_cotan_out, double* area_before_out);
 /* probe for the tests: the local Delaunay 1-ring of the origin among n tangent-plane points (returns the ring size) */
 int shm3d_debug_local_ring(const double* coords2d, int32_t n, int32_t* ring_out, int32_t* tri_after_out);
+/* test probe: which k-nearest-neighbour search shm3d_point_weights uses on the calling process.  0 (default): the
+ * restatement of nanoflann's kd-tree (ties among exactly equidistant points in its visiting order, like geometry-central);
+ * 1: an independent cell-list search with ties broken by point index -- identical wherever no distances tie, used by the
+ * tests as a cross-check of the former.  Not thread-safe; not part of the product path. */
+void shm3d_debug_knn_mode(int32_t mode);
 
 /* ---- Row N3: the consumer of phi, on the device -------------------------------------------------
  * The reference hands N doubles to polyscope, which narrows them to float32

@@ -20,6 +20,15 @@
 // Delaunay triangulation, total area preserved by the flips, the final cover intrinsically Delaunay, closed forms on
 // sampled spheres.  Any positive rescaling of all areas cancels in Steps 1-2 (normalisation) and in the shift.
 // kNN queries and local triangulations run on the host threads (chunks assembled in point order: thread-count independent).
+//
+// THIS FILE IS A PORT, not a re-design: `class KdTree` follows nanoflann (BSD 2-clause; Copyright 2008-2009 Marius Muja,
+// David G. Lowe; 2011-2016 Jose Luis Blanco) and `local_ring` follows geometry-central's local_triangulation.cpp (MIT;
+// Copyright 2017-2019 Nicholas Sharp and the geometry-central contributors) statement by statement; licence texts in
+// THIRD_PARTY_NOTICES.md at the repository root.  Why a port: measured with an independent kNN (knn_all_cells below,
+// ties by point index instead of the kd-tree's visiting order) four of the reference's five sample clouds give
+// bit-identical weights, but data/SprayBottle.pc -- the vertices of a structured mesh, full of exactly equidistant
+// neighbours -- changes h by 6e-5, single areas by up to 88 %, and phi by 1.8e-4 relative L2 (fp64 oracle, 32^3 and
+// 64^3): above the 1e-4 parity bar.  Identity with the reference therefore needs nanoflann's tie order itself.
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -405,6 +414,108 @@ void knn_all(const double* P, int64_t n, int k, std::vector<int64_t>& nbr) {
     });
 }
 
+// Own kNN: a uniform cell list over the cloud's bounding box, exact squared distances (x, y, z terms summed in that order),
+// neighbours ordered by (distance, index) -- i.e. ties are broken by point index, not by a search tree's visiting order.
+// Shells of cells around the query's cell are scanned until the (k+1)-th best distance is strictly inside the scanned
+// block.  Same result as knn_all wherever no two candidates are exactly equidistant from the query.
+void knn_all_cells(const double* P, int64_t n, int k, std::vector<int64_t>& nbr) {
+    nbr.assign((size_t)n * k, -1);
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; a++) lo[a] = hi[a] = P[a];
+    for (int64_t i = 1; i < n; i++)
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::min(lo[a], P[3 * i + a]);
+            hi[a] = std::max(hi[a], P[3 * i + a]);
+        }
+    double ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    if (!(ext > 0)) ext = 1;
+    const int G = (int)std::max(1.0, std::min(512.0, std::floor(std::cbrt((double)n))));
+    const double cs = ext / G * (1 + 1e-12);
+    int dims[3];
+    for (int a = 0; a < 3; a++) dims[a] = std::max(1, std::min(G, (int)std::floor((hi[a] - lo[a]) / cs) + 1));
+    auto cell_of = [&](const double* q, int* c) {
+        for (int a = 0; a < 3; a++) c[a] = std::max(0, std::min(dims[a] - 1, (int)std::floor((q[a] - lo[a]) / cs)));
+    };
+    const size_t ncell = (size_t)dims[0] * dims[1] * dims[2];
+    std::vector<int64_t> start(ncell + 1, 0), order((size_t)n);
+    std::vector<int> cid((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        int c[3];
+        cell_of(P + 3 * i, c);
+        cid[(size_t)i] = c[0] + dims[0] * (c[1] + dims[1] * c[2]);
+        start[(size_t)cid[(size_t)i] + 1]++;
+    }
+    for (size_t c = 0; c < ncell; c++) start[c + 1] += start[c];
+    {
+        std::vector<int64_t> fill(start.begin(), start.end() - 1);
+        for (int64_t i = 0; i < n; i++) order[(size_t)fill[(size_t)cid[(size_t)i]]++] = i;  // ascending index inside a cell
+    }
+    parallel_chunks(n, [&](int64_t i_begin, int64_t i_end, int) {
+        typedef std::pair<double, int64_t> Cand;  // (squared distance, index): lexicographic order = the tie rule
+        std::vector<Cand> best;                   // max-heap of the k+1 best so far
+        for (int64_t i = i_begin; i < i_end; i++) {
+            const double* q = P + 3 * i;
+            int c[3];
+            cell_of(q, c);
+            best.clear();
+            for (int R = 0;; R++) {
+                bool any_cell = false;
+                for (int z = c[2] - R; z <= c[2] + R; z++) {
+                    if (z < 0 || z >= dims[2]) continue;
+                    for (int y = c[1] - R; y <= c[1] + R; y++) {
+                        if (y < 0 || y >= dims[1]) continue;
+                        const bool inner_yz = std::abs(z - c[2]) < R && std::abs(y - c[1]) < R;
+                        for (int x = c[0] - R; x <= c[0] + R; x += (inner_yz && x == c[0] - R && R > 0) ? 2 * R : 1) {
+                            if (x < 0 || x >= dims[0]) continue;
+                            any_cell = true;
+                            const size_t cc = (size_t)x + (size_t)dims[0] * ((size_t)y + (size_t)dims[1] * (size_t)z);
+                            for (int64_t t = start[cc]; t < start[cc + 1]; t++) {
+                                const int64_t j = order[(size_t)t];
+                                double d = 0;
+                                for (int a = 0; a < 3; a++) {
+                                    const double diff = q[a] - P[3 * j + a];
+                                    d += diff * diff;
+                                }
+                                const Cand cd(d, j);
+                                if ((int)best.size() < k + 1) {
+                                    best.push_back(cd);
+                                    std::push_heap(best.begin(), best.end());
+                                } else if (cd < best.front()) {
+                                    std::pop_heap(best.begin(), best.end());
+                                    best.back() = cd;
+                                    std::push_heap(best.begin(), best.end());
+                                }
+                            }
+                        }
+                    }
+                }
+                if ((int)best.size() == k + 1) {
+                    // every point outside the scanned block is farther than the block's nearest face
+                    double dmin = 1e300;
+                    for (int a = 0; a < 3; a++) {
+                        if (c[a] - R > 0) dmin = std::min(dmin, q[a] - (lo[a] + cs * (c[a] - R)));
+                        if (c[a] + R < dims[a] - 1) dmin = std::min(dmin, (lo[a] + cs * (c[a] + R + 1)) - q[a]);
+                    }
+                    if (dmin == 1e300 || best.front().first < dmin * dmin) break;
+                }
+                if (!any_cell && R > std::max(dims[0], std::max(dims[1], dims[2]))) break;
+            }
+            std::sort(best.begin(), best.end());
+            // the point itself leaves the list; if it is not in it (k+1 or more exact duplicates), the last entry does
+            size_t self = best.size() - 1;
+            for (size_t t = 0; t < best.size(); t++)
+                if (best[t].second == i) {
+                    self = t;
+                    break;
+                }
+            for (size_t t = 0, o = 0; t < best.size() && o < (size_t)k; t++)
+                if (t != self) nbr[(size_t)i * k + o++] = best[t].second;
+        }
+    });
+}
+
+int g_knn_mode = 0;  // 0: knn_all (kd-tree order), 1: knn_all_cells (ties by index)
+
 // ---------------------------------------------------------------- tufted cover + intrinsic Delaunay flips
 struct CoverStats {
     int64_t flips = 0;
@@ -693,6 +804,8 @@ int shm3d_debug_tufted_weights(const double* P, int64_t nP, const int64_t* tris,
     return SHM3D_OK;
 }
 
+void shm3d_debug_knn_mode(int32_t mode) { g_knn_mode = mode; }
+
 int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_neighbors, double* areas_out,
                         double* h_out, int64_t* n_triangles_out, int64_t* n_flips_out, double* min_cotan_out,
                         double* area_before_out) {
@@ -705,7 +818,8 @@ int shm3d_point_weights(const double* P, const double* N, int64_t nP, int32_t k_
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now();
     std::vector<int64_t> nbr;
-    knn_all(P, nP, k, nbr);
+    if (g_knn_mode == 1) knn_all_cells(P, nP, k, nbr);
+    else knn_all(P, nP, k, nbr);
     if (dbg) std::fprintf(stderr, "[shm3d] point_weights: kNN %.3fs", now() - t0), t0 = now();
 
     std::vector<int64_t> tris;

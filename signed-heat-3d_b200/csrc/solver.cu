@@ -399,7 +399,7 @@ struct Solver {
         prof.on = (prm->flags & SHM3D_FLAG_PROFILE) != 0;
         constrained_mg = !(prm->flags & SHM3D_FLAG_PLAIN_MG);
         set_march_config(!(prm->flags & SHM3D_FLAG_NO_TMA), c->sm_count);
-        use_tail = !(prm->flags & SHM3D_FLAG_NO_CLUSTER_TAIL);
+        use_tail = (prm->flags & SHM3D_FLAG_TAIL_PROGRAM) != 0;
         set_projector_chained_launches(!(prm->flags & SHM3D_FLAG_NO_PDL));
 #ifdef SHM3D_TUNING_KNOBS
         if (const char* e = getenv("SHM3D_TAIL_CTAS")) tail_ctas = atoi(e);
@@ -753,12 +753,15 @@ struct Solver {
                          /*exchange=*/k + 1 < nul);
     }
 
-    // ---------------------------------------------------------------- V-cycle tail as one program launch
+    // ---------------------------------------------------------------- V-cycle tail as one program launch (opt-in experiment)
     // From the first level with <= 16^3 nodes down, every operation of the V-cycle -- sweeps, transfers, the dense coarsest
     // solve and each tree level of the projected smoothers' multifrontal sweeps -- is a launch-latency-bound kernel of a
     // few microseconds.  record_tail() restates vcycle() for those levels as a program of TailOp (mg_tail.cuh) that one
-    // CTA executes in a single launch.  Recorded once per solve, after build_levels().
-    bool use_tail = true, use_graph = true;
+    // CTA executes in a single launch.  Measured on B200 at 512^3 (profiles/experiments/r02_pcg_probe_*.jsonl), against the
+    // same iteration replayed from a CUDA graph (4.04 ms): 16-CTA cluster from 64^3 down 4.78 ms, one CTA from 32^3 down
+    // 4.32 ms, one CTA from 16^3 down 4.08 ms -- a graph node boundary (~3 us) is cheaper than an op of a 1- or 16-SM
+    // program whose loads all miss L1.  Hence SHM3D_FLAG_TAIL_PROGRAM is off by default.
+    bool use_tail = false, use_graph = true;
     int tail_level = -1, tail_len = 0;
     int tail_ctas = 1;                                 // one CTA (see mg_tail.cuh for the 16-CTA cluster measurement)
     size_t tail_max_nodes = (size_t)16 * 16 * 16;      // first level the tail program takes over (one quad per thread)

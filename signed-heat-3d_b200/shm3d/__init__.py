@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libshm3d_grid.so")
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NONFINITE, ERR_FACTORIZATION, ERR_NO_CONVERGENCE, ERR_NCCL = range(7)
 FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_PROFILE = 1, 2, 4, 8, 16, 32
 FLAG_NO_TMA = 128         # diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones
-FLAG_NO_CLUSTER_TAIL = 256  # diagnostics: no single-launch cluster programs (V-cycle tail, small projectors)
+FLAG_TAIL_PROGRAM = 256     # experiment, off by default: coarsest multigrid levels as one program launch (mg_tail.cuh)
 FLAG_NO_PDL = 1024        # diagnostics: projector sweep kernels without programmatic dependent launch
 FLAG_NO_GRAPH = 512       # diagnostics: PCG iterations launched kernel by kernel instead of CUDA-graph replays
 FLAG_FP64_UNDERFLOW = 64  # reproduce the reference's fp64 underflow in X.norm() at far nodes (include/shm3d_grid.h)
@@ -70,7 +70,7 @@ EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
            "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points", "shm3d_point_weights",
-           "shm3d_debug_local_ring", "shm3d_debug_tufted_weights", "shm3d_isosurface", "shm3d_isosurface_fetch",
+           "shm3d_debug_local_ring", "shm3d_debug_tufted_weights", "shm3d_debug_knn_mode", "shm3d_isosurface", "shm3d_isosurface_fetch",
            "shm3d_isosurface_device", "shm3d_slice", "shm3d_debug_stencil_op"]
 
 _lib = None
@@ -109,6 +109,8 @@ def lib():
         L.shm3d_version.restype = C.c_char_p
         L.shm3d_point_weights.argtypes = [dp, dp, C.c_int64, C.c_int32, dp, dp, i64p, i64p, dp, dp]
         L.shm3d_debug_local_ring.argtypes = [dp, C.c_int32, i32p, i32p]
+        L.shm3d_debug_knn_mode.argtypes = [C.c_int32]
+        L.shm3d_debug_knn_mode.restype = None
         L.shm3d_debug_tufted_weights.argtypes = [dp, C.c_int64, i64p, C.c_int64, dp, dp, i64p, dp, dp]
         L.shm3d_isosurface.argtypes = [vp, PP, vp, C.c_int32, C.c_float, fp, fp, C.c_uint32, C.POINTER(IsoStats)]
         L.shm3d_isosurface_fetch.argtypes = [vp, fp, C.POINTER(C.c_uint32)]

@@ -1,5 +1,5 @@
-"""The single-launch tail program (csrc/mg_tail.cuh: the V-cycle from 32^3 down as ONE launch), the programmatic dependent
-launch of the projector sweeps and the CUDA-graph replay of the PCG iteration (csrc/solver.cu run_pcg) against the
+"""The CUDA-graph replay of the PCG iteration (csrc/solver.cu run_pcg), the programmatic dependent launch of the projector
+sweeps, and the opt-in single-launch tail program (csrc/mg_tail.cuh: the V-cycle from 16^3 down as ONE launch) against the
 fully serialised kernel-by-kernel path they replace: same operations in the same order (only the dense coarsest solve sums in another order), so the fields
 agree to fp32 rounding and the iteration counts match.  The parity tests against the oracle run the default (cluster
 programs + graph) path; this file pins the two paths to each other and checks that the fast path is really taken."""
@@ -23,8 +23,8 @@ def test_cluster_tail_and_graph_equal_launch_by_launch(gpu_ctx, hCoef):
     import shm3d
     from conftest import icosphere
     V, F = icosphere(3)
-    phi, st = _solve(gpu_ctx, V, F, hCoef)
-    ref, st0 = _solve(gpu_ctx, V, F, hCoef, shm3d.FLAG_NO_CLUSTER_TAIL | shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_PDL)
+    phi, st = _solve(gpu_ctx, V, F, hCoef, shm3d.FLAG_TAIL_PROGRAM)
+    ref, st0 = _solve(gpu_ctx, V, F, hCoef, shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_PDL)
     assert st0.tail_ops == 0 and st0.graph_replays == 0
     assert st.tail_ops > 0, "the V-cycle tail did not run as a cluster program"
     assert st.graph_replays >= st.cg_iters - 2 > 0, "the PCG iterations were not replayed from the captured graph"
@@ -40,9 +40,9 @@ def test_each_switch_alone(gpu_ctx):
     import shm3d
     from conftest import icosphere
     V, F = icosphere(3)
-    ref, st0 = _solve(gpu_ctx, V, F, 2, shm3d.FLAG_NO_CLUSTER_TAIL | shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_PDL)
-    a, sa = _solve(gpu_ctx, V, F, 2, shm3d.FLAG_NO_GRAPH)
-    b, sb = _solve(gpu_ctx, V, F, 2, shm3d.FLAG_NO_CLUSTER_TAIL | shm3d.FLAG_NO_PDL)
+    ref, st0 = _solve(gpu_ctx, V, F, 2, shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_PDL)
+    a, sa = _solve(gpu_ctx, V, F, 2, shm3d.FLAG_NO_GRAPH | shm3d.FLAG_TAIL_PROGRAM)
+    b, sb = _solve(gpu_ctx, V, F, 2, shm3d.FLAG_NO_PDL)
     assert sa.tail_ops > 0 and sa.graph_replays == 0
     assert sb.tail_ops == 0 and sb.graph_replays > 0
     # graph replay runs the very same kernels on the same buffers (only the order of the forward sweep's fp64 atomics
@@ -59,7 +59,7 @@ def test_graph_is_reused_and_updated_across_solves(gpu_ctx):
     for sub, h in ((3, 2), (2, 2), (3, 1), (3, 2)):
         V, F = icosphere(sub, radius=1.0 + 0.1 * sub)
         phi, st = _solve(gpu_ctx, V, F, h)
-        ref, _ = _solve(gpu_ctx, V, F, h, shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_CLUSTER_TAIL | shm3d.FLAG_NO_PDL)
+        ref, _ = _solve(gpu_ctx, V, F, h, shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_PDL)
         assert st.graph_replays > 0
         assert np.linalg.norm(phi - ref) <= 5e-5 * np.linalg.norm(ref)
 

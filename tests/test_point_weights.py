@@ -337,3 +337,26 @@ def test_gpu_point_overload_with_tufted_weights_matches_oracle(gpu_ctx):
     assert len(src) == st.m_constraints
     assert np.abs(v[src] + st.shift).max() < 2e-4 * np.abs(phi).max()   # pinned cells interpolate to the common level
     assert phi[0] > 0 and phi[-1] > 0 and o.evaluate_function(g, np.asarray(phi), c[None, :])[0] < 0
+
+
+def test_kdtree_port_equals_independent_knn_where_no_distances_tie():
+    """Cross-check of the nanoflann restatement: an independent cell-list kNN (ties by point index) must give the very same
+    weights on clouds without exactly equidistant neighbours -- random samples and the bunny cloud.  (On data/SprayBottle.pc,
+    a structured mesh's vertices, the two differ: phi moves by 1.8e-4, which is why the port is the product path.)"""
+    L = shm3d.lib()
+    rng = np.random.default_rng(5)
+    clouds = []
+    X = rng.standard_normal((6000, 3))
+    X /= np.linalg.norm(X, axis=1)[:, None]
+    clouds.append((X * [1.0, 0.8, 1.3], X / [1.0, 0.8, 1.3]))
+    d = np.load(os.path.join(GOLDEN, "bunny_pc.npz"))
+    clouds.append((d["P"], d["N"]))
+    try:
+        for P, N in clouds:
+            L.shm3d_debug_knn_mode(0)
+            a0, h0, nt0 = shm3d.point_weights(P, N)
+            L.shm3d_debug_knn_mode(1)
+            a1, h1, nt1 = shm3d.point_weights(P, N)
+            assert nt0 == nt1 and h0 == h1 and np.array_equal(a0, a1)
+    finally:
+        L.shm3d_debug_knn_mode(0)

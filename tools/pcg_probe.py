@@ -23,9 +23,9 @@ def main():
     dev = torch.device("cuda", 0)
     d_pos, d_nrm, d_area = (torch.from_numpy(a).to(dev) for a in (pos, nrm, area))
     d_phi = torch.empty(p.N, dtype=torch.float32, device=dev)
-    variants = [("default (tail program + PDL sweeps + graph)", 0), ("no graph", shm3d.FLAG_NO_GRAPH),
-                ("no tail program", shm3d.FLAG_NO_CLUSTER_TAIL), ("no PDL", shm3d.FLAG_NO_PDL),
-                ("none (round-1 launch structure)", shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_CLUSTER_TAIL | shm3d.FLAG_NO_PDL),
+    variants = [("default (graph replay + PDL sweeps)", 0), ("no graph", shm3d.FLAG_NO_GRAPH),
+                ("+ tail program", shm3d.FLAG_TAIL_PROGRAM), ("no PDL", shm3d.FLAG_NO_PDL),
+                ("none (round-1 launch structure)", shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_PDL),
                 ("default + profile", shm3d.FLAG_PROFILE)]
     for name, fl in variants:
         best = None
