@@ -7,10 +7,12 @@
 // Here shm3d_solve_device leaves phi in HBM as float32 and four launches produce the same indexed mesh -- identical
 // vertex coordinates, vertex numbering and triangle order (logic and its derivation: isosurface_core.h):
 //
-//   k_mc_count      one thread per lattice column (fixed j,i; marching along k), lanes along i so that every step reads
-//                   contiguous rows of the k-plane; per column: vertices created, triangles emitted      [reads phi once]
+//   k_mc_count      one thread per lattice column (fixed j,i; marching along k), lanes along i: two coalesced rows per
+//                   warp and plane, the z+1 corners as sign bits by shuffle, eight planes of loads in flight; per column:
+//                   vertices created, triangles emitted, first / last non-trivial cell                 [reads phi once]
 //   k_mc_scan       exclusive scan of the (nx-1)(ny-1) column counts (one CTA)
-//   k_mc_vertices   columns that create vertices march again and write positions + per-column search keys
+//   k_mc_vertices   columns that create vertices march again (first..last non-trivial cell only) and write positions +
+//                   per-column search keys
 //   k_mc_triangles  columns that emit triangles march again and resolve each corner to a vertex id by locating the
 //                   creating cell's column and bisecting its short key list
 //
@@ -39,18 +41,59 @@ __device__ __forceinline__ void load_table(unsigned long long* s_tab) {
     __syncthreads();
 }
 
+// Count pass.  A warp owns the 32 columns (y; z0..z0+31) and marches along lattice X (the slowest memory axis): per plane
+// every lane loads its own two nodes (y,z) and (y+1,z) -- two coalesced 128-byte rows per warp -- and gets the two nodes
+// at z+1 as sign bits from the next lane by one shuffle (the last lane of a row segment loads them itself).  The loads of
+// kCountAhead planes are issued before any of them is used, so each thread keeps 2*kCountAhead (+2) requests in flight:
+// the first version (one plane at a time, four loads per step) was latency-bound at 0.04 of the HBM roofline.
+constexpr int kCountAhead = 8;
+
 __global__ void __launch_bounds__(kLanesZ* kRowsY)
     k_mc_count(const Lattice L, const float* __restrict__ field, unsigned int* __restrict__ col_v,
-               unsigned int* __restrict__ col_t) {
+               unsigned int* __restrict__ col_t, unsigned int* __restrict__ col_x) {
     __shared__ unsigned long long s_tab[256];
     load_table(s_tab);
     int y, z;
-    if (!mc::thread_column(L, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, y, z)) return;
-    mc::CountVisitor cv{s_tab, y, z, 0u, 0u};
-    mc::march_column(L, field, y, z, cv);
+    const bool active = mc::thread_column(L, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, y, z);
+    if (y >= L.SY - 1) return;  // (y is warp-uniform: the whole warp leaves)
+    const int lane = threadIdx.x;
+    const int zc = min(z, L.SZ - 2);  // idle lanes (z beyond the last column) still take part in the shuffles
+    const bool own_next = lane == kLanesZ - 1 || z >= L.SZ - 2;  // nobody to shuffle the z+1 nodes from
+    const float niso = -L.isoval;
+    const float* p = field + (long long)y * L.SZ + zc;
+    auto nibble = [&](float v0, float v1, float w0, float w1) {
+        const unsigned mine = mc::sign_bit(niso, v0) | (mc::sign_bit(niso, v1) << 1);
+        unsigned next = __shfl_down_sync(0xffffffffu, mine, 1);
+        if (own_next) next = mc::sign_bit(niso, w0) | (mc::sign_bit(niso, w1) << 1);
+        return mine | (next << 2);
+    };
+    unsigned n_prev = nibble(p[0], p[L.SZ], own_next ? p[1] : 0.f, own_next ? p[L.SZ + 1] : 0.f);
+    mc::ColumnCount cc{0u, 0u, 0, 0};
+    const int ncell = L.SX - 1;
+    for (int x0 = 0; x0 < ncell; x0 += kCountAhead) {
+        float v0[kCountAhead], v1[kCountAhead], w0[kCountAhead], w1[kCountAhead];
+#pragma unroll
+        for (int u = 0; u < kCountAhead; u++) {
+            const float* q = p + (long long)min(x0 + u + 1, ncell) * L.strideX;
+            v0[u] = q[0];
+            v1[u] = q[L.SZ];
+            w0[u] = own_next ? q[1] : 0.f;
+            w1[u] = own_next ? q[L.SZ + 1] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kCountAhead; u++) {
+            if (x0 + u < ncell) {  // (warp-uniform)
+                const unsigned n_cur = nibble(v0[u], v1[u], w0[u], w1[u]);
+                mc::count_cell(cc, s_tab, mc::case_of_nibbles(n_prev, n_cur), x0 + u, y, zc);
+                n_prev = n_cur;
+            }
+        }
+    }
+    if (!active) return;
     const int c = mc::column_id(L, y, z);
-    col_v[c] = cv.nv;
-    col_t[c] = cv.nt;
+    col_v[c] = cc.nv;
+    col_t[c] = cc.nt;
+    col_x[c] = mc::pack_range(cc.x_lo, cc.x_hi);
 }
 
 // one CTA: thread t owns a contiguous chunk of the n column counts (mc::scan_chunk)
@@ -82,20 +125,22 @@ __global__ void __launch_bounds__(kScanThreads)
 
 __global__ void __launch_bounds__(kLanesZ* kRowsY)
     k_mc_vertices(const Lattice L, const float* __restrict__ field, const unsigned long long* __restrict__ voff,
-                  float* __restrict__ vertices, uint32_t* __restrict__ vkey) {
+                  const unsigned int* __restrict__ col_x, float* __restrict__ vertices, uint32_t* __restrict__ vkey) {
     int y, z;
     if (!mc::thread_column(L, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, y, z)) return;
     const int c = mc::column_id(L, y, z);
     const unsigned long long v0 = voff[c];
     if (voff[c + 1] == v0) return;  // this column creates nothing: no need to read it again
+    int x_lo, x_hi;
+    mc::unpack_range(col_x[c], x_lo, x_hi);  // only the cells between the column's first and last non-trivial case
     mc::VertexVisitor vv{&L, y, z, v0, vertices, vkey};
-    mc::march_column(L, field, y, z, vv);
+    mc::march_column(L, field, y, z, vv, x_lo, x_hi);
 }
 
 __global__ void __launch_bounds__(kLanesZ* kRowsY)
     k_mc_triangles(const Lattice L, const float* __restrict__ field, const unsigned long long* __restrict__ voff,
-                   const unsigned long long* __restrict__ toff, const uint32_t* __restrict__ vkey,
-                   uint32_t* __restrict__ triangles) {
+                   const unsigned long long* __restrict__ toff, const unsigned int* __restrict__ col_x,
+                   const uint32_t* __restrict__ vkey, uint32_t* __restrict__ triangles) {
     __shared__ unsigned long long s_tab[256];
     load_table(s_tab);
     int y, z;
@@ -103,8 +148,10 @@ __global__ void __launch_bounds__(kLanesZ* kRowsY)
     const int c = mc::column_id(L, y, z);
     const unsigned long long t0 = toff[c];
     if (toff[c + 1] == t0) return;
+    int x_lo, x_hi;
+    mc::unpack_range(col_x[c], x_lo, x_hi);
     mc::TriangleVisitor tv{&L, s_tab, voff, vkey, y, z, t0, triangles};
-    mc::march_column(L, field, y, z, tv);
+    mc::march_column(L, field, y, z, tv, x_lo, x_hi);
 }
 
 __global__ void k_narrow_f64(const double* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -188,15 +235,17 @@ IsoResult IsoSurface::extract(cudaStream_t s, int nx, int ny, int nz, const floa
     const int nc = L.ncols();
     col_v_.alloc((size_t)nc);
     col_t_.alloc((size_t)nc);
+    col_x_.alloc((size_t)nc);
     voff_.alloc((size_t)nc + 1);
     toff_.alloc((size_t)nc + 1);
     unsigned gx, gy;
     mc::launch_grid(L, gx, gy);
     const dim3 block(kLanesZ, kRowsY), grid(gx, gy);
     if (grid.y > 65535u) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: ny too large");
+    if (L.SX > 65535) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: nz too large");  // (the packed per-column cell range)
     IsoResult res;
     SHM3D_CUDA_CHECK(cudaEventRecord(ev0_, s));
-    k_mc_count<<<grid, block, 0, s>>>(L, d_field, col_v_.p, col_t_.p);
+    k_mc_count<<<grid, block, 0, s>>>(L, d_field, col_v_.p, col_t_.p, col_x_.p);
     SHM3D_LAUNCHED();
     k_mc_scan<<<1, kScanThreads, 0, s>>>(col_v_.p, col_t_.p, nc, voff_.p, toff_.p);
     SHM3D_LAUNCHED();
@@ -210,13 +259,13 @@ IsoResult IsoSurface::extract(cudaStream_t s, int nx, int ny, int nz, const floa
     if (nV > 0) {
         verts_.alloc((size_t)(3 * nV));
         vkey_.alloc((size_t)nV);
-        k_mc_vertices<<<grid, block, 0, s>>>(L, d_field, voff_.p, verts_.p, vkey_.p);
+        k_mc_vertices<<<grid, block, 0, s>>>(L, d_field, voff_.p, col_x_.p, verts_.p, vkey_.p);
         SHM3D_LAUNCHED();
         res.launches++;
     }
     if (nT > 0) {  // a triangle only references edges that cross, i.e. vertices that exist
         tris_.alloc((size_t)(3 * nT));
-        k_mc_triangles<<<grid, block, 0, s>>>(L, d_field, voff_.p, toff_.p, vkey_.p, tris_.p);
+        k_mc_triangles<<<grid, block, 0, s>>>(L, d_field, voff_.p, toff_.p, col_x_.p, vkey_.p, tris_.p);
         SHM3D_LAUNCHED();
         res.launches++;
     }

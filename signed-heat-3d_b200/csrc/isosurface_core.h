@@ -170,12 +170,16 @@ MC_HD void edge_vertex(const Lattice& L, int e, int x, int y, int z, const float
 // March column (y,z) along X.  `visit(x, cfg, vs)` is called for every cell whose case is neither 0 nor 255, in
 // increasing x.  field index of lattice node (X,Y,Z) = X*strideX + Y*SZ + Z.  Per step the four values of the next X
 // plane are loaded; a warp whose lanes hold consecutive z reads four (nearly) contiguous 128-byte rows.
+// [x_begin, x_end): the cells of the column to visit -- the whole column, or the range outside which the count pass
+// found only trivial cells (cases 0 / 255 create and emit nothing, so skipping them changes no output).
 template <typename Visit>
-MC_HD void march_column(const Lattice& L, const float* __restrict__ field, int y, int z, Visit& visit) {
-    const float* p = field + (long long)y * L.SZ + z;
+MC_HD void march_column(const Lattice& L, const float* __restrict__ field, int y, int z, Visit& visit, int x_begin = 0,
+                        int x_end = -1) {
+    if (x_end < 0) x_end = L.SX - 1;
+    const float* p = field + (long long)x_begin * L.strideX + (long long)y * L.SZ + z;
     const float niso = -L.isoval;
     float a0 = fadd(niso, p[0]), a1 = fadd(niso, p[L.SZ]), a2 = fadd(niso, p[1]), a3 = fadd(niso, p[L.SZ + 1]);
-    for (int x = 0; x < L.SX - 1; x++) {
+    for (int x = x_begin; x < x_end; x++) {
         p += L.strideX;
         float b0 = fadd(niso, p[0]), b1 = fadd(niso, p[L.SZ]), b2 = fadd(niso, p[1]), b3 = fadd(niso, p[L.SZ + 1]);
         unsigned cfg = (unsigned)(a0 < 0.f) | ((unsigned)(b0 < 0.f) << 1) | ((unsigned)(a1 < 0.f) << 2) |
@@ -190,6 +194,35 @@ MC_HD void march_column(const Lattice& L, const float* __restrict__ field, int y
         a2 = b2;
         a3 = b3;
     }
+}
+
+// ---- the count pass in bit form (k_mc_count): one sign nibble per column and lattice plane, two nibbles = one case ----
+// nibble of plane X for column (y,z): bit0 = node (y,z), bit1 = (y+1,z), bit2 = (y,z+1), bit3 = (y+1,z+1) below the level
+MC_HD unsigned sign_bit(float niso, float v) { return (unsigned)(fadd(niso, v) < 0.f); }
+// case number of the cell between plane X (nibble n0) and plane X+1 (nibble n1): corner c of march_column's cfg is
+// bit 2*(c/2) of n0 (even c) or of n1 (odd c)
+MC_HD unsigned case_of_nibbles(unsigned n0, unsigned n1) {
+    unsigned s0 = (n0 & 1u) | ((n0 & 2u) << 1) | ((n0 & 4u) << 2) | ((n0 & 8u) << 3);
+    unsigned s1 = (n1 & 1u) | ((n1 & 2u) << 1) | ((n1 & 4u) << 2) | ((n1 & 8u) << 3);
+    return s0 | (s1 << 1);
+}
+// per-column record of the count pass: vertices created, triangles emitted, and the cell range [x_lo, x_hi) outside which
+// every cell of the column is trivial (x_lo = x_hi = 0 for a column the surface does not touch)
+struct ColumnCount {
+    unsigned nv, nt;
+    int x_lo, x_hi;
+};
+MC_HD void count_cell(ColumnCount& cc, const unsigned long long* table, unsigned cfg, int x, int y, int z) {
+    if (cfg == 0u || cfg == 255u) return;
+    cc.nv += (unsigned)popcount(crossing_mask(cfg) & creator_mask(x, y, z));
+    cc.nt += (unsigned)(table[cfg] & 0xFull);
+    if (cc.x_hi == 0) cc.x_lo = x;
+    cc.x_hi = x + 1;
+}
+MC_HD unsigned pack_range(int x_lo, int x_hi) { return (unsigned)x_lo | ((unsigned)x_hi << 16); }  // SX <= 65535
+MC_HD void unpack_range(unsigned r, int& x_lo, int& x_hi) {
+    x_lo = (int)(r & 0xFFFFu);
+    x_hi = (int)(r >> 16);
 }
 
 // ---- launch geometry and the chunked scan, shared with the host emulation ------------------------------------------

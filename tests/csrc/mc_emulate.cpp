@@ -39,12 +39,32 @@ extern "C" int mc_emulate(const float* field, int nx, int ny, int nz, float isov
     };
     // k_mc_count
     std::vector<unsigned> col_v(nc, 0xdeadbeefu), col_t(nc, 0xdeadbeefu);
+    std::vector<unsigned> col_x(nc, 0xdeadbeefu);
+    int count_mismatch = 0;
     for_each_thread([&](int y, int z) {
+        // the kernel's bit form: one sign nibble per plane (its z+1 half comes from the next lane there), two nibbles = a case
+        const float niso = -L.isoval;
+        auto nibble = [&](int x) {
+            const float* q = field + (long long)x * L.strideX + (long long)y * L.SZ + z;
+            return sign_bit(niso, q[0]) | (sign_bit(niso, q[L.SZ]) << 1) | (sign_bit(niso, q[1]) << 2) |
+                   (sign_bit(niso, q[L.SZ + 1]) << 3);
+        };
+        ColumnCount cc{0u, 0u, 0, 0};
+        unsigned n_prev = nibble(0);
+        for (int x = 0; x < L.SX - 1; x++) {
+            const unsigned n_cur = nibble(x + 1);
+            count_cell(cc, kTable, case_of_nibbles(n_prev, n_cur), x, y, z);
+            n_prev = n_cur;
+        }
+        // ... must equal the visitor form the emit passes use
         CountVisitor cv{kTable, y, z, 0u, 0u};
         march_column(L, field, y, z, cv);
-        col_v[column_id(L, y, z)] = cv.nv;
-        col_t[column_id(L, y, z)] = cv.nt;
+        if (cv.nv != cc.nv || cv.nt != cc.nt) count_mismatch = 1;
+        col_v[column_id(L, y, z)] = cc.nv;
+        col_t[column_id(L, y, z)] = cc.nt;
+        col_x[column_id(L, y, z)] = pack_range(cc.x_lo, cc.x_hi);
     });
+    if (count_mismatch) return 6;
     // k_mc_scan: phase 1 (chunk sums), the CTA-wide inclusive scan, phase 2 (chunk writes)
     std::vector<unsigned long long> voff(nc + 1, ~0ull), toff(nc + 1, ~0ull), sv(kScanThreads), st(kScanThreads), a(kScanThreads),
         c(kScanThreads);
@@ -86,16 +106,20 @@ extern "C" int mc_emulate(const float* field, int nx, int ny, int nz, float isov
     for_each_thread([&](int y, int z) {
         const int col = column_id(L, y, z);
         if (voff[col + 1] == voff[col]) return;
+        int x_lo, x_hi;
+        unpack_range(col_x[col], x_lo, x_hi);
         VertexVisitor vv{&L, y, z, voff[col], vertices, vkey.data()};
-        march_column(L, field, y, z, vv);
+        march_column(L, field, y, z, vv, x_lo, x_hi);
         if (vv.v != voff[col + 1]) bad = 3;
     });
     // k_mc_triangles
     for_each_thread([&](int y, int z) {
         const int col = column_id(L, y, z);
         if (toff[col + 1] == toff[col]) return;
+        int x_lo, x_hi;
+        unpack_range(col_x[col], x_lo, x_hi);
         TriangleVisitor tv{&L, kTable, voff.data(), vkey.data(), y, z, toff[col], triangles};
-        march_column(L, field, y, z, tv);
+        march_column(L, field, y, z, tv, x_lo, x_hi);
         if (tv.t != toff[col + 1]) bad = 4;
     });
     if (bad) return bad;
