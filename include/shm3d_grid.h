@@ -224,7 +224,10 @@ typedef struct shm3d_iso_stats {
 } shm3d_iso_stats;
 /* Uses p->nx,ny,nz (and bbox_min, cell when the bounds are NULL).  bound_min / bound_max: the float[3] bounds the volume
  * grid was registered with (src/signed_heat_grid_solver.cpp:20-24,35); NULL = (float)bbox_min and
- * (float)(bbox_min + cell*(n-1)).  The mesh stays in buffers owned by the context until the next call. */
+ * (float)(bbox_min + cell*(n-1)).  The mesh stays in buffers owned by the context until the next call.
+ * z-slab contexts (shm3d_ctx_create_dist): a collective call -- every rank passes ITS slab as SHM3D_FIELD_DEVICE_F32 (the
+ * phi_dev of shm3d_solve_device); the slabs are gathered over NVLink on rank 0, which extracts the mesh; the other ranks
+ * report 0 vertices / triangles.  shm3d_slice works the same way (rank 0's `out` is filled). */
 int shm3d_isosurface(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t field_kind, float isoval,
                      const float* bound_min, const float* bound_max, uint32_t iso_flags, shm3d_iso_stats* out);
 /* Copies the last mesh to the host: vertices_out float[n_vertices][3], triangles_out uint32[n_triangles][3]

@@ -146,6 +146,28 @@ void Dist::recv_plane(float* p, size_t n, int peer, cudaStream_t s) {
     NCCL_CHECK(api().Recv(p, n, ncclFloat32, peer, (ncclComm_t)comm_, s));
 }
 
+void Dist::gather_slabs(const float* local, float* full, size_t plane, int nz, int root, cudaStream_t s) {
+    NcclApi& a = api();
+    ncclComm_t comm = (ncclComm_t)comm_;
+    int k0, k1;
+    slab_range(rank_, world_, nz, k0, k1);
+    if (rank_ == root)
+        SHM3D_CUDA_CHECK(cudaMemcpyAsync(full + (size_t)k0 * plane, local, (size_t)(k1 - k0) * plane * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, s));
+    NCCL_CHECK(a.GroupStart());
+    if (rank_ == root) {
+        for (int r = 0; r < world_; r++) {
+            if (r == root) continue;
+            int r0, r1;
+            slab_range(r, world_, nz, r0, r1);
+            if (r1 > r0) NCCL_CHECK(a.Recv(full + (size_t)r0 * plane, (size_t)(r1 - r0) * plane, ncclFloat32, r, comm, s));
+        }
+    } else if (k1 > k0) {
+        NCCL_CHECK(a.Send(local, (size_t)(k1 - k0) * plane, ncclFloat32, root, comm, s));
+    }
+    NCCL_CHECK(a.GroupEnd());
+}
+
 unsigned int Dist::allreduce_max_host(unsigned int v) {
     SHM3D_CUDA_CHECK(cudaMemcpyAsync(d_tmp_, &v, sizeof(v), cudaMemcpyHostToDevice, stream_));
     NCCL_CHECK(api().AllReduce(d_tmp_, d_tmp_, 1, ncclUint32, ncclMax, (ncclComm_t)comm_, stream_));

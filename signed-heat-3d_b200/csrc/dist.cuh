@@ -35,6 +35,9 @@ class Dist {
     void allgather(float* full, size_t count_per_rank, cudaStream_t s);  // in place, rank r owns [r*count, (r+1)*count)
     void send_plane(const float* p, size_t n, int peer, cudaStream_t s);  // point-to-point (chained prefix sums)
     void recv_plane(float* p, size_t n, int peer, cudaStream_t s);
+    // the slabs of a float field (rank r owns planes [k0_r, k1_r) of nz) gathered on rank `root`: `full` (root only) gets
+    // nz*plane floats, every rank sends its `local` slab -- grouped ncclSend/ncclRecv over NVLink (row N3 on slab contexts)
+    void gather_slabs(const float* local, float* full, size_t plane, int nz, int root, cudaStream_t s);
     unsigned int allreduce_max_host(unsigned int v);
     void attach(Projector& P);  // hook the projector's gather to an all-reduce
 

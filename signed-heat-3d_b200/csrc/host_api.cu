@@ -30,27 +30,46 @@ int shm3d_prepare_mesh(const double* V, int64_t nV, const int64_t* face_vertices
         double d0 = c[0] - V[3 * v], d1 = c[1] - V[3 * v + 1], d2 = c[2] - V[3 * v + 2];
         r = std::max(r, std::sqrt(d0 * d0 + d1 * d1 + d2 * d2));
     }
-    // mean length of the unique (unordered) vertex-pair edges
-    std::vector<std::pair<int64_t, int64_t>> edges;
-    edges.reserve((size_t)face_offsets[nF]);
+    // mean length of the unique (unordered) vertex-pair edges, visited in (min vertex, max vertex) order: counting sort on
+    // the smaller vertex, then each vertex's handful of partners sorted and deduplicated (a global sort of the 3e5 pairs of a
+    // 1e5-triangle mesh was 30 of the 40 ms this function took)
+    std::vector<int64_t> start((size_t)nV + 1, 0);
     for (int64_t f = 0; f < nF; f++) {
         int64_t b = face_offsets[f], e = face_offsets[f + 1], d = e - b;
         if (d < 3) return SHM3D_ERR_INVALID_ARG;
         for (int64_t t = 0; t < d; t++) {
             int64_t va = face_vertices[b + t], vb = face_vertices[b + (t + 1) % d];
             if (va < 0 || vb < 0 || va >= nV || vb >= nV) return SHM3D_ERR_INVALID_ARG;
-            edges.emplace_back(std::min(va, vb), std::max(va, vb));
+            start[(size_t)std::min(va, vb) + 1]++;
         }
     }
-    std::sort(edges.begin(), edges.end());
-    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
-    double hsum = 0;
-    for (auto& e : edges) {
-        const double* a = V + 3 * e.first;
-        const double* b = V + 3 * e.second;
-        hsum += std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+    for (int64_t v = 0; v < nV; v++) start[(size_t)v + 1] += start[(size_t)v];
+    std::vector<int64_t> partner((size_t)start[(size_t)nV]);
+    {
+        std::vector<int64_t> fill(start.begin(), start.end() - 1);
+        for (int64_t f = 0; f < nF; f++) {
+            int64_t b = face_offsets[f], d = face_offsets[f + 1] - b;
+            for (int64_t t = 0; t < d; t++) {
+                int64_t va = face_vertices[b + t], vb = face_vertices[b + (t + 1) % d];
+                partner[(size_t)fill[(size_t)std::min(va, vb)]++] = std::max(va, vb);
+            }
+        }
     }
-    const double h = hsum / (double)edges.size();
+    double hsum = 0;
+    int64_t n_edges = 0;
+    for (int64_t v = 0; v < nV; v++) {
+        int64_t* pb = partner.data() + start[(size_t)v];
+        int64_t* pe = partner.data() + start[(size_t)v + 1];
+        std::sort(pb, pe);
+        pe = std::unique(pb, pe);
+        const double* a = V + 3 * v;
+        for (int64_t* q = pb; q < pe; q++) {
+            const double* b = V + 3 * *q;
+            hsum += std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+            n_edges++;
+        }
+    }
+    const double h = hsum / (double)n_edges;
     if (h_out) *h_out = h;
 
     const double s = r * scale;

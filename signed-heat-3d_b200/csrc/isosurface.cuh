@@ -21,6 +21,11 @@ public:
     // Device-resident float field of a full (unpartitioned) grid, index i + j*nx + k*nx*ny.  Host fields are staged
     // (and doubles narrowed to float32 the way the consumer stores them) into a buffer owned by this object.
     const float* stage_field(cudaStream_t s, size_t n, const void* field, int kind);
+    // the staging buffer itself, sized for n floats (slab contexts gather the ranks' slabs into it)
+    float* field_buffer(size_t n) {
+        field32_.alloc(n);
+        return field32_.p;
+    }
 
     // bound_min / bound_max: the float bounds the volume grid was registered with; both NULL = lattice coordinates.
     IsoResult extract(cudaStream_t s, int nx, int ny, int nz, const float* d_field, float isoval, const float* bound_min,
@@ -29,6 +34,7 @@ public:
     const float* d_vertices() const { return verts_.p; }
     const uint32_t* d_triangles() const { return tris_.p; }
     void fetch(cudaStream_t s, float* vertices_out, uint32_t* triangles_out) const;
+    void clear_result() { last_ = IsoResult(); }  // (slab contexts: ranks other than the gathering one hold no mesh)
 
     // out[a + b*nu] = trilinear interpolant (src/signed_heat_grid_solver.cpp:405-431) at origin + a*du + b*dv; NaN outside
     int64_t slice(cudaStream_t s, int nx, int ny, int nz, const float* d_field, const double bbox_min[3], double cell,

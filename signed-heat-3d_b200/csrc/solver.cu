@@ -1183,6 +1183,12 @@ void shm3d_ctx_destroy(shm3d_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    // the captured PCG iteration holds NCCL operations of this context's communicator: the executable graphs go first
+    for (cudaGraphExec_t& g : ctx->pcg_graph)
+        if (g) {
+            cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
     ctx->levels.clear();
     ctx->dist.reset();
     if (ctx->h_rho) cudaFreeHost(ctx->h_rho);
@@ -1454,13 +1460,22 @@ int shm3d_debug_stencil_op(shm3d_ctx* ctx, int32_t op, int32_t nx, int32_t ny, i
 }
 
 // ---- row N3: consumer of phi on the device (isosurface.cu) -------------------------------------------------------
+// The field the consumer kernels read.  Single-GPU contexts: the caller's full field (staged / narrowed if it is on the
+// host).  Slab contexts: every rank passes ITS slab as device float32 (what shm3d_solve_device left in phi_dev); the slabs
+// are gathered over NVLink into rank 0's staging buffer (4.3 GB at 1024^3: ~10 ms, against 8.6 GB of doubles over PCIe to
+// the host in the reference flow) and rank 0 does the consumer's work; the other ranks get nullptr = nothing to do.
 static const float* n3_field(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t kind, const char* who) {
     if (!p || !phi) throw Error(SHM3D_ERR_INVALID_ARG, std::string(who) + ": null argument");
-    if (ctx->world != 1)
-        throw Error(SHM3D_ERR_INVALID_ARG, std::string(who) + ": single-GPU contexts only (a z-slab rank holds part of the field)");
     if (p->nx < 2 || p->ny < 2 || p->nz < 2) throw Error(SHM3D_ERR_INVALID_ARG, std::string(who) + ": grid too small");
     if (!ctx->iso) ctx->iso.reset(new IsoSurface());
-    return ctx->iso->stage_field(ctx->stream, (size_t)p->nx * p->ny * p->nz, phi, kind);
+    if (ctx->world == 1) return ctx->iso->stage_field(ctx->stream, (size_t)p->nx * p->ny * p->nz, phi, kind);
+    if (kind != SHM3D_FIELD_DEVICE_F32)
+        throw Error(SHM3D_ERR_INVALID_ARG, std::string(who) + ": on a z-slab context the field is this rank's slab as device "
+                                                                  "float32 (SHM3D_FIELD_DEVICE_F32, phi_dev of shm3d_solve_device)");
+    const size_t plane = (size_t)p->nx * p->ny;
+    float* full = ctx->rank == 0 ? ctx->iso->field_buffer(plane * (size_t)p->nz) : nullptr;
+    ctx->dist->gather_slabs(static_cast<const float*>(phi), full, plane, p->nz, 0, ctx->stream);
+    return full;
 }
 
 int shm3d_isosurface(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t field_kind, float isoval,
@@ -1475,6 +1490,12 @@ int shm3d_isosurface(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int
         bmax[a] = bound_max ? bound_max[a] : (float)(p->bbox_min[a] + p->cell * (double)(n[a] - 1));
     }
     const bool lattice = (iso_flags & SHM3D_ISO_LATTICE) != 0;
+    if (!d_field) {  // slab context, rank > 0: the mesh is rank 0's
+        ctx->iso->clear_result();
+        SHM3D_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // (the slab has left)
+        if (out) memset(out, 0, sizeof(*out));
+        return SHM3D_OK;
+    }
     IsoResult r = ctx->iso->extract(ctx->stream, p->nx, p->ny, p->nz, d_field, isoval, lattice ? nullptr : bmin,
                                     lattice ? nullptr : bmax);
     if (out) {
@@ -1506,6 +1527,7 @@ int shm3d_slice(shm3d_ctx* ctx, const shm3d_params* p, const void* phi, int32_t 
     SHM3D_API_BEGIN(ctx)
     if (!origin || !du || !dv || !out) throw Error(SHM3D_ERR_INVALID_ARG, "shm3d_slice: null argument");
     const float* d_field = n3_field(ctx, p, phi, field_kind, "shm3d_slice");
+    if (!d_field) return SHM3D_OK;  // slab context, rank > 0: rank 0 samples the gathered field (`out` is left untouched)
     ctx->iso->slice(ctx->stream, p->nx, p->ny, p->nz, d_field, p->bbox_min, p->cell, origin, du, dv, nu, nv, out);
     SHM3D_API_END(ctx)
 }

@@ -47,5 +47,36 @@ for c in (sys.argv[1:] or ["sphere:3", "bunny_small:1", "bunny_small:0"]):
               f"(sum {st1.ms_sum:.0f} pcg {st1.ms_pcg:.0f})", flush=True)
     if float(e[0]) > 1e-4:
         bad = 1
+# row N3 on slab contexts: every rank hands its device-resident float32 slab to shm3d_isosurface; the slabs are gathered on
+# rank 0 over NVLink and contoured there -- the mesh must be the one a single GPU extracts from the whole field
+V, F = fibonacci_sphere(100000)
+p, pos, nrm, area, h = shm3d.prepare_mesh(V, F, hCoef=3)
+dev = torch.device("cuda", local)
+d_in = [torch.from_numpy(a).to(dev) for a in (pos, nrm, area)]
+k0, k1 = dctx.slab(p.nz)
+d_slab = torch.empty((k1 - k0) * p.ny * p.nx, dtype=torch.float32, device=dev)
+dctx.solve_device(p, d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(), d_slab.data_ptr(), len(area))
+Vd, Td, std_ = dctx.isosurface(p, d_slab.data_ptr())
+sl = dctx.slice(p, d_slab.data_ptr(), [p.bbox_min[0], p.bbox_min[1], p.bbox_min[2] + 0.37 * p.cell * (p.nz - 1)],
+                [p.cell * 1.7, 0, 0], [0, p.cell * 1.3, 0], 40, 30)
+parts = [torch.empty_like(d_slab) for _ in range(world)] if (p.nz % world == 0) else None
+if parts is not None:
+    dist.all_gather(parts, d_slab)
+    if rank == 0:
+        full = torch.cat(parts)
+        Vs, Ts, sts = sctx.isosurface(p, full.data_ptr())
+        sl1 = sctx.slice(p, full.data_ptr(), [p.bbox_min[0], p.bbox_min[1], p.bbox_min[2] + 0.37 * p.cell * (p.nz - 1)],
+                         [p.cell * 1.7, 0, 0], [0, p.cell * 1.3, 0], 40, 30)
+        same = np.array_equal(Vd.view(np.uint32), Vs.view(np.uint32)) and np.array_equal(Td, Ts)
+        same_slice = np.array_equal(sl.view(np.uint32), sl1.view(np.uint32))
+        print(f"isosurface on {world} slabs (gathered on rank 0): {len(Vd)} vertices, {len(Td)} triangles, identical to the "
+              f"single-GPU mesh: {same}; slice identical: {same_slice}", flush=True)
+        if not (same and same_slice and len(Vd) > 0):
+            bad = 1
+    else:
+        assert len(Vd) == 0 and len(Td) == 0
+dist.barrier()
+dctx.close()
+sctx.close()
 dist.destroy_process_group()
 sys.exit(bad)
