@@ -10,7 +10,7 @@
 //   k_mc_count      one thread per lattice column (fixed j,i; marching along k), lanes along i: two coalesced rows per
 //                   warp and plane, the z+1 corners as sign bits by shuffle, eight planes of loads in flight; per column:
 //                   vertices created, triangles emitted, first / last non-trivial cell                 [reads phi once]
-//   k_mc_scan       exclusive scan of the (nx-1)(ny-1) column counts (one CTA)
+//   k_mc_scan_sums / k_mc_scan_write   exclusive scan of the (nx-1)(ny-1) column counts (per-CTA partial sums, then offsets)
 //   k_mc_vertices   columns that create vertices march again (first..last non-trivial cell only) and write positions +
 //                   per-column search keys
 //   k_mc_triangles  columns that emit triangles march again and resolve each corner to a vertex id by locating the
@@ -34,7 +34,8 @@ __device__ const unsigned long long d_mc_table[256] = {
 
 using mc::kLanesZ;
 using mc::kRowsY;
-using mc::kScanThreads;
+using mc::kScanBlock;
+using mc::kScanBlocks;
 
 __device__ __forceinline__ void load_table(unsigned long long* s_tab) {
     for (int i = threadIdx.y * kLanesZ + threadIdx.x; i < 256; i += kLanesZ * kRowsY) s_tab[i] = d_mc_table[i];
@@ -96,30 +97,78 @@ __global__ void __launch_bounds__(kLanesZ* kRowsY)
     col_x[c] = mc::pack_range(cc.x_lo, cc.x_hi);
 }
 
-// one CTA: thread t owns a contiguous chunk of the n column counts (mc::scan_chunk)
-__global__ void __launch_bounds__(kScanThreads)
-    k_mc_scan(const unsigned int* __restrict__ col_v, const unsigned int* __restrict__ col_t, int n,
-              unsigned long long* __restrict__ voff, unsigned long long* __restrict__ toff) {
-    __shared__ unsigned long long sv[kScanThreads], st[kScanThreads];
-    const int t = threadIdx.x;
+// Exclusive scan of the column counts in two launches.  Scan thread t (of kScanBlocks * kScanBlock) owns a short contiguous
+// chunk (mc::scan_chunk: 8 columns at 512^2); k_mc_scan_sums leaves one partial sum per CTA, k_mc_scan_write adds the
+// partial sums of the CTAs before it, scans its threads' sums, and writes the chunk.  (Round 1 scanned with ONE CTA whose
+// threads walked 1 KB chunks element by element: 0.98 ms of the 1.85 ms the whole isosurface took.)
+__device__ __forceinline__ void block_sum2(unsigned long long& a, unsigned long long& c, unsigned long long* sa,
+                                           unsigned long long* sc) {  // sums over the CTA, returned to every thread
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+        sa[w] = a;
+        sc[w] = c;
+    }
+    __syncthreads();
+    a = c = 0;
+    for (int i = 0; i < kScanBlock / 32; i++) {
+        a += sa[i];
+        c += sc[i];
+    }
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+    k_mc_scan_sums(const unsigned int* __restrict__ col_v, const unsigned int* __restrict__ col_t, int n,
+                   unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long sa[kScanBlock / 32], sc[kScanBlock / 32];
     int b, e;
-    mc::scan_chunk(n, t, b, e);
+    mc::scan_chunk(n, blockIdx.x * kScanBlock + threadIdx.x, b, e);
+    unsigned long long a, c;
+    mc::scan_chunk_sum(col_v, col_t, b, e, a, c);
+    block_sum2(a, c, sa, sc);
+    if (threadIdx.x == 0) {
+        block_sums[2 * blockIdx.x] = a;
+        block_sums[2 * blockIdx.x + 1] = c;
+    }
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+    k_mc_scan_write(const unsigned int* __restrict__ col_v, const unsigned int* __restrict__ col_t, int n,
+                    const unsigned long long* __restrict__ block_sums, unsigned long long* __restrict__ voff,
+                    unsigned long long* __restrict__ toff) {
+    __shared__ unsigned long long sa[kScanBlock / 32], sc[kScanBlock / 32];
+    __shared__ unsigned long long sv[kScanBlock], st[kScanBlock];
+    const int t = threadIdx.x;
+    // everything the CTAs before this one hold
+    unsigned long long pa = 0, pc = 0;
+    for (int i = t; i < (int)blockIdx.x; i += kScanBlock) {
+        pa += block_sums[2 * i];
+        pc += block_sums[2 * i + 1];
+    }
+    block_sum2(pa, pc, sa, sc);
+    int b, e;
+    mc::scan_chunk(n, blockIdx.x * kScanBlock + t, b, e);
     unsigned long long a, c;
     mc::scan_chunk_sum(col_v, col_t, b, e, a, c);
     sv[t] = a;
     st[t] = c;
     __syncthreads();
-    for (int off = 1; off < kScanThreads; off <<= 1) {  // inclusive scan of the chunk sums
+    for (int off = 1; off < kScanBlock; off <<= 1) {  // inclusive scan of the threads' chunk sums
         unsigned long long x = t >= off ? sv[t - off] : 0ull, y = t >= off ? st[t - off] : 0ull;
         __syncthreads();
         sv[t] += x;
         st[t] += y;
         __syncthreads();
     }
-    mc::scan_chunk_write(col_v, col_t, b, e, sv[t] - a, st[t] - c, voff, toff);
-    if (t == kScanThreads - 1) {
-        voff[n] = sv[t];
-        toff[n] = st[t];
+    mc::scan_chunk_write(col_v, col_t, b, e, pa + sv[t] - a, pc + st[t] - c, voff, toff);
+    if (blockIdx.x == gridDim.x - 1 && t == kScanBlock - 1) {
+        voff[n] = pa + sv[t];
+        toff[n] = pc + st[t];
     }
 }
 
@@ -247,7 +296,10 @@ IsoResult IsoSurface::extract(cudaStream_t s, int nx, int ny, int nz, const floa
     SHM3D_CUDA_CHECK(cudaEventRecord(ev0_, s));
     k_mc_count<<<grid, block, 0, s>>>(L, d_field, col_v_.p, col_t_.p, col_x_.p);
     SHM3D_LAUNCHED();
-    k_mc_scan<<<1, kScanThreads, 0, s>>>(col_v_.p, col_t_.p, nc, voff_.p, toff_.p);
+    block_sums_.alloc(2 * (size_t)kScanBlocks);
+    k_mc_scan_sums<<<kScanBlocks, kScanBlock, 0, s>>>(col_v_.p, col_t_.p, nc, block_sums_.p);
+    SHM3D_LAUNCHED();
+    k_mc_scan_write<<<kScanBlocks, kScanBlock, 0, s>>>(col_v_.p, col_t_.p, nc, block_sums_.p, voff_.p, toff_.p);
     SHM3D_LAUNCHED();
     SHM3D_CUDA_CHECK(cudaGetLastError());
     SHM3D_CUDA_CHECK(cudaMemcpyAsync(&h_totals_[0], voff_.p + nc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

@@ -44,7 +44,7 @@ private:
     DevBuf<float> field32_;
     DevBuf<double> stage64_;
     DevBuf<unsigned int> col_v_, col_t_, col_x_;
-    DevBuf<unsigned long long> voff_, toff_;
+    DevBuf<unsigned long long> voff_, toff_, block_sums_;
     DevBuf<float> verts_;
     DevBuf<uint32_t> vkey_, tris_;
     DevBuf<float> slice_;

@@ -228,7 +228,9 @@ MC_HD void unpack_range(unsigned r, int& x_lo, int& x_hi) {
 // ---- launch geometry and the chunked scan, shared with the host emulation ------------------------------------------
 constexpr int kLanesZ = 32;        // lattice Z (grid i, contiguous in memory) across the lanes of a warp
 constexpr int kRowsY = 8;          // warps per CTA: consecutive lattice Y (grid j)
-constexpr int kScanThreads = 1024; // the one CTA of the scan kernel
+constexpr int kScanBlock = 256;    // threads per CTA of the two scan kernels
+constexpr int kScanBlocks = 128;   // CTAs: 32768 scan threads, each owning a short contiguous chunk of the column counts
+constexpr int kScanThreads = kScanBlock * kScanBlocks;
 
 MC_HD void launch_grid(const Lattice& L, unsigned& gx, unsigned& gy) {
     gx = (unsigned)((L.SZ - 1 + kLanesZ - 1) / kLanesZ);

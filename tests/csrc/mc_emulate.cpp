@@ -65,31 +65,33 @@ extern "C" int mc_emulate(const float* field, int nx, int ny, int nz, float isov
         col_x[column_id(L, y, z)] = pack_range(cc.x_lo, cc.x_hi);
     });
     if (count_mismatch) return 6;
-    // k_mc_scan: phase 1 (chunk sums), the CTA-wide inclusive scan, phase 2 (chunk writes)
+    // k_mc_scan_sums: one partial sum per CTA; k_mc_scan_write: offsets of the CTAs before + scan of the CTA's thread sums
     std::vector<unsigned long long> voff(nc + 1, ~0ull), toff(nc + 1, ~0ull), sv(kScanThreads), st(kScanThreads), a(kScanThreads),
-        c(kScanThreads);
+        c(kScanThreads), bsum(2 * kScanBlocks, 0ull);
     for (int t = 0; t < kScanThreads; t++) {
         int b, e;
         scan_chunk(nc, t, b, e);
         scan_chunk_sum(col_v.data(), col_t.data(), b, e, a[t], c[t]);
-        sv[t] = a[t];
-        st[t] = c[t];
+        bsum[2 * (t / kScanBlock)] += a[t];
+        bsum[2 * (t / kScanBlock) + 1] += c[t];
     }
-    for (int off = 1; off < kScanThreads; off <<= 1) {
-        std::vector<unsigned long long> x(kScanThreads), y(kScanThreads);
-        for (int t = 0; t < kScanThreads; t++) {
-            x[t] = t >= off ? sv[t - off] : 0ull;
-            y[t] = t >= off ? st[t - off] : 0ull;
+    for (int blk = kScanBlocks - 1; blk >= 0; blk--) {  // (CTAs in any order)
+        unsigned long long pa = 0, pc = 0;
+        for (int i = 0; i < blk; i++) {
+            pa += bsum[2 * i];
+            pc += bsum[2 * i + 1];
         }
-        for (int t = 0; t < kScanThreads; t++) {
-            sv[t] += x[t];
-            st[t] += y[t];
+        unsigned long long ra = 0, rc = 0;
+        for (int tt = 0; tt < kScanBlock; tt++) {
+            const int t = blk * kScanBlock + tt;
+            ra += a[t];
+            rc += c[t];
+            sv[t] = pa + ra;   // = offset of the CTA + inclusive scan of its threads' sums
+            st[t] = pc + rc;
+            int b, e;
+            scan_chunk(nc, t, b, e);
+            scan_chunk_write(col_v.data(), col_t.data(), b, e, sv[t] - a[t], st[t] - c[t], voff.data(), toff.data());
         }
-    }
-    for (int t = kScanThreads - 1; t >= 0; t--) {
-        int b, e;
-        scan_chunk(nc, t, b, e);
-        scan_chunk_write(col_v.data(), col_t.data(), b, e, sv[t] - a[t], st[t] - c[t], voff.data(), toff.data());
     }
     voff[nc] = sv[kScanThreads - 1];
     toff[nc] = st[kScanThreads - 1];
