@@ -2,7 +2,11 @@
 # Build libshm3d_grid.so (sm_100a only).  Usage: csrc/build.sh [extra nvcc flags]
 set -e
 cd "$(dirname "$0")"
-NCCL_INC=${NCCL_INC:-/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/include}
+# nccl.h: $NCCL_INC, else the nvidia-nccl wheel of the python on PATH, else the system include path
+if [ -z "$NCCL_INC" ]; then
+    NCCL_INC=$(python -c "import importlib.util, os; s = importlib.util.find_spec('nvidia.nccl'); print(os.path.join(list(s.submodule_search_locations)[0], 'include') if s else '')" 2>/dev/null || true)
+fi
+NCCL_INC=${NCCL_INC:-/usr/include}
 OUT=../lib/libshm3d_grid.so
 mkdir -p ../lib
 # point_weights.cpp (row N1, host only) is compiled without floating-point contraction: its degenerate-case decisions

@@ -1,4 +1,5 @@
 // dist.cu -- NCCL plumbing for the slab-partitioned solve (see dist.cuh).
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -29,14 +30,18 @@ NcclApi& api() {
     static NcclApi a;
     static std::once_flag once;
     std::call_once(once, [&] {
-        const char* names[] = {"libnccl.so.2", "libnccl.so",
-                               "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2"};
-        for (const char* n : names) {
-            a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-            if (a.h) break;
+        // SHM3D_NCCL_LIB (a path) wins; else the libnccl already mapped into the process (torch's, when the caller is a
+        // torch.distributed program) or whatever the loader's search path offers -- no environment-specific paths here
+        const char* env = getenv("SHM3D_NCCL_LIB");
+        if (env && *env) a.h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        for (const char* n : {"libnccl.so.2", "libnccl.so"}) {
+            if (!a.h) a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+        }
+        for (const char* n : {"libnccl.so.2", "libnccl.so"}) {
+            if (!a.h) a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         }
         if (!a.h) {
-            a.err = std::string("cannot load libnccl.so.2: ") + dlerror();
+            a.err = std::string("cannot load libnccl.so.2 (set SHM3D_NCCL_LIB to its path): ") + dlerror();
             return;
         }
 #define BIND(field, sym)                                        \

@@ -274,6 +274,7 @@ class Context:
         self._h = C.c_void_p()
         L = lib()
         if world > 1:
+            _point_at_nccl()
             buf = C.create_string_buffer(nccl_id, 128)
             rc = L.shm3d_ctx_create_dist(C.byref(self._h), device, rank, world, C.cast(buf, C.c_void_p))
         else:
@@ -432,7 +433,26 @@ def slab_range(rank, world, nz):
     return k0.value, k1.value
 
 
+def _point_at_nccl():
+    """The library binds NCCL at run time: SHM3D_NCCL_LIB, else a libnccl already mapped into the process (torch's), else
+    the loader's search path.  When none of that is set up, offer the copy that ships in the `nvidia-nccl` wheel next to
+    torch -- found through the import system, not through a hard-coded path."""
+    if os.environ.get("SHM3D_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["SHM3D_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def nccl_unique_id() -> bytes:
+    _point_at_nccl()
     buf = C.create_string_buffer(128)
     rc = lib().shm3d_nccl_unique_id(C.cast(buf, C.c_void_p))
     if rc != OK:
