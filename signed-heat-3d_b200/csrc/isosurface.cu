@@ -85,7 +85,10 @@ __global__ void __launch_bounds__(kLanesZ* kRowsY)
         for (int u = 0; u < kCountAhead; u++) {
             if (x0 + u < ncell) {  // (warp-uniform)
                 const unsigned n_cur = nibble(v0[u], v1[u], w0[u], w1[u]);
-                mc::count_cell(cc, s_tab, mc::case_of_nibbles(n_prev, n_cur), x0 + u, y, zc);
+                // ~98 % of the cells are entirely on one side of the level (cases 0 / 255): decided on the nibbles, before
+                // the case number is assembled
+                if (!((n_prev | n_cur) == 0u || (n_prev & n_cur) == 15u))
+                    mc::count_cell(cc, s_tab, mc::case_of_nibbles(n_prev, n_cur), x0 + u, y, zc);
                 n_prev = n_cur;
             }
         }
