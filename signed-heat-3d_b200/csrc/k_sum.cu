@@ -71,6 +71,30 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// (Measured and dropped, profiles/experiments/r02_ksum_poly_ex2_mix.jsonl: evaluating a fraction of the exponentials on the
+// FMA pipe -- round-to-nearest split by the 1.5*2^23 trick, degree-5 polynomial in FFMA2 with immediate coefficients, 2^n by
+// an integer add into the exponent -- to relieve the XU pipe.  0 / 2 / 3 / 4 / 5 of every 8 sources: 509 / 520 / 539 / 565 /
+// 599 ms.  The extra 12 issue slots per offloaded pair cost more than the 16 XU cycles they free.)
+
+// one source against the lane's two nodes (packed: low half z0, high half z1)
+__device__ __forceinline__ void pair_step(const float4& p, const float4& n, float px, float py, f32x2 pz, f32x2 nl, f32x2 cm,
+                                          f32x2& Xx, f32x2& Xy, f32x2& Xz) {
+    const float dx = px - p.x, dy = py - p.y;
+    const float dxy2 = fmaf(dy, dy, dx * dx);
+    const f32x2 dz = sub2(pz, pack2(p.z, p.z));
+    const f32x2 r2 = fma2(dz, dz, pack2(dxy2, dxy2));
+    float r20, r21;
+    unpack2(r2, r20, r21);
+    const f32x2 ri = pack2(fast_rsqrt(r20), fast_rsqrt(r21));
+    const f32x2 arg = fma2(nl, mul2(r2, ri), cm);
+    float a0, a1;
+    unpack2(arg, a0, a1);
+    const f32x2 wgt = mul2(pack2(fast_ex2(a0), fast_ex2(a1)), ri);
+    Xx = fma2(wgt, pack2(n.x, n.x), Xx);
+    Xy = fma2(wgt, pack2(n.y, n.y), Xy);
+    Xz = fma2(wgt, pack2(n.z, n.z), Xz);
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -275,25 +299,14 @@ k_sum(SumParams P, const float4* __restrict__ cl_bounds, const int2* __restrict_
                 {
                     const f32x2 pz = pack2(pz0, pz1), cm = pack2(cm0, cm1), nl = pack2(nlam2, nlam2);
                     f32x2 Xx = pack2(X00, X10), Xy = pack2(X01, X11), Xz = pack2(X02, X12);
-#pragma unroll 4
-                    for (int s = 0; s < rg.y; s++) {
-                        const float4 p = s_src[w][0][s];
-                        const float4 n = s_src[w][1][s];
-                        const float dx = px - p.x, dy = py - p.y;
-                        const float dxy2 = fmaf(dy, dy, dx * dx);
-                        const f32x2 dz = sub2(pz, pack2(p.z, p.z));
-                        const f32x2 r2 = fma2(dz, dz, pack2(dxy2, dxy2));
-                        float r20, r21;
-                        unpack2(r2, r20, r21);
-                        const f32x2 ri = pack2(fast_rsqrt(r20), fast_rsqrt(r21));
-                        const f32x2 arg = fma2(nl, mul2(r2, ri), cm);
-                        float a0, a1;
-                        unpack2(arg, a0, a1);
-                        const f32x2 wgt = mul2(pack2(fast_ex2(a0), fast_ex2(a1)), ri);
-                        Xx = fma2(wgt, pack2(n.x, n.x), Xx);
-                        Xy = fma2(wgt, pack2(n.y, n.y), Xy);
-                        Xz = fma2(wgt, pack2(n.z, n.z), Xz);
+                    int s = 0;
+                    for (; s + 8 <= rg.y; s += 8) {  // (blocks of 8 + remainder: 509 ms against 517 with `#pragma unroll 4`)
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            pair_step(s_src[w][0][s + u], s_src[w][1][s + u], px, py, pz, nl, cm, Xx, Xy, Xz);
                     }
+#pragma unroll 4
+                    for (; s < rg.y; s++) pair_step(s_src[w][0][s], s_src[w][1][s], px, py, pz, nl, cm, Xx, Xy, Xz);
                     unpack2(Xx, X00, X10);
                     unpack2(Xy, X01, X11);
                     unpack2(Xz, X02, X12);

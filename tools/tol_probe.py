@@ -1,0 +1,30 @@
+"""PCG stopping tolerance vs distance to the fp64 oracle at the headline size (512^3 sphere, tests/golden/sphere_h5.npz), over
+inputs that differ only in the last bits of Y (cull_tau nudged): how much of phi's error is where the iteration stops.
+    python tools/tol_probe.py"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "signed-heat-3d_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import numpy as np  # noqa: E402
+import shm3d  # noqa: E402
+import bench  # noqa: E402
+
+p, pos, nrm, area, _ = bench.prepare("sphere512")
+gl = np.load(os.path.join(ROOT, "tests", "golden", "sphere_h5.npz"))
+sub, ref = gl["sub_index"], gl["sub_phi"]
+ctx = shm3d.Context(0)
+for tol in (3e-6, 2e-6, 1.5e-6, 1e-6, 5e-7):
+    errs, its = [], []
+    for tau in (10.0, 10.01, 10.02, 10.03, 10.05, 9.98):
+        q = shm3d.Params.from_buffer_copy(p)
+        q.cull_tau = tau
+        q.cg_rel_tol = tol
+        phi, st = ctx.solve(q, pos, nrm, area)
+        errs.append(float(np.linalg.norm(phi[sub] - ref) / np.linalg.norm(ref)))
+        its.append(int(st.cg_iters))
+    print(json.dumps({"cg_rel_tol": tol, "phi_rel_l2": [round(e, 8) for e in errs], "worst": max(errs), "iters": its}), flush=True)
+ctx.close()
