@@ -904,6 +904,28 @@ void Projector::apply_shifted(float* v, const double* shift_num, double shift_de
     scatter_sub(v, s);
 }
 
+namespace {
+__global__ void k_sum_doubles(const double* __restrict__ v, int m, double* out) {  // one CTA, fixed order
+    __shared__ double sh[256];
+    double a = 0;
+    for (int i = threadIdx.x; i < m; i += 256) a += v[i];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+}  // namespace
+
+void Projector::violation_sum(const float* v, double* out_sum, cudaStream_t s) const {
+    if (!m_) return;
+    gather(v, nullptr, nullptr, 1.0, s);  // (with the all-reduce of the slab-parallel runs)
+    k_sum_doubles<<<1, 256, 0, s>>>(d_rhs_, m_, out_sum);
+    SHM3D_LAUNCHED();
+}
+
 void Projector::multipliers(const float* v, std::vector<double>& lam_host, cudaStream_t s) const {
     lam_host.assign(m_, 0.0);
     if (!m_) return;

@@ -87,6 +87,9 @@ class Projector {
     void apply_update(float* v, const float* w, cudaStream_t s) const;
     // v <- v - D^-1 A^T (A D^-1 A^T)^-1 A (v - shift), shift = *shift_num / shift_den (rows of A sum to one)
     void apply_shifted(float* v, const double* shift_num, double shift_den, cudaStream_t s) const;
+    // *out_sum (device) = sum of the m entries of A v: the rows of A sum to one, so sum / m is the constant by which v
+    // violates the constraints on average (Solver::run_pcg removes it from the whole field before the last projection)
+    void violation_sum(const float* v, double* out_sum, cudaStream_t s) const;
     // lam <- (A D^-1 A^T)^-1 (A v): multipliers only (diagnostics / tests); lam_host has m entries in row order
     void multipliers(const float* v, std::vector<double>& lam_host, cudaStream_t s) const;
     // weighted source average helper is elsewhere (solver.cu)

@@ -876,12 +876,11 @@ struct Solver {
         float* pbuf[2] = {c->vp.ip(), c->vp2.ip()};
         // relative preconditioned residual; the unpreconditioned fallback (odd grids) needs a tighter bar for the same
         // error in phi because its residual norm under-weights the smooth error components
-        // default 1e-6.  On knot.obj @128^3 the distance to the fp64 oracle is ~3e-6 for every tolerance <= 1e-5 (the
-        // floor set by the fp32 Steps 1-2), 4.3e-6 at 3e-5 and 3e-5 at 1e-4 -- against a parity bar of 1e-4.  At 512^3 the
-        // error AT the stopping point matters more: with 3e-6, inputs that differ by 1e-7 in Y stopped between 2e-6 and
-        // 4.5e-5 from the fp64 oracle (profiles/experiments/r02_ksum_poly_ex2_mix.jsonl), i.e. within 2x of the bar at
-        // worst; 1e-6 costs ~7 of ~85 iterations and puts the worst case at ~1.5e-5
-        const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : (use_mg ? 1e-6 : 3e-7);
+        // default 3e-6: on knot.obj @128^3 the distance to the fp64 oracle is ~3e-6 for every tolerance <= 1e-5 (the
+        // floor set by the fp32 Steps 1-2), 4.3e-6 at 3e-5 and 3e-5 at 1e-4 -- against a parity bar of 1e-4.  At 512^3
+        // (tools/tol_probe.py against the fp64 fixture) the distance to the oracle is THE SAME for every tolerance from
+        // 3e-6 down to 5e-7: what is left there is the far-field culling of Steps 1-2, not the solve
+        const double tol = p->cg_rel_tol > 0 ? p->cg_rel_tol : (use_mg ? 3e-6 : 3e-7);
         const int maxit = p->cg_max_iters > 0 ? p->cg_max_iters : 2000;
         const bool verbose = (p->flags & SHM3D_FLAG_VERBOSE) != 0;
         const int kCheck = verbose ? 1 : 4;  // (the event profiler is asynchronous: it does not need per-iteration syncs)
@@ -1022,8 +1021,17 @@ struct Solver {
             }
             it = next;
         }
-        // x = sum alpha_k p_k left null(A) only by fp32 rounding (|A x| ~ 1e-4 after ~100 iterations at 512^3):
-        // one last projection restores the zero level set at the pinned sources to rounding
+        // x = sum alpha_k p_k leaves null(A) by fp32 rounding, and it does so along the CONSTANTS: K annihilates them, so
+        // nothing in the iteration sees or corrects a drift c * 1 (|A x| ~ 1e-4 after ~100 iterations at 512^3), while
+        // A (c * 1) = c because the rows of A sum to one.  Measured against the fp64 oracle at 512^3
+        // (profiles/experiments/r02_err_probe_constant_offset.jsonl): phi was off by a uniform 1e-5 .. 1e-4 (whatever tau or
+        // the tolerance were) and by 1e-6 .. 5e-6 once that constant was removed -- the last projection alone only pulls
+        // the pinned cells back (a local correction) and thereby also hides the offset from the source-average shift.
+        // So: first subtract the mean constraint violation from the whole field, then project.
+        if (P.m() > 0) {
+            P.violation_sum(x, sc + kTmp, s);
+            launch_axpy_const(x, n, sc + kTmp, (double)P.m(), -1.f, s);
+        }
         P.apply(x, s);
         t.stop();
         st.ms_pcg = t.ms();
