@@ -19,7 +19,7 @@ sub, ref = gl["sub_index"], gl["sub_phi"]
 ctx = shm3d.Context(0)
 mode = sys.argv[1] if len(sys.argv) > 1 else "tol"
 if mode == "tol":
-    for tol in (3e-6, 2e-6, 1.5e-6, 1e-6, 5e-7):
+    for tol in ([float(a) for a in sys.argv[2:]] or [3e-6, 2e-6, 1.5e-6, 1e-6, 5e-7]):
         errs, its = [], []
         for tau in (10.0, 10.01, 10.02, 10.03, 10.05, 9.98):
             q = shm3d.Params.from_buffer_copy(p)
