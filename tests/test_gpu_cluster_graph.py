@@ -28,7 +28,7 @@ def test_cluster_tail_and_graph_equal_launch_by_launch(gpu_ctx, hCoef):
     assert st0.tail_ops == 0 and st0.graph_replays == 0
     assert st.tail_ops > 0, "the V-cycle tail did not run as a cluster program"
     assert st.graph_replays >= st.cg_iters - 2 > 0, "the PCG iterations were not replayed from the captured graph"
-    assert abs(st.cg_iters - st0.cg_iters) <= 1
+    assert abs(st.cg_iters - st0.cg_iters) <= 4  # (convergence is checked every 4th iteration)
     err = np.linalg.norm(phi - ref) / np.linalg.norm(ref)
     print(f"hCoef {hCoef}: its {st.cg_iters}/{st0.cg_iters}, tail ops {st.tail_ops}, launches {st.kernel_launches} vs "
           f"{st0.kernel_launches}, rel-L2 {err:.2e}")

@@ -51,5 +51,5 @@ def test_solver_with_and_without_tma_agree(gpu_ctx):
     q, _, _, _, _ = shm3d.prepare_mesh(V, F, hCoef=3)
     q.flags |= shm3d.FLAG_NO_TMA
     phi2, st2 = gpu_ctx.solve(q, pos, nrm, area)
-    assert abs(st.cg_iters - st2.cg_iters) <= 1
+    assert abs(st.cg_iters - st2.cg_iters) <= 4  # (convergence is checked every 4th iteration)
     assert np.linalg.norm(phi - phi2) <= 2e-5 * np.linalg.norm(phi2)
