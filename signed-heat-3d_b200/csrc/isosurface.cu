@@ -42,58 +42,61 @@ __device__ __forceinline__ void load_table(unsigned long long* s_tab) {
     __syncthreads();
 }
 
-// Count pass.  A warp owns the 32 columns (y; z0..z0+31) and marches along lattice X (the slowest memory axis): per plane
-// every lane loads its own two nodes (y,z) and (y+1,z) -- two coalesced 128-byte rows per warp -- and gets the two nodes
-// at z+1 as sign bits from the next lane by one shuffle (the last lane of a row segment loads them itself).  The loads of
-// kCountAhead planes are issued before any of them is used, so each thread keeps 2*kCountAhead (+2) requests in flight:
-// the first version (one plane at a time, four loads per step) was latency-bound at 0.04 of the HBM roofline.
+// Count pass.  A warp marches along lattice X (the slowest memory axis) over the nodes (y, y+1; z0 .. z0+31) and owns the 31
+// columns (y; z0 .. z0+30): per plane every lane loads its own two nodes -- two coalesced 128-byte rows per warp -- and gets
+// the two nodes at z+1 as sign bits from the next lane by one shuffle (lane 31 only supplies them; consecutive warps
+// overlap by one node).  The loads of kCountAhead planes are issued before any of them is used, so each thread keeps
+// 2 * kCountAhead requests in flight: the first version (one plane at a time, four loads per step) was latency-bound at
+// 0.04 of the HBM roofline; with the loads pipelined the pass became instruction-bound (ncu: 44 instructions per
+// cell step, issue slots 72 %), hence the lean step below (pointer increments, no per-lane edge cases, trivial cells decided
+// on the nibbles).
 constexpr int kCountAhead = 8;
+constexpr int kCountCols = kLanesZ - 1;  // columns per warp
 
 __global__ void __launch_bounds__(kLanesZ* kRowsY)
     k_mc_count(const Lattice L, const float* __restrict__ field, unsigned int* __restrict__ col_v,
                unsigned int* __restrict__ col_t, unsigned int* __restrict__ col_x) {
     __shared__ unsigned long long s_tab[256];
     load_table(s_tab);
-    int y, z;
-    const bool active = mc::thread_column(L, blockIdx.x, blockIdx.y, threadIdx.x, threadIdx.y, y, z);
-    if (y >= L.SY - 1) return;  // (y is warp-uniform: the whole warp leaves)
     const int lane = threadIdx.x;
-    const int zc = min(z, L.SZ - 2);  // idle lanes (z beyond the last column) still take part in the shuffles
-    const bool own_next = lane == kLanesZ - 1 || z >= L.SZ - 2;  // nobody to shuffle the z+1 nodes from
+    const int y = (int)(blockIdx.y * kRowsY + threadIdx.y);
+    const int z = (int)(blockIdx.x * kCountCols) + lane;
+    if (y >= L.SY - 1) return;  // (warp-uniform)
+    const bool owns = lane < kCountCols && z < L.SZ - 1;
     const float niso = -L.isoval;
-    const float* p = field + (long long)y * L.SZ + zc;
-    auto nibble = [&](float v0, float v1, float w0, float w1) {
+    const float* q = field + (long long)y * L.SZ + min(z, L.SZ - 1);  // (lanes past the last node re-read it: never used)
+    auto nibble = [&](float v0, float v1) {
         const unsigned mine = mc::sign_bit(niso, v0) | (mc::sign_bit(niso, v1) << 1);
-        unsigned next = __shfl_down_sync(0xffffffffu, mine, 1);
-        if (own_next) next = mc::sign_bit(niso, w0) | (mc::sign_bit(niso, w1) << 1);
-        return mine | (next << 2);
+        return mine | (__shfl_down_sync(0xffffffffu, mine, 1) << 2);
     };
-    unsigned n_prev = nibble(p[0], p[L.SZ], own_next ? p[1] : 0.f, own_next ? p[L.SZ + 1] : 0.f);
+    unsigned n_prev = nibble(q[0], q[L.SZ]);
     mc::ColumnCount cc{0u, 0u, 0, 0};
     const int ncell = L.SX - 1;
-    for (int x0 = 0; x0 < ncell; x0 += kCountAhead) {
-        float v0[kCountAhead], v1[kCountAhead], w0[kCountAhead], w1[kCountAhead];
+    auto step = [&](int x, float v0, float v1) {
+        const unsigned n_cur = nibble(v0, v1);
+        // ~98 % of the cells are entirely on one side of the level (cases 0 / 255): decided on the nibbles, before the case
+        // number is assembled
+        if (!((n_prev | n_cur) == 0u || (n_prev & n_cur) == 15u))
+            mc::count_cell(cc, s_tab, mc::case_of_nibbles(n_prev, n_cur), x, y, z);
+        n_prev = n_cur;
+    };
+    int x0 = 0;
+    for (; x0 + kCountAhead <= ncell; x0 += kCountAhead) {
+        float v0[kCountAhead], v1[kCountAhead];
 #pragma unroll
         for (int u = 0; u < kCountAhead; u++) {
-            const float* q = p + (long long)min(x0 + u + 1, ncell) * L.strideX;
+            q += L.strideX;
             v0[u] = q[0];
             v1[u] = q[L.SZ];
-            w0[u] = own_next ? q[1] : 0.f;
-            w1[u] = own_next ? q[L.SZ + 1] : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < kCountAhead; u++) {
-            if (x0 + u < ncell) {  // (warp-uniform)
-                const unsigned n_cur = nibble(v0[u], v1[u], w0[u], w1[u]);
-                // ~98 % of the cells are entirely on one side of the level (cases 0 / 255): decided on the nibbles, before
-                // the case number is assembled
-                if (!((n_prev | n_cur) == 0u || (n_prev & n_cur) == 15u))
-                    mc::count_cell(cc, s_tab, mc::case_of_nibbles(n_prev, n_cur), x0 + u, y, zc);
-                n_prev = n_cur;
-            }
-        }
+        for (int u = 0; u < kCountAhead; u++) step(x0 + u, v0[u], v1[u]);
     }
-    if (!active) return;
+    for (; x0 < ncell; x0++) {
+        q += L.strideX;
+        step(x0, q[0], q[L.SZ]);
+    }
+    if (!owns) return;
     const int c = mc::column_id(L, y, z);
     col_v[c] = cc.nv;
     col_t[c] = cc.nt;
@@ -297,7 +300,8 @@ IsoResult IsoSurface::extract(cudaStream_t s, int nx, int ny, int nz, const floa
     if (L.SX > 65535) throw Error(SHM3D_ERR_INVALID_ARG, "isosurface: nz too large");  // (the packed per-column cell range)
     IsoResult res;
     SHM3D_CUDA_CHECK(cudaEventRecord(ev0_, s));
-    k_mc_count<<<grid, block, 0, s>>>(L, d_field, col_v_.p, col_t_.p, col_x_.p);
+    const dim3 grid_count((unsigned)((L.SZ - 1 + kCountCols - 1) / kCountCols), gy);  // 31 columns per warp
+    k_mc_count<<<grid_count, block, 0, s>>>(L, d_field, col_v_.p, col_t_.p, col_x_.p);
     SHM3D_LAUNCHED();
     block_sums_.alloc(2 * (size_t)kScanBlocks);
     k_mc_scan_sums<<<kScanBlocks, kScanBlock, 0, s>>>(col_v_.p, col_t_.p, nc, block_sums_.p);
