@@ -66,6 +66,8 @@ extern "C" {
 #define SHM3D_FLAG_NO_TMA 128u          /* diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones */
 #define SHM3D_FLAG_TAIL_PROGRAM 256u    /* experiment (off by default: measured 1 % slower than graph-replayed launches): the coarsest
                                           multigrid levels (<= 16^3) as ONE launch of a recorded op program (csrc/mg_tail.cuh) */
+#define SHM3D_FLAG_NO_CYCLIC_SUM 2048u  /* diagnostics (slab contexts): every rank sums its own slab instead of the round-robin
+                                          z-chunks that balance Steps 1-2 across the ranks */
 #define SHM3D_FLAG_NO_PDL 1024u         /* diagnostics: the projector's sweep kernels launched fully serialised instead of with
                                           programmatic dependent launch */
 #define SHM3D_FLAG_NO_GRAPH 512u        /* diagnostics: launch every PCG iteration kernel by kernel instead of replaying the

@@ -173,6 +173,15 @@ void Dist::gather_slabs(const float* local, float* full, size_t plane, int nz, i
     NCCL_CHECK(a.GroupEnd());
 }
 
+void Dist::p2p_round(const std::vector<P2P>& sends, const std::vector<P2P>& recvs, cudaStream_t s) {
+    NcclApi& a = api();
+    ncclComm_t comm = (ncclComm_t)comm_;
+    NCCL_CHECK(a.GroupStart());
+    for (const P2P& t : sends) NCCL_CHECK(a.Send(t.ptr, t.count, ncclFloat32, t.peer, comm, s));
+    for (const P2P& t : recvs) NCCL_CHECK(a.Recv(t.ptr, t.count, ncclFloat32, t.peer, comm, s));
+    NCCL_CHECK(a.GroupEnd());
+}
+
 unsigned int Dist::allreduce_max_host(unsigned int v) {
     SHM3D_CUDA_CHECK(cudaMemcpyAsync(d_tmp_, &v, sizeof(v), cudaMemcpyHostToDevice, stream_));
     NCCL_CHECK(api().AllReduce(d_tmp_, d_tmp_, 1, ncclUint32, ncclMax, (ncclComm_t)comm_, stream_));

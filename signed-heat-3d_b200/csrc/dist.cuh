@@ -38,6 +38,14 @@ class Dist {
     // the slabs of a float field (rank r owns planes [k0_r, k1_r) of nz) gathered on rank `root`: `full` (root only) gets
     // nz*plane floats, every rank sends its `local` slab -- grouped ncclSend/ncclRecv over NVLink (row N3 on slab contexts)
     void gather_slabs(const float* local, float* full, size_t plane, int nz, int root, cudaStream_t s);
+    // one grouped round of point-to-point transfers (Steps 1-2 computed on cyclically assigned z-chunks, then moved to
+    // the slab owners); sends and receives to / from one peer must be listed in the same order on both sides
+    struct P2P {
+        float* ptr;
+        size_t count;
+        int peer;
+    };
+    void p2p_round(const std::vector<P2P>& sends, const std::vector<P2P>& recvs, cudaStream_t s);
     unsigned int allreduce_max_host(unsigned int v);
     void attach(Projector& P);  // hook the projector's gather to an all-reduce
 

@@ -67,6 +67,7 @@ struct shm3d_ctx {
     int sm_count = 148;
     PVec Y[1];  // component-major: 3 padded components stored back to back
     DevBuf<float> Ybuf;
+    DevBuf<float> Ystage;  // slab contexts: Steps 1-2 of the cyclically assigned z-chunks, before they move to their owners
     PVec vx, vr, vp, vp2, vq;
     double* h_rho = nullptr;  // pinned ring of the PCG's rho values (lagged convergence check)
     DevBuf<float> d_pinv;
@@ -424,7 +425,10 @@ struct Solver {
     std::vector<double> h_pos, h_nrm, h_area;  // host copies when inputs are device-resident
     const double *pos = nullptr, *nrm = nullptr, *area = nullptr;
 
-    void prepare_sources(int64_t M_, const double* pos_, const double* nrm_, const double* area_, bool on_device) {
+    // inside_grid: the caller goes on to the shift / the constraints, which interpolate phi at the sources (Steps 1-2 alone
+    // -- shm3d_step12 -- accept sources anywhere)
+    void prepare_sources(int64_t M_, const double* pos_, const double* nrm_, const double* area_, bool on_device,
+                         bool inside_grid = true) {
         M = M_;
         if (M <= 0 || !pos_ || !area_) throw Error(SHM3D_ERR_INVALID_ARG, "no sources");
         double t0 = now_ms();
@@ -454,7 +458,7 @@ struct Solver {
         }
         // every source must lie inside the node lattice: the shift (k_source_average) and the constraint rows index the
         // eight corner nodes of its cell (the reference's own evaluateFunction / trilinearCoefficients, :405-464, assume it)
-        for (int64_t i = 0; i < M; i++)
+        for (int64_t i = 0; inside_grid && i < M; i++)
             for (int a = 0; a < 3; a++) {
                 const int na = a == 0 ? G.nx : (a == 1 ? G.ny : G.nz);
                 const double t = (pos[3 * i + a] - G.bmin[a]) / G.cell;
@@ -537,8 +541,12 @@ struct Solver {
         SHM3D_CUDA_CHECK(cudaMemsetAsync(c->Ybuf.p, 0, 3 * ycomp() * sizeof(float), s));
         pending_sum_timer.reset(new Timer(s));
         pending_sum_timer->start();
-        // Y is written component-major with the padded component stride
-        launch_heat_sum(P, c->d_cbounds.p, c->d_crange.p, c->d_spos.p, c->d_swn.p, Ycomp(0), ycomp(), c->counters.p, s);
+        if (cyclic_step12()) {
+            run_step12_cyclic(P);
+        } else {
+            // Y is written component-major with the padded component stride
+            launch_heat_sum(P, c->d_cbounds.p, c->d_crange.p, c->d_spos.p, c->d_swn.p, Ycomp(0), ycomp(), c->counters.p, s);
+        }
         if (!coincident.empty()) {
             c->d_coinc.upload(coincident, s);
             k_poison_nodes<<<(unsigned)((coincident.size() + 127) / 128), 128, 0, s>>>(
@@ -549,6 +557,49 @@ struct Solver {
         st.pairs_bruteforce = (int64_t)L0.n() * M;
     }
     std::unique_ptr<Timer> pending_sum_timer;
+
+    // Slab-parallel Steps 1-2, load-balanced.  The cost of a node is the number of source clusters it cannot cull, and that
+    // depends on where the node sits: at 1024^3 / 8 GPUs the outer slabs take 532 ms, the inner ones 407 (max / mean 1.14,
+    // profiles/experiments/r02_ksum_slab_balance.jsonl), and the solve waits for the slowest.  So the summation is done on
+    // z-chunks of kChunk planes (one tile layer of k_sum) dealt round-robin to the ranks -- every rank samples the whole
+    // z range -- into a staging buffer, and one grouped round of ncclSend/ncclRecv then moves each chunk to the slab that
+    // owns it (12 B/node over NVLink: ~1.4 GB per rank at 1024^3 / 8, a few ms against the ~65 ms the imbalance cost).
+    static constexpr int kChunk = 8;
+    bool cyclic_step12() const {
+        return c->dist && c->world > 1 && !(p->flags & SHM3D_FLAG_NO_CYCLIC_SUM) && G.nz % (kChunk * c->world) == 0;
+    }
+    void run_step12_cyclic(SumParams P) {
+        const int W = c->world, me = c->rank;
+        const int n_chunks = G.nz / kChunk, per_slab = n_chunks / W;  // (slabs are uniform and chunk-aligned here)
+        const size_t pl = L0.plane(), chunk_comp = (size_t)kChunk * pl, chunk_all = 3 * chunk_comp;
+        std::vector<int> mine;
+        for (int ch = me; ch < n_chunks; ch += W) mine.push_back(ch);
+        c->Ystage.alloc(std::max<size_t>(1, mine.size()) * chunk_all);
+        for (size_t j = 0; j < mine.size(); j++) {
+            P.k0 = mine[j] * kChunk;
+            P.k1 = P.k0 + kChunk;
+            launch_heat_sum(P, c->d_cbounds.p, c->d_crange.p, c->d_spos.p, c->d_swn.p, c->Ystage.p + j * chunk_all, chunk_comp,
+                            c->counters.p, s);
+        }
+        std::vector<Dist::P2P> sends, recvs;
+        for (size_t j = 0; j < mine.size(); j++) {
+            const int owner = mine[j] / per_slab;
+            for (int a = 0; a < 3; a++) {
+                float* src = c->Ystage.p + j * chunk_all + (size_t)a * chunk_comp;
+                if (owner == me)
+                    SHM3D_CUDA_CHECK(cudaMemcpyAsync(Ycomp(a) + (size_t)(mine[j] * kChunk - G.k0) * pl, src,
+                                                     chunk_comp * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                else
+                    sends.push_back({src, chunk_comp, owner});
+            }
+        }
+        for (int ch = me * per_slab; ch < (me + 1) * per_slab; ch++) {
+            const int from = ch % W;
+            if (from == me) continue;
+            for (int a = 0; a < 3; a++) recvs.push_back({Ycomp(a) + (size_t)(ch * kChunk - G.k0) * pl, chunk_comp, from});
+        }
+        c->dist->p2p_round(sends, recvs, s);
+    }
 
     void finish_step12_stats() {
         if (pending_sum_timer) {
@@ -1293,7 +1344,7 @@ int shm3d_step12(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double*
     double t0 = now_ms();
     int64_t l0 = g_kernel_launches;
     Solver S(ctx, p);
-    S.prepare_sources(M, pos, nrm, area, false);
+    S.prepare_sources(M, pos, nrm, area, false, /*inside_grid=*/false);
     S.cluster_and_upload();
     S.run_step12();
     S.finish_step12_stats();

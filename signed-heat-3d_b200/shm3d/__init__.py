@@ -22,6 +22,7 @@ FLAG_FAST, FLAG_SCRUB_NONFINITE, FLAG_VERBOSE, FLAG_NO_MG, FLAG_PLAIN_MG, FLAG_P
 FLAG_NO_TMA = 128         # diagnostics: row-streaming stencil kernels instead of the TMA-staged marching ones
 FLAG_TAIL_PROGRAM = 256     # experiment, off by default: coarsest multigrid levels as one program launch (mg_tail.cuh)
 FLAG_NO_PDL = 1024        # diagnostics: projector sweep kernels without programmatic dependent launch
+FLAG_NO_CYCLIC_SUM = 2048  # diagnostics (slab contexts): no round-robin z-chunks for Steps 1-2
 FLAG_NO_GRAPH = 512       # diagnostics: PCG iterations launched kernel by kernel instead of CUDA-graph replays
 FLAG_FP64_UNDERFLOW = 64  # reproduce the reference's fp64 underflow in X.norm() at far nodes (include/shm3d_grid.h)
 

@@ -12,6 +12,8 @@ sys.path.insert(0, os.path.join(ROOT, "signed-heat-3d_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch  # noqa: E402
 import shm3d  # noqa: E402
+if os.environ.get("SHM3D_LIB_PATH"):  # experiment builds (e.g. -DSHM3D_TUNING_KNOBS)
+    shm3d.LIB_PATH = os.path.abspath(os.environ["SHM3D_LIB_PATH"])
 import bench  # noqa: E402
 
 
@@ -27,6 +29,8 @@ def main():
                 ("+ tail program", shm3d.FLAG_TAIL_PROGRAM), ("no PDL", shm3d.FLAG_NO_PDL),
                 ("none (round-1 launch structure)", shm3d.FLAG_NO_GRAPH | shm3d.FLAG_NO_PDL),
                 ("default + profile", shm3d.FLAG_PROFILE)]
+    if os.environ.get("PCG_PROBE_QUICK"):
+        variants = variants[:1]
     for name, fl in variants:
         best = None
         for _ in range(reps):
