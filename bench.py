@@ -318,7 +318,7 @@ def run_ours(args):
 
     def step_device(flags=0):
         q = shm3d.Params.from_buffer_copy(p)
-        q.flags |= flags
+        q.flags |= flags | args.extra_flags
         return ctx.solve_device(q, d_pos.data_ptr(), d_nrm.data_ptr(), d_area.data_ptr(), d_phi.data_ptr(), M)
 
     # ---- N > 1: the slab-partitioned solve against the single-GPU solve of the same (256^3) problem, before timing
@@ -590,6 +590,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="default: ~512^3 nodes per GPU (sphere512 / 640 / 768 / 1024 at 1 / 2 / 4 / 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--extra-flags", type=int, default=0, help="diagnostics: SHM3D_FLAG_* bits OR-ed into every solve of the "
+                    "device-resident arm (e.g. 2048 = no round-robin z-chunks for Steps 1-2 on slab contexts)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the dist_parity block")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling block")
     args = ap.parse_args()

@@ -67,7 +67,7 @@ struct shm3d_ctx {
     int sm_count = 148;
     PVec Y[1];  // component-major: 3 padded components stored back to back
     DevBuf<float> Ybuf;
-    DevBuf<float> Ystage;  // slab contexts: Steps 1-2 of the cyclically assigned z-chunks, before they move to their owners
+    DevBuf<float> Ystage, Yrecv;  // slab contexts: Steps 1-2 of the round-robin z-chunks, before / after they move to their owners
     PVec vx, vr, vp, vp2, vq;
     double* h_rho = nullptr;  // pinned ring of the PCG's rho values (lagged convergence check)
     DevBuf<float> d_pinv;
@@ -566,39 +566,55 @@ struct Solver {
     // owns it (12 B/node over NVLink: ~1.4 GB per rank at 1024^3 / 8, a few ms against the ~65 ms the imbalance cost).
     static constexpr int kChunk = 8;
     bool cyclic_step12() const {
-        return c->dist && c->world > 1 && !(p->flags & SHM3D_FLAG_NO_CYCLIC_SUM) && G.nz % (kChunk * c->world) == 0;
+        // (2 slabs of a centred object are mirror images: nothing to balance, and half of Y would travel for nothing)
+        return c->dist && c->world > 2 && !(p->flags & SHM3D_FLAG_NO_CYCLIC_SUM) && G.nz % (kChunk * c->world) == 0;
     }
     void run_step12_cyclic(SumParams P) {
         const int W = c->world, me = c->rank;
         const int n_chunks = G.nz / kChunk, per_slab = n_chunks / W;  // (slabs are uniform and chunk-aligned here)
         const size_t pl = L0.plane(), chunk_comp = (size_t)kChunk * pl, chunk_all = 3 * chunk_comp;
-        std::vector<int> mine;
-        for (int ch = me; ch < n_chunks; ch += W) mine.push_back(ch);
-        c->Ystage.alloc(std::max<size_t>(1, mine.size()) * chunk_all);
-        for (size_t j = 0; j < mine.size(); j++) {
-            P.k0 = mine[j] * kChunk;
-            P.k1 = P.k0 + kChunk;
-            launch_heat_sum(P, c->d_cbounds.p, c->d_crange.p, c->d_spos.p, c->d_swn.p, c->Ystage.p + j * chunk_all, chunk_comp,
-                            c->counters.p, s);
+        // my chunks (ch = me, me + W, ...), grouped by the slab that owns them: everything bound for one peer is contiguous in
+        // the staging buffer, so the round is ONE send and ONE receive per peer (a first version with a send per chunk and
+        // component spent ~0.3 ms per operation inside the NCCL group)
+        std::vector<std::vector<int>> to(W), from(W);
+        for (int ch = me; ch < n_chunks; ch += W) to[ch / per_slab].push_back(ch);
+        for (int ch = me * per_slab; ch < (me + 1) * per_slab; ch++) from[ch % W].push_back(ch);
+        size_t n_out = 0, n_in = 0;
+        for (int r = 0; r < W; r++) {
+            n_out += to[r].size();
+            if (r != me) n_in += from[r].size();
         }
+        c->Ystage.alloc(std::max<size_t>(1, n_out) * chunk_all);
+        c->Yrecv.alloc(std::max<size_t>(1, n_in) * chunk_all);
         std::vector<Dist::P2P> sends, recvs;
-        for (size_t j = 0; j < mine.size(); j++) {
-            const int owner = mine[j] / per_slab;
-            for (int a = 0; a < 3; a++) {
-                float* src = c->Ystage.p + j * chunk_all + (size_t)a * chunk_comp;
-                if (owner == me)
-                    SHM3D_CUDA_CHECK(cudaMemcpyAsync(Ycomp(a) + (size_t)(mine[j] * kChunk - G.k0) * pl, src,
-                                                     chunk_comp * sizeof(float), cudaMemcpyDeviceToDevice, s));
-                else
-                    sends.push_back({src, chunk_comp, owner});
+        size_t slot = 0;
+        for (int r = 0; r < W; r++) {
+            if (r != me && !to[r].empty()) sends.push_back({c->Ystage.p + slot * chunk_all, to[r].size() * chunk_all, r});
+            for (int ch : to[r]) {
+                P.k0 = ch * kChunk;
+                P.k1 = P.k0 + kChunk;
+                float* out = c->Ystage.p + slot * chunk_all;
+                launch_heat_sum(P, c->d_cbounds.p, c->d_crange.p, c->d_spos.p, c->d_swn.p, out, chunk_comp, c->counters.p, s);
+                if (r == me)  // my own chunk: straight into place
+                    for (int a = 0; a < 3; a++)
+                        SHM3D_CUDA_CHECK(cudaMemcpyAsync(Ycomp(a) + (size_t)(ch * kChunk - G.k0) * pl, out + (size_t)a * chunk_comp,
+                                                         chunk_comp * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                slot++;
             }
         }
-        for (int ch = me * per_slab; ch < (me + 1) * per_slab; ch++) {
-            const int from = ch % W;
-            if (from == me) continue;
-            for (int a = 0; a < 3; a++) recvs.push_back({Ycomp(a) + (size_t)(ch * kChunk - G.k0) * pl, chunk_comp, from});
+        slot = 0;
+        std::vector<std::pair<int, size_t>> placed;  // (chunk, slot in Yrecv)
+        for (int r = 0; r < W; r++) {
+            if (r == me || from[r].empty()) continue;
+            recvs.push_back({c->Yrecv.p + slot * chunk_all, from[r].size() * chunk_all, r});
+            for (int ch : from[r]) placed.emplace_back(ch, slot++);
         }
         c->dist->p2p_round(sends, recvs, s);
+        for (const auto& pc : placed)
+            for (int a = 0; a < 3; a++)
+                SHM3D_CUDA_CHECK(cudaMemcpyAsync(Ycomp(a) + (size_t)(pc.first * kChunk - G.k0) * pl,
+                                                 c->Yrecv.p + pc.second * chunk_all + (size_t)a * chunk_comp,
+                                                 chunk_comp * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
 
     void finish_step12_stats() {
