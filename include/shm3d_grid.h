@@ -84,7 +84,7 @@ typedef struct shm3d_params {
     uint32_t flags;
     double cull_tau;      /* far-field cut: drop sources with lambda*(r - r_min) > tau.  <=0: default 10.
                              +inf: brute force (every source at every node, like the reference) */
-    double cg_rel_tol;    /* <=0: default 3e-6 (relative preconditioned residual) */
+    double cg_rel_tol;    /* <=0: default 1e-5 (relative preconditioned residual; csrc/solver.cu run_pcg says why) */
     int32_t cg_max_iters; /* <=0: default 2000 */
     int32_t mg_smooth;    /* Jacobi sweeps per multigrid leg; <=0: default 2 */
     int32_t mg_constrained_from; /* first multigrid level (0 = finest) whose smoothers are projected onto that level's
