@@ -202,6 +202,11 @@ int shm3d_debug_tufted_weights(const double* P, int64_t nP, const int64_t* tris,
                                int64_t* n_flips_out, double* min_cotan_out, double* area_before_out);
 /* probe for the tests: the local Delaunay 1-ring of the origin among n tangent-plane points (returns the ring size) */
 int shm3d_debug_local_ring(const double* coords2d, int32_t n, int32_t* ring_out, int32_t* tri_after_out);
+/* test probe (host logic, no GPU): the exchange plan of the load-balanced Steps 1-2 on slab contexts -- the 8-plane z-chunks
+ * rank `rank` computes for slab `peer` (to_out) and the chunks of its own slab that `peer` computes (from_out), in message
+ * order.  Returns -1 when nz is not a multiple of 8 * world (such grids keep slab-local summation). */
+int shm3d_debug_cyclic_plan(int32_t nz, int32_t world, int32_t rank, int32_t peer, int32_t* to_out, int32_t* n_to,
+                            int32_t* from_out, int32_t* n_from);
 /* test probe: which k-nearest-neighbour search shm3d_point_weights uses on the calling process.  0 (default): the
  * restatement of nanoflann's kd-tree (ties among exactly equidistant points in its visiting order, like geometry-central);
  * 1: an independent cell-list search with ties broken by point index -- identical wherever no distances tie, used by the

@@ -565,6 +565,16 @@ struct Solver {
     // z range -- into a staging buffer, and one grouped round of ncclSend/ncclRecv then moves each chunk to the slab that
     // owns it (12 B/node over NVLink: ~1.4 GB per rank at 1024^3 / 8, a few ms against the ~65 ms the imbalance cost).
     static constexpr int kChunk = 8;
+    // who computes what, who owns what: to[r] = the chunks this rank computes that slab r owns, from[r] = the chunks of this
+    // rank's slab that rank r computes -- both in increasing chunk order, which is the order of the data inside the one
+    // message per peer (checked for every rank pair by tests/test_dist.py through shm3d_debug_cyclic_plan)
+    static void cyclic_plan(int nz, int W, int me, std::vector<std::vector<int>>& to, std::vector<std::vector<int>>& from) {
+        const int n_chunks = nz / kChunk, per_slab = n_chunks / W;
+        to.assign(W, {});
+        from.assign(W, {});
+        for (int ch = me; ch < n_chunks; ch += W) to[ch / per_slab].push_back(ch);
+        for (int ch = me * per_slab; ch < (me + 1) * per_slab; ch++) from[ch % W].push_back(ch);
+    }
     bool cyclic_step12() const {
         // (2 slabs of a centred object are mirror images: nothing to balance, and half of Y would travel for nothing)
         return c->dist && c->world > 2 && !(p->flags & SHM3D_FLAG_NO_CYCLIC_SUM) && G.nz % (kChunk * c->world) == 0;
@@ -576,9 +586,8 @@ struct Solver {
         // my chunks (ch = me, me + W, ...), grouped by the slab that owns them: everything bound for one peer is contiguous in
         // the staging buffer, so the round is ONE send and ONE receive per peer (a first version with a send per chunk and
         // component spent ~0.3 ms per operation inside the NCCL group)
-        std::vector<std::vector<int>> to(W), from(W);
-        for (int ch = me; ch < n_chunks; ch += W) to[ch / per_slab].push_back(ch);
-        for (int ch = me * per_slab; ch < (me + 1) * per_slab; ch++) from[ch % W].push_back(ch);
+        std::vector<std::vector<int>> to, from;
+        cyclic_plan(G.nz, W, me, to, from);
         size_t n_out = 0, n_in = 0;
         for (int r = 0; r < W; r++) {
             n_out += to[r].size();
@@ -1443,6 +1452,21 @@ int shm3d_step3(shm3d_ctx* ctx, const shm3d_params* p, int64_t M, const double* 
     S.st.ms_total = now_ms() - t0;
     if (stats) *stats = S.st;
     SHM3D_API_END(ctx)
+}
+
+// the exchange plan of the balanced Steps 1-2 (host logic; tests): chunks rank `rank` sends to / receives from `peer`, in
+// message order.  Returns the two counts through n_to / n_from; -1 when the grid does not qualify (nz % (8 * world) != 0).
+int shm3d_debug_cyclic_plan(int32_t nz, int32_t world, int32_t rank, int32_t peer, int32_t* to_out, int32_t* n_to,
+                            int32_t* from_out, int32_t* n_from) {
+    if (world < 1 || rank < 0 || rank >= world || peer < 0 || peer >= world || nz < 1 || !n_to || !n_from) return SHM3D_ERR_INVALID_ARG;
+    if (nz % (Solver::kChunk * world) != 0) return -1;
+    std::vector<std::vector<int>> to, from;
+    Solver::cyclic_plan(nz, world, rank, to, from);
+    *n_to = (int32_t)to[peer].size();
+    *n_from = (int32_t)from[peer].size();
+    if (to_out) std::copy(to[peer].begin(), to[peer].end(), to_out);
+    if (from_out) std::copy(from[peer].begin(), from[peer].end(), from_out);
+    return SHM3D_OK;
 }
 
 // ---- host-logic probes (no GPU needed): used by the CPU test-suite to check the constraint assembly and the

@@ -71,7 +71,7 @@ EXPORTS = ["shm3d_slab_range", "shm3d_ctx_create", "shm3d_ctx_create_dist", "shm
            "shm3d_last_error", "shm3d_slab", "shm3d_solve", "shm3d_solve_device", "shm3d_step12", "shm3d_rhs",
            "shm3d_step3", "shm3d_prepare_mesh", "shm3d_prepare_points", "shm3d_debug_constraints",
            "shm3d_debug_factor_solve", "shm3d_version", "shm3d_ctx_stream", "shm3d_host_alloc", "shm3d_host_free", "shm3d_step12_points", "shm3d_point_weights",
-           "shm3d_debug_local_ring", "shm3d_debug_tufted_weights", "shm3d_debug_knn_mode", "shm3d_isosurface", "shm3d_isosurface_fetch",
+           "shm3d_debug_local_ring", "shm3d_debug_tufted_weights", "shm3d_debug_knn_mode", "shm3d_debug_cyclic_plan", "shm3d_isosurface", "shm3d_isosurface_fetch",
            "shm3d_isosurface_device", "shm3d_slice", "shm3d_debug_stencil_op"]
 
 _lib = None

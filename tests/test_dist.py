@@ -77,3 +77,42 @@ def test_slab_partitioned_solve_matches_single_gpu():
            "--master-port", "29618", os.path.join(ROOT, "tools", "check_dist.py"), "bunny_small:0", "bunny_small:1", "knot:2", "bunny_small:1:fast"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("nz,world", [(1024, 8), (768, 4), (256, 8), (256, 4), (64, 4), (128, 16), (96, 4)])
+def test_cyclic_step12_plan_is_consistent_between_every_rank_pair(nz, world):
+    """Balanced Steps 1-2 on slab contexts (csrc/solver.cu run_step12_cyclic): what rank a sends to rank b must be exactly what b
+    expects from a, chunk by chunk in the same order (one message per peer: a mismatch is a deadlock or silently permuted
+    planes); every chunk is computed once and lands on the slab that owns it."""
+    import ctypes as C
+    import shm3d
+    L = shm3d.lib()
+    i32p = C.POINTER(C.c_int32)
+    L.shm3d_debug_cyclic_plan.argtypes = [C.c_int32] * 4 + [i32p, i32p, i32p, i32p]
+
+    def plan(rank, peer):
+        to = (C.c_int32 * (nz // 8))()
+        fr = (C.c_int32 * (nz // 8))()
+        nt, nf = C.c_int32(), C.c_int32()
+        rc = L.shm3d_debug_cyclic_plan(nz, world, rank, peer, to, C.byref(nt), fr, C.byref(nf))
+        return rc, list(to[:nt.value]), list(fr[:nf.value])
+
+    if nz % (8 * world):
+        assert plan(0, 0)[0] == -1
+        return
+    seen = []
+    for a in range(world):
+        computed = 0
+        for b in range(world):
+            rc, to_ab, _ = plan(a, b)
+            rc2, _, from_ba = plan(b, a)
+            assert rc == 0 and rc2 == 0
+            assert to_ab == from_ba, (a, b)
+            k0, k1 = shm3d.slab_range(b, world, nz)
+            assert all(k0 <= 8 * ch and 8 * ch + 8 <= k1 for ch in to_ab)      # lands on the owner's slab
+            assert all(ch % world == a for ch in to_ab)                         # round-robin assignment
+            assert to_ab == sorted(to_ab)
+            seen += to_ab
+            computed += len(to_ab)
+        assert computed == nz // 8 // world                                     # equal shares
+    assert sorted(seen) == list(range(nz // 8))                                 # every chunk exactly once
