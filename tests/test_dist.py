@@ -116,3 +116,25 @@ def test_cyclic_step12_plan_is_consistent_between_every_rank_pair(nz, world):
             computed += len(to_ab)
         assert computed == nz // 8 // world                                     # equal shares
     assert sorted(seen) == list(range(nz // 8))                                 # every chunk exactly once
+
+
+def test_bench_reference_arm_line_is_truthful_and_product_free():
+    """`bench.py --impl reference` (rank 0): one JSON line with the contract's keys, the grid it REALLY measured (the 16^3
+    proxy, flagged same_config = false), and no trace of the product library in the process (VERDICT r01 / ADVICE r01)."""
+    import json
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--workload', 'sphere128'];"
+            "runpy.run_path(%r, run_name='__main__');"
+            "maps = open('/proc/self/maps').read(); print('PRODUCT_LOADED' if 'libshm3d_grid' in maps else 'PRODUCT_ABSENT');"
+            "print('SHM3D_IMPORTED' if 'shm3d' in sys.modules else 'SHM3D_NOT_IMPORTED')" % os.path.join(ROOT, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert "PRODUCT_ABSENT" in lines and "SHM3D_NOT_IMPORTED" in lines
+    d = json.loads(next(ln for ln in lines if ln.startswith("{")))
+    assert d["impl"] == "reference" and d["metric"] == "grid_nodes_per_sec_end_to_end" and d["unit"] == "grid-nodes/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert d["config"]["grid"] == [16, 16, 16] and d["same_config"] is False and d["extrapolated"] is True
+        assert "PROXY" in d["config"]["workload"]
