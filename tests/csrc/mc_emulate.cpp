@@ -65,6 +65,54 @@ extern "C" int mc_emulate(const float* field, int nx, int ny, int nz, float isov
         col_x[column_id(L, y, z)] = pack_range(cc.x_lo, cc.x_hi);
     });
     if (count_mismatch) return 6;
+    // ... and over k_mc_count's OWN launch geometry: a warp holds 32 consecutive nodes (z0 .. z0+31; lanes past the last node
+    // re-read it) and owns 31 columns; lane l takes the z+1 half of its nibble from lane l+1 (a shuffle on the device; lane
+    // 31's result is never used).  Every column must get the counts and the cell range found above, exactly once.
+    {
+        const int cols = kLanesZ - 1;
+        const unsigned cgx = (unsigned)((L.SZ - 1 + cols - 1) / cols);
+        std::vector<unsigned> v2(nc, 0xdeadbeefu), t2(nc, 0xdeadbeefu), x2(nc, 0xdeadbeefu);
+        const float niso = -L.isoval;
+        for (unsigned by = 0; by < gy; by++)
+            for (unsigned bx = 0; bx < cgx; bx++)
+                for (unsigned ty = 0; ty < (unsigned)kRowsY; ty++) {
+                    const int y = (int)(by * kRowsY + ty);
+                    if (y >= L.SY - 1) continue;
+                    ColumnCount cc[kLanesZ];
+                    unsigned n_prev[kLanesZ], mine[kLanesZ];
+                    auto plane = [&](int x, unsigned* nib) {
+                        for (int l = 0; l < kLanesZ; l++) {
+                            const int z = (int)(bx * cols) + l, zc = z < L.SZ - 1 ? z : L.SZ - 1;
+                            const float* q = field + (long long)x * L.strideX + (long long)y * L.SZ + zc;
+                            mine[l] = sign_bit(niso, q[0]) | (sign_bit(niso, q[L.SZ]) << 1);
+                        }
+                        for (int l = 0; l < kLanesZ; l++) nib[l] = mine[l] | (mine[l + 1 < kLanesZ ? l + 1 : l] << 2);
+                    };
+                    plane(0, n_prev);
+                    for (int l = 0; l < kLanesZ; l++) cc[l] = ColumnCount{0u, 0u, 0, 0};
+                    for (int x = 0; x < L.SX - 1; x++) {
+                        unsigned n_cur[kLanesZ];
+                        plane(x + 1, n_cur);
+                        for (int l = 0; l < kLanesZ; l++) {
+                            const int z = (int)(bx * cols) + l;
+                            if (!((n_prev[l] | n_cur[l]) == 0u || (n_prev[l] & n_cur[l]) == 15u))
+                                count_cell(cc[l], kTable, case_of_nibbles(n_prev[l], n_cur[l]), x, y, z);
+                            n_prev[l] = n_cur[l];
+                        }
+                    }
+                    for (int l = 0; l < cols; l++) {
+                        const int z = (int)(bx * cols) + l;
+                        if (z >= L.SZ - 1) continue;
+                        const int c = column_id(L, y, z);
+                        if (v2[c] != 0xdeadbeefu) return 7;  // written twice
+                        v2[c] = cc[l].nv;
+                        t2[c] = cc[l].nt;
+                        x2[c] = pack_range(cc[l].x_lo, cc[l].x_hi);
+                    }
+                }
+        for (int c = 0; c < nc; c++)
+            if (v2[c] != col_v[c] || t2[c] != col_t[c] || x2[c] != col_x[c]) return 7;
+    }
     // k_mc_scan_sums: one partial sum per CTA; k_mc_scan_write: offsets of the CTAs before + scan of the CTA's thread sums
     std::vector<unsigned long long> voff(nc + 1, ~0ull), toff(nc + 1, ~0ull), sv(kScanThreads), st(kScanThreads), a(kScanThreads),
         c(kScanThreads), bsum(2 * kScanBlocks, 0ull);
