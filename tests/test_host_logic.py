@@ -157,3 +157,27 @@ def test_no_cpu_fallback():
         shm3d.Context(0)
     assert e.value.code == shm3d.ERR_CUDA
     assert "no CPU fallback" in str(e.value)
+
+
+def test_drop_in_defaults_follow_the_reference_underflow_and_scrub_rules():
+    """the drop-in must return what the reference returns.  The mesh overload scrubs non-finite rhs
+    entries (:72-74) and both overloads evaluate X /= X.norm() in double (:61 / :171) -- so the host half sets
+    SCRUB + FP64_UNDERFLOW for meshes and FP64_UNDERFLOW alone for point clouds, and the adapter, the C++ mirror and the
+    Python mirror do the same by default.  No GPU needed: flags and sources only."""
+    V, F = icosphere(1)
+    p, *_ = shm3d.prepare_mesh(V, F)
+    assert p.flags & shm3d.FLAG_SCRUB_NONFINITE and p.flags & shm3d.FLAG_FP64_UNDERFLOW
+    q = shm3d.prepare_points(V, 0.3)
+    assert q.flags & shm3d.FLAG_FP64_UNDERFLOW and not (q.flags & shm3d.FLAG_SCRUB_NONFINITE)
+    adapter = open(os.path.join(ROOT, "adapter", "signed_heat_grid_solver_b200.cpp")).read()
+    flag_lines = [ln for ln in adapter.splitlines() if "p.flags =" in ln]
+    assert len(flag_lines) == 2 and all("SHM3D_FLAG_FP64_UNDERFLOW" in ln for ln in flag_lines)
+    assert sum("SHM3D_FLAG_SCRUB_NONFINITE" in ln for ln in flag_lines) == 1       # mesh overload only
+    mirror = open(os.path.join(ROOT, "include", "shm3d", "signed_heat_grid_solver.hpp")).read()
+    assert "bool referenceUnderflow = true;" in mirror
+    src = open(os.path.join(ROOT, "signed-heat-3d_b200", "shm3d", "__init__.py")).read()
+    assert "self.reference_underflow = True" in src
+    # every diagnostics flag of the header has its mirror constant with the same value
+    hdr = open(os.path.join(ROOT, "include", "shm3d_grid.h")).read()
+    for name, val in re.findall(r"#define SHM3D_FLAG_([A-Z0-9_]+) (\d+)u", hdr):
+        assert getattr(shm3d, "FLAG_" + name) == int(val), name
